@@ -1,0 +1,15 @@
+"""fibers.jl_b200 -- B200-native voxel-wise diffusion reconstruction behind the Fibers.jl API.
+
+Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C ABI of
+libfibers_cuda.so), the host-side mirror of the reference's function signatures (`recon.py`),
+the MRI / ODF containers those signatures take, and synthetic phantoms.  Import as
+`fibers_jl_b200` (see the loader module at the repo root: the directory name contains a dot).
+"""
+from . import _lib
+from ._lib import FibersCudaError, device_count
+from .mri import MRI
+from .odf import ODF, sphere_362, sphere_642, sphere_724
+from .recon import DTI, GQI, DSI, adc_fit, dti_fit, gqi_rec, dsi_rec
+
+__all__ = ["MRI", "ODF", "sphere_362", "sphere_642", "sphere_724", "DTI", "GQI", "DSI",
+           "adc_fit", "dti_fit", "gqi_rec", "dsi_rec", "FibersCudaError", "device_count"]

@@ -1,0 +1,366 @@
+// DTI / ADC log-linear fit kernels (reference: src/dti.jl:164-213 adc_fit, :243-316 dti_fit_ls,
+// :325-335 dti_maps; eigen-decomposition = StaticArrays.jl closed form, call site :311).
+//
+// One thread per voxel.  The DWI array is frame-major with contiguous voxels, so a warp reads
+// 128 contiguous bytes per volume: fully coalesced, purely HBM-bound (4N + 64 + 1 B / voxel).
+// pinv(A) (7 x N) sits in shared memory and is read with warp-uniform (broadcast) addresses.
+// This translation unit is compiled with -fmad=false so that the eigen-solver follows the
+// reference's unfused fp32 operation order; the dot products use explicit fmaf().
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace fibers {
+
+namespace {
+
+constexpr int DTI_THREADS = 128;
+constexpr int UNROLL = 8;
+
+struct Cross { float x, y, z; };
+__device__ __forceinline__ Cross cross3(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return {a1 * b2 - a2 * b1, a2 * b0 - a0 * b2, a0 * b1 - a1 * b0};
+}
+
+// Closed-form eigen-decomposition of a real symmetric 3x3 matrix; values ascending in w[],
+// k-th eigenvector in (v[0][k], v[1][k], v[2][k]).  Restates StaticArrays.jl
+// `_eig(::Size{(3,3)}, ::RealHermSymComplexHerm)` (mirrored by oracle/fibers_oracle.py:eig3_sym).
+__device__ void eig3_sym(float a11, float a12, float a13, float a22, float a23, float a33,
+                         float w[3], float v[3][3]) {
+    float p1 = a12 * a12 + a13 * a13 + a23 * a23;
+    if (p1 == 0.f) {   // diagonal matrix: sorted diagonal, unit vectors
+        int o0, o1, o2;
+        if (a11 < a22) {
+            if (a22 < a33) { o0 = 0; o1 = 1; o2 = 2; }
+            else if (a33 < a11) { o0 = 2; o1 = 0; o2 = 1; }
+            else { o0 = 0; o1 = 2; o2 = 1; }
+        } else {
+            if (a11 < a33) { o0 = 1; o1 = 0; o2 = 2; }
+            else if (a33 < a22) { o0 = 2; o1 = 1; o2 = 0; }
+            else { o0 = 1; o1 = 2; o2 = 0; }
+        }
+        float d[3] = {a11, a22, a33};
+        int o[3] = {o0, o1, o2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            w[k] = d[o[k]];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) v[r][k] = (r == o[k]) ? 1.f : 0.f;
+        }
+        return;
+    }
+    float q = (a11 + a22 + a33) / 3.f;
+    float d11 = a11 - q, d22 = a22 - q, d33 = a33 - q;
+    float p2 = d11 * d11 + d22 * d22 + d33 * d33 + 2.f * p1;
+    float p = sqrtf(p2 / 6.f);
+    float invp = 1.f / p;
+    float b11 = d11 * invp, b22 = d22 * invp, b33 = d33 * invp;
+    float b12 = a12 * invp, b13 = a13 * invp, b23 = a23 * invp;
+    Cross c = cross3(b12, b22, b23, b13, b23, b33);
+    float r = (b11 * c.x + b12 * c.y + b13 * c.z) / 2.f;
+    const float pif = 3.14159274f;
+    float phi;
+    if (r <= -1.f) phi = pif / 3.f;
+    else if (r >= 1.f) phi = 0.f;
+    else phi = acosf(r) / 3.f;
+    float eig3 = q + 2.f * p * cosf(phi);
+    float eig1 = q + 2.f * p * cosf(phi + (2.f * pif / 3.f));
+    float eig2 = 3.f * q - eig1 - eig3;
+    const bool swap = r > 0.f;
+    float e1 = swap ? eig3 : eig1;
+    float e3 = swap ? eig1 : eig3;
+    // first eigenvector: best-conditioned cross product of two rows of A - e1 I
+    float r1x = a11 - e1, r1y = a12, r1z = a13;
+    float r2x = a12, r2y = a22 - e1, r2z = a23;
+    float r3x = a13, r3y = a23, r3z = a33 - e1;
+    float n1 = r1x * r1x + r1y * r1y + r1z * r1z;
+    float n2 = r2x * r2x + r2y * r2y + r2z * r2z;
+    float n3 = r3x * r3x + r3y * r3y + r3z * r3z;
+    Cross r12 = cross3(r1x, r1y, r1z, r2x, r2y, r2z);
+    Cross r23 = cross3(r2x, r2y, r2z, r3x, r3y, r3z);
+    Cross r31 = cross3(r3x, r3y, r3z, r1x, r1y, r1z);
+    float n12 = r12.x * r12.x + r12.y * r12.y + r12.z * r12.z;
+    float n23 = r23.x * r23.x + r23.y * r23.y + r23.z * r23.z;
+    float n31 = r31.x * r31.x + r31.y * r31.y + r31.z * r31.z;
+    Cross best; float nb;
+    if (n12 * n3 > n23 * n1) {
+        if (n12 * n3 > n31 * n2) { best = r12; nb = n12; } else { best = r31; nb = n31; }
+    } else {
+        if (n23 * n1 > n31 * n2) { best = r23; nb = n23; } else { best = r31; nb = n31; }
+    }
+    float sn = sqrtf(nb);
+    float v1x = best.x / sn, v1y = best.y / sn, v1z = best.z / sn;
+    // orthonormal complement of v1
+    float o1x, o1y, o1z;
+    if (fabsf(v1x) < fabsf(v1y)) {
+        float dn = sqrtf(v1x * v1x + v1z * v1z);
+        o1x = -v1z / dn; o1y = 0.f; o1z = v1x / dn;
+    } else {
+        float dn = sqrtf(v1y * v1y + v1z * v1z);
+        o1x = 0.f; o1y = v1z / dn; o1z = -v1y / dn;
+    }
+    Cross o2 = cross3(v1x, v1y, v1z, o1x, o1y, o1z);
+    // projected 2x2 problem of A - eig2 I on {o1, o2}
+    float ao1x = a11 * o1x + a12 * o1y + a13 * o1z;
+    float ao1y = a12 * o1x + a22 * o1y + a23 * o1z;
+    float ao1z = a13 * o1x + a23 * o1y + a33 * o1z;
+    float ao2x = a11 * o2.x + a12 * o2.y + a13 * o2.z;
+    float ao2y = a12 * o2.x + a22 * o2.y + a23 * o2.z;
+    float ao2z = a13 * o2.x + a23 * o2.y + a33 * o2.z;
+    float c11 = o1x * ao1x + o1y * ao1y + o1z * ao1z - eig2;
+    float c12 = o1x * ao2x + o1y * ao2y + o1z * ao2z;
+    float c22 = o2.x * ao2x + o2.y * ao2y + o2.z * ao2z - eig2;
+    float s11 = c11 * c11, s12 = c12 * c12, s22 = c22 * c22;
+    float v2x, v2y, v2z;
+    float pp1, pp2;
+    bool degen = false;
+    if (s11 >= s22) {
+        if (s11 > 0.f || s12 > 0.f) {
+            if (s11 >= s12) { float t = c12 / c11; pp2 = 1.f / sqrtf(1.f + t * t); pp1 = t * pp2; }
+            else            { float t = c11 / c12; pp1 = 1.f / sqrtf(1.f + t * t); pp2 = t * pp1; }
+        } else { degen = true; pp1 = 1.f; pp2 = 0.f; }
+    } else {
+        if (s22 >= s12) { float t = c12 / c22; pp1 = 1.f / sqrtf(1.f + t * t); pp2 = t * pp1; }
+        else            { float t = c22 / c12; pp2 = 1.f / sqrtf(1.f + t * t); pp1 = t * pp2; }
+    }
+    if (degen) { v2x = o1x; v2y = o1y; v2z = o1z; }
+    else {
+        v2x = pp1 * o1x - pp2 * o2.x; v2y = pp1 * o1y - pp2 * o2.y; v2z = pp1 * o1z - pp2 * o2.z;
+    }
+    Cross v3 = cross3(v1x, v1y, v1z, v2x, v2y, v2z);
+    if (swap) {
+        w[0] = e3; w[1] = eig2; w[2] = e1;
+        v[0][0] = v3.x; v[1][0] = v3.y; v[2][0] = v3.z;
+        v[0][2] = v1x;  v[1][2] = v1y;  v[2][2] = v1z;
+    } else {
+        w[0] = e1; w[1] = eig2; w[2] = e3;
+        v[0][0] = v1x;  v[1][0] = v1y;  v[2][0] = v1z;
+        v[0][2] = v3.x; v[1][2] = v3.y; v[2][2] = v3.z;
+    }
+    v[0][1] = v2x; v[1][1] = v2y; v[2][1] = v2z;
+}
+
+struct DtiOut {
+    float* p[10];   // s0, l1, l2, l3, v1, v2, v3, rd, md, fa
+    int64_t pitch;
+    uint8_t* valid;
+};
+
+// s0 = exp(d7), eigen, maps, stores  (src/dti.jl:305-315, :325-335)
+__device__ void dti_finish(const float d[7], int64_t vox, const DtiOut& o) {
+    float s0 = expf(d[6]);
+    float w[3], v[3][3];
+    eig3_sym(d[0], d[1], d[2], d[3], d[4], d[5], w, v);
+    float l1 = w[2], l2 = w[1], l3 = w[0];
+    float rd = l2 + l3;
+    float md = (l1 + rd) / 3.f;
+    rd = rd / 2.f;
+    float a = l1 - md, b = l2 - md, c = l3 - md;
+    float fa = sqrtf((a * a + b * b + c * c) / (l1 * l1 + l2 * l2 + l3 * l3) * 1.5f);
+    o.p[0][vox] = s0; o.p[1][vox] = l1; o.p[2][vox] = l2; o.p[3][vox] = l3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        o.p[4][vox + r * o.pitch] = v[r][2];
+        o.p[5][vox + r * o.pitch] = v[r][1];
+        o.p[6][vox + r * o.pitch] = v[r][0];
+    }
+    o.p[7][vox] = rd; o.p[8][vox] = md; o.p[9][vox] = fa;
+    if (o.valid) o.valid[vox] = 1;
+}
+
+__device__ void dti_zero(int64_t vox, const DtiOut& o) {
+    o.p[0][vox] = 0.f; o.p[1][vox] = 0.f; o.p[2][vox] = 0.f; o.p[3][vox] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        o.p[4][vox + r * o.pitch] = 0.f; o.p[5][vox + r * o.pitch] = 0.f; o.p[6][vox + r * o.pitch] = 0.f;
+    }
+    o.p[7][vox] = 0.f; o.p[8][vox] = 0.f; o.p[9][vox] = 0.f;
+    if (o.valid) o.valid[vox] = 0;
+}
+
+// NC = 7 (DTI) or 2 (ADC).  Full-sample path; voxels needing the partial path are appended
+// to `list` and handled by fit_partial_kernel.
+template <int NC>
+__global__ void __launch_bounds__(DTI_THREADS)
+fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __restrict__ mask, int64_t nvox,
+                int nvol, const float* __restrict__ pinv, const uint8_t* __restrict__ ib0,
+                DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
+                int* __restrict__ list, int* __restrict__ count) {
+    extern __shared__ float sm[];
+    float* spa = sm;                                    // [NC][nvol]
+    uint8_t* sb0 = (uint8_t*)(spa + (size_t)NC * nvol);  // [nvol]
+    for (int i = threadIdx.x; i < NC * nvol; i += blockDim.x) spa[i] = pinv[i];
+    for (int i = threadIdx.x; i < nvol; i += blockDim.x) sb0[i] = ib0[i];
+    __syncthreads();
+    const int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vox >= nvox) return;
+    bool inside = mask[vox] != 0;
+    float d[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) d[k] = 0.f;
+    int npos = 0;
+    bool b0pos = false;
+    if (inside) {
+        const float* src = dwi + vox;
+        int j = 0;
+        for (; j + UNROLL <= nvol; j += UNROLL) {
+            float s[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) s[u] = __ldg(src + (int64_t)(j + u) * pitch);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                bool pos = s[u] > 0.f;
+                npos += pos;
+                b0pos |= pos && sb0[j + u];
+                float lg = pos ? logf(s[u]) : 0.f;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) d[k] = fmaf(spa[k * nvol + j + u], lg, d[k]);
+            }
+        }
+        for (; j < nvol; ++j) {
+            float s = __ldg(src + (int64_t)j * pitch);
+            bool pos = s > 0.f;
+            npos += pos;
+            b0pos |= pos && sb0[j];
+            float lg = pos ? logf(s) : 0.f;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) d[k] = fmaf(spa[k * nvol + j], lg, d[k]);
+        }
+    }
+    const bool full = inside && npos == nvol;                       // src/dti.jl:294
+    const bool part = inside && !full && npos > 6 && b0pos;         // :297 (ADC keeps the same rule, :206)
+    if (full) {
+        if (NC == 7) dti_finish(d, vox, out);
+        else { adc[vox] = d[0]; adc_s0[vox] = expf(d[1]); }
+    } else {
+        if (NC == 7) dti_zero(vox, out);
+        else { adc[vox] = 0.f; adc_s0[vox] = 0.f; }
+        if (part) { int slot = atomicAdd(count, 1); list[slot] = (int)vox; }
+    }
+}
+
+// Partial-sample path: d = pinv(A[ipos,:]) * log(s[ipos])  (src/dti.jl:298, :207).
+// One thread per listed voxel; pinv through the eigen-decomposition of the NCxNC normal matrix in
+// float64 (cyclic Jacobi) with LAPACK-pinv truncation (sigma <= eps32*min(m,n)*sigma_max dropped).
+template <int NC>
+__global__ void fit_partial_kernel(const float* __restrict__ dwi, int64_t pitch, int nvol,
+                                   const float* __restrict__ design /*[nvol][NC]*/,
+                                   DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
+                                   const int* __restrict__ list, const int* __restrict__ count) {
+  const int total = *count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int64_t vox = list[i];
+    double G[NC][NC], V[NC][NC], rhs[NC];
+    for (int a = 0; a < NC; ++a) { rhs[a] = 0; for (int b = 0; b < NC; ++b) { G[a][b] = 0; V[a][b] = (a == b); } }
+    int npos = 0;
+    for (int j = 0; j < nvol; ++j) {
+        float s = dwi[vox + (int64_t)j * pitch];
+        if (!(s > 0.f)) continue;
+        ++npos;
+        double lg = (double)logf(s);
+        double row[NC];
+        for (int a = 0; a < NC; ++a) row[a] = (double)design[j * NC + a];
+        for (int a = 0; a < NC; ++a) {
+            rhs[a] += row[a] * lg;
+            for (int b = a; b < NC; ++b) G[a][b] += row[a] * row[b];
+        }
+    }
+    for (int a = 0; a < NC; ++a) for (int b = 0; b < a; ++b) G[a][b] = G[b][a];
+    // cyclic Jacobi: G = V diag(lam) V'
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0, dg = 0;
+        for (int a = 0; a < NC; ++a) { dg += G[a][a] * G[a][a]; for (int b = a + 1; b < NC; ++b) off += G[a][b] * G[a][b]; }
+        if (off <= 1e-36 * dg) break;
+        for (int p = 0; p < NC - 1; ++p)
+            for (int q = p + 1; q < NC; ++q) {
+                double apq = G[p][q];
+                if (apq == 0.0) continue;
+                double theta = (G[q][q] - G[p][p]) / (2.0 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < NC; ++k) {
+                    double gkp = G[k][p], gkq = G[k][q];
+                    G[k][p] = c * gkp - s * gkq; G[k][q] = s * gkp + c * gkq;
+                }
+                for (int k = 0; k < NC; ++k) {
+                    double gpk = G[p][k], gqk = G[q][k];
+                    G[p][k] = c * gpk - s * gqk; G[q][k] = s * gpk + c * gqk;
+                }
+                for (int k = 0; k < NC; ++k) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    double lmax = 0;
+    for (int a = 0; a < NC; ++a) lmax = fmax(lmax, G[a][a]);
+    const int mn = npos < NC ? npos : NC;
+    const double rtol = 1.1920929e-7 * mn;
+    float d[NC];
+    for (int a = 0; a < NC; ++a) d[a] = 0.f;
+    double acc[NC];
+    for (int a = 0; a < NC; ++a) acc[a] = 0;
+    for (int k = 0; k < NC; ++k) {
+        double lam = G[k][k];
+        if (!(lam > rtol * rtol * lmax) || lam <= 0) continue;
+        double proj = 0;
+        for (int a = 0; a < NC; ++a) proj += V[a][k] * rhs[a];
+        proj /= lam;
+        for (int a = 0; a < NC; ++a) acc[a] += V[a][k] * proj;
+    }
+    for (int a = 0; a < NC; ++a) d[a] = (float)acc[a];
+    if (NC == 7) dti_finish(d, vox, out);
+    else { adc[vox] = d[0]; adc_s0[vox] = expf(d[1]); }
+  }
+}
+
+int ensure_list(Plan* p, int64_t nvox) {
+    if (p->list_cap >= nvox && p->d_count) return 0;
+    if (p->d_list) cudaFree(p->d_list);
+    p->d_list = nullptr;
+    FB_CUDA(cudaMalloc(&p->d_list, sizeof(int) * (size_t)nvox));
+    if (!p->d_count) FB_CUDA(cudaMalloc(&p->d_count, sizeof(int)));
+    p->list_cap = nvox;
+    return 0;
+}
+
+template <int NC>
+int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_mask, int64_t nvox,
+               DtiOut out, float* adc, float* adc_s0, cudaStream_t st) {
+    if (nvox <= 0) return 0;
+    if (nvox > 0x7FFFFFFFLL) return fail(FIBERS_ERR_ARG, "slab too large (nvox must fit in int32)");
+    int rc = ensure_list(p, nvox);
+    if (rc) return rc;
+    FB_CUDA(cudaMemsetAsync(p->d_count, 0, sizeof(int), st));
+    size_t smem = sizeof(float) * NC * p->nvol + p->nvol;
+    if (smem > 48 * 1024)
+        FB_CUDA(cudaFuncSetAttribute(fit_full_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned blocks = (unsigned)((nvox + DTI_THREADS - 1) / DTI_THREADS);
+    fit_full_kernel<NC><<<blocks, DTI_THREADS, smem, st>>>(d_dwi, dwi_pitch, d_mask, nvox, p->nvol, p->d_pinv,
+                                                           p->d_ib0, out, adc, adc_s0, p->d_list, p->d_count);
+    // The partial path is rare: a fixed 4-CTA-per-SM grid strides over the device-side list
+    // (no host sync needed to learn the count).  64-thread blocks: heavy per-thread state.
+    unsigned pblocks = (unsigned)std::min<int64_t>((nvox + 63) / 64, 148 * 4);
+    fit_partial_kernel<NC><<<pblocks, 64, 0, st>>>(d_dwi, dwi_pitch, p->nvol, p->d_design, out, adc, adc_s0,
+                                                   p->d_list, p->d_count);
+    count_launch(2);
+    FB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int launch_dti(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_mask, int64_t nvox,
+               int64_t out_pitch, float* const outp[10], uint8_t* d_valid, cudaStream_t st) {
+    DtiOut o;
+    for (int i = 0; i < 10; ++i) o.p[i] = outp[i];
+    o.pitch = out_pitch; o.valid = d_valid;
+    return launch_fit<7>(p, d_dwi, dwi_pitch, d_mask, nvox, o, nullptr, nullptr, st);
+}
+
+int launch_adc(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_mask, int64_t nvox,
+               float* d_adc, float* d_s0, cudaStream_t st) {
+    DtiOut o{};
+    return launch_fit<2>(p, d_dwi, dwi_pitch, d_mask, nvox, o, d_adc, d_s0, st);
+}
+
+}  // namespace fibers

@@ -1,0 +1,139 @@
+"""Host-side mirror of the reference's reconstruction API (same names, argument meaning and
+error behaviour), each function one blocking call into libfibers_cuda.so:
+
+    adc_fit(dwi, mask)                                    reference: src/dti.jl:164
+    dti_fit(dwi, mask)                                    reference: src/dti.jl:221
+    gqi_rec(dwi, mask, odf_dirs=sphere_642, sigma=1.25)   reference: src/gqi.jl:109
+    dsi_rec(dwi, mask, odf_dirs=sphere_642, hann_width=32)  reference: src/dsi.jl:171
+
+This is exactly what julia/FibersCUDA.jl does with `ccall`; Python stands in for Julia because
+Julia is not installed in this image.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .mri import MRI
+from .odf import ODF, sphere_642
+
+
+@dataclass
+class DTI:                     # reference: src/dti.jl:11-22 (field order = file-name suffixes)
+    s0: MRI
+    eigval1: MRI
+    eigval2: MRI
+    eigval3: MRI
+    eigvec1: MRI
+    eigvec2: MRI
+    eigvec3: MRI
+    rd: MRI
+    md: MRI
+    fa: MRI
+    valid: np.ndarray | None = None    # extra (test aid): voxels that took a fit branch
+
+
+@dataclass
+class GQI:                     # reference: src/gqi.jl:10-14
+    odf: MRI
+    peak: list
+    qa: list
+    peak_idx: np.ndarray | None = None   # extra (test aid): 0-based vertex index or -1
+
+
+@dataclass
+class DSI:                     # reference: src/dsi.jl:10-15
+    pdf: MRI
+    odf: MRI
+    peak: list
+    qa: list
+    peak_idx: np.ndarray | None = None
+
+
+def _mask_u8(mask: MRI, shape):
+    m = np.asarray(mask.vol)
+    if m.ndim == 4 and m.shape[3] == 1:          # tutorial masks are [nx,ny,nz,1]
+        m = m[..., 0]
+    if tuple(m.shape) != tuple(shape):
+        raise _lib.FibersCudaError(1, f"mask size {m.shape} does not match dwi size {shape}")
+    return np.asfortranarray(m != 0).astype(np.uint8, order="F")
+
+
+def _check_tables(dwi: MRI, need_bvec: bool):
+    if dwi.bval is None or dwi.bval.size == 0:
+        raise RuntimeError("Missing b-value table from input DWI structure")      # src/dti.jl:166-168
+    if need_bvec and (dwi.bvec is None or dwi.bvec.size == 0):
+        raise RuntimeError("Missing gradient table from input DWI structure")     # src/dti.jl:227-229
+    nvol = dwi.vol.shape[3]
+    if dwi.bval.shape[0] != nvol or (need_bvec and dwi.bvec.shape[0] != nvol):
+        raise _lib.FibersCudaError(1, "b-table length does not match the number of volumes")
+
+
+def adc_fit(dwi: MRI, mask: MRI, ngpu: int = 1):
+    """Fit the apparent diffusion coefficient; returns (adc, s0) as MRI structures."""
+    _check_tables(dwi, False)
+    if dwi.vol.dtype != np.float32:
+        raise TypeError("adc_fit requires a Float32 DWI volume (reference method signature, src/dti.jl:197)")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwi.vol.shape
+    m = _mask_u8(mask, (nx, ny, nz))
+    adc, s0 = MRI.like(mask, 1), MRI.like(mask, 1)
+    vol = np.asfortranarray(dwi.vol)
+    _lib.check(L.fibers_adc_fit(_lib.ptr(vol), _lib.ptr(m), nx, ny, nz, nvol, _lib.ptr(dwi.bval),
+                                _lib.ptr(adc.vol), _lib.ptr(s0.vol), ngpu))
+    return adc, s0
+
+
+def dti_fit(dwi: MRI, mask: MRI, ngpu: int = 1) -> DTI:
+    """Fit tensors to DWIs and return a `DTI` structure."""
+    _check_tables(dwi, True)
+    if dwi.vol.dtype != np.float32:
+        raise TypeError("dti_fit requires a Float32 DWI volume (reference method signature, src/dti.jl:286)")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwi.vol.shape
+    m = _mask_u8(mask, (nx, ny, nz))
+    outs = [MRI.like(mask, n) for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)]
+    valid = np.zeros((nx, ny, nz), np.uint8, order="F")
+    vol = np.asfortranarray(dwi.vol)
+    bvec = np.asfortranarray(dwi.bvec, np.float32)
+    _lib.check(L.fibers_dti_fit(_lib.ptr(vol), _lib.ptr(m), nx, ny, nz, nvol, _lib.ptr(dwi.bval), _lib.ptr(bvec),
+                                *[_lib.ptr(o.vol) for o in outs], _lib.ptr(valid), ngpu))
+    return DTI(*outs, valid=valid.astype(bool))
+
+
+def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int):
+    _check_tables(dwi, True)
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwi.vol.shape
+    m = _mask_u8(mask, (nx, ny, nz))
+    vol = np.asfortranarray(dwi.vol)
+    code = _lib.dtype_code(vol.dtype)
+    M = odf_dirs.nvert
+    odf = MRI.like(mask, M)
+    peak = [MRI.like(mask, 3) for _ in range(3)]
+    qa = [MRI.like(mask, 1) for _ in range(3)]
+    idx = np.zeros((nx, ny, nz, 3), np.int16, order="F")
+    bvec = np.asfortranarray(dwi.bvec, np.float32)
+    V = np.asfortranarray(odf_dirs.vertices, np.float32)
+    F = np.asfortranarray(odf_dirs.faces, np.int32)            # Matrix{Integer} -> Matrix{Int32}
+    common = (_lib.ptr(vol), code, _lib.ptr(m), nx, ny, nz, nvol, _lib.ptr(dwi.bval), _lib.ptr(bvec),
+              _lib.ptr(V), V.shape[0], _lib.ptr(F), F.shape[0])
+    tail = (_lib.ptr(odf.vol), *[_lib.ptr(p.vol) for p in peak], *[_lib.ptr(q.vol) for q in qa], _lib.ptr(idx), ngpu)
+    if kind == "gqi":
+        _lib.check(L.fibers_gqi_rec(*common, float(np.float32(param)), *tail))
+        return GQI(odf, peak, qa, idx)
+    pdf = MRI.like(mask, nvol)
+    _lib.check(L.fibers_dsi_rec(*common, int(param), _lib.ptr(pdf.vol), *tail))
+    return DSI(pdf, odf, peak, qa, idx)
+
+
+def gqi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1) -> GQI:
+    """Generalized q-sampling imaging reconstruction; returns a `GQI` structure."""
+    return _recon("gqi", dwi, mask, odf_dirs, sigma, ngpu)
+
+
+def dsi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, hann_width: int = 32, ngpu: int = 1) -> DSI:
+    """Diffusion spectrum imaging reconstruction; returns a `DSI` structure."""
+    return _recon("dsi", dwi, mask, odf_dirs, hann_width, ngpu)

@@ -1,0 +1,177 @@
+/*
+ * libfibers_cuda.so -- C ABI of the B200-native voxel-wise diffusion reconstruction path
+ * (drop-in for the hot loops of lincbrain/Fibers.jl v1.0.0).
+ *
+ * The reference has no FFI layer: its boundary is the exported Julia API
+ *   adc_fit(dwi::MRI, mask::MRI)                       src/dti.jl:164
+ *   dti_fit(dwi::MRI, mask::MRI)                       src/dti.jl:221  (-> dti_fit_ls :243)
+ *   gqi_rec(dwi, mask, odf_dirs=sphere_642, σ=1.25f0)  src/gqi.jl:109
+ *   dsi_rec(dwi, mask, odf_dirs=sphere_642, hann=32)   src/dsi.jl:171
+ * Each host entry point below replaces the `Threads.@threads for iz` voxel nest (and, for
+ * GQI/DSI, the serial odfmax post-pass) of one of those functions with one blocking call;
+ * julia/FibersCUDA.jl shows the `ccall` a maintainer adds.
+ *
+ * Conventions
+ *  - Every array is Julia column-major [nx, ny, nz, nframes]: the voxel index is contiguous,
+ *    the frame (volume / vertex / xyz component) has stride nx*ny*nz  (src/mri.jl:249-255).
+ *  - Host entry points take HOST pointers; the caller owns every buffer; the library only
+ *    borrows them for the duration of the call.  Outputs are fully overwritten (voxels that
+ *    the reference leaves untouched are written as 0, matching its zero-filled MRI ctor).
+ *  - `mask` is uint8, non-zero = inside (Julia side: UInt8.(mask.vol .!= 0)).
+ *  - `faces` is int32, 1-based, [nface, 3] column-major, exactly `odf_dirs.faces`;
+ *    `vertices` is float32 [nvert2, 3] column-major, exactly `odf_dirs.vertices`.
+ *  - `bvec` is float32 [nvol, 3] column-major, `bval` float32 [nvol].
+ *  - Return value: 0 = OK, otherwise a FIBERS_ERR_* code; fibers_cuda_last_error() gives the
+ *    message for the calling thread (Julia wrapper re-raises it with error(msg), matching the
+ *    reference's exception convention, e.g. src/gqi.jl:111-117).
+ *  - There is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *    FIBERS_ERR_NODEV.
+ *  - ngpu: number of GPUs to shard z-slabs over (>=1; clipped to the configured device list).
+ *    No inter-GPU collective is used; the host gathers slabs and reduces the one scalar (odfmax).
+ */
+#ifndef FIBERS_CUDA_H
+#define FIBERS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIBERS_OK          0
+#define FIBERS_ERR_ARG     1   /* bad argument (null pointer, non-positive size, unsupported mesh) */
+#define FIBERS_ERR_TABLE   2   /* missing b-value / gradient table (reference: error(...) src/dti.jl:166-168,223-229) */
+#define FIBERS_ERR_NODEV   3   /* no CUDA device / driver: there is no CPU fallback */
+#define FIBERS_ERR_CUDA    4   /* CUDA runtime error, message has the detail */
+#define FIBERS_ERR_NOMEM   5   /* device or pinned-host allocation failed */
+
+/* dwi element types accepted by gqi_rec / dsi_rec (the reference converts with `.=`,
+ * src/gqi.jl:139; dti_fit / adc_fit are Float32-only like the reference's method signature
+ * src/dti.jl:286). */
+#define FIBERS_F32 0
+#define FIBERS_F64 1
+#define FIBERS_I16 2
+#define FIBERS_U16 3
+#define FIBERS_I32 4
+#define FIBERS_U8  5
+
+/* Reconstruction kernel selection for GQI/DSI (all are CUDA paths). */
+#define FIBERS_KERNEL_AUTO  0   /* tensor-core path when the shape allows it, else SIMT */
+#define FIBERS_KERNEL_SIMT  1   /* fp32 CUDA-core tiled contraction + fused peak epilogue */
+#define FIBERS_KERNEL_TC    2   /* tcgen05 split-fp16 (fp32-accurate) contraction + fused epilogue */
+
+/* ---- library / device management ------------------------------------------------------- */
+int         fibers_cuda_version(void);                 /* 100*major + minor */
+int         fibers_cuda_device_count(void);            /* number of visible CUDA devices (0 if none) */
+const char* fibers_cuda_last_error(void);              /* thread-local, never NULL */
+/* Device ordinals used by the host entry points for shards 0..n-1 (default 0,1,2,...; the env
+ * var FIBERS_CUDA_DEVICES="3,1" is read at first use). */
+int         fibers_cuda_set_devices(const int* devices, int n);
+/* Force a reconstruction kernel for subsequently created plans / host calls (FIBERS_KERNEL_*). */
+int         fibers_cuda_set_kernel(int kernel);
+
+/* ---- host-pointer entry points (what the Julia wrapper ccalls) ------------------------- */
+
+/* dti_fit / dti_fit_ls: src/dti.jl:243-278 voxel nest + :286-316 voxel fit + :325-335 maps.
+ * Outputs s0, eval*, rd, md, fa: [nx,ny,nz]; evec*: [nx,ny,nz,3].  valid (optional, may be
+ * NULL): uint8 [nx,ny,nz], 1 where the voxel took the full or partial fit branch. */
+int fibers_dti_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol,
+                   const float* bval, const float* bvec,
+                   float* s0, float* eval1, float* eval2, float* eval3,
+                   float* evec1, float* evec2, float* evec3,
+                   float* rd, float* md, float* fa, uint8_t* valid, int ngpu);
+
+/* adc_fit: src/dti.jl:164-213. */
+int fibers_adc_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol,
+                   const float* bval, float* adc, float* s0, int ngpu);
+
+/* gqi_rec: src/gqi.jl:109-171 (work set-up :42-82, peaks :180-201, odfmax post-pass :164-168).
+ * odf: [nx,ny,nz,nvert2/2]; peak1..3: [nx,ny,nz,3]; qa1..3: [nx,ny,nz] (already divided by odfmax).
+ * peak_idx (optional, test aid; may be NULL): int16 [nx,ny,nz,3], 0-based vertex index or -1. */
+int fibers_gqi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask,
+                   int nx, int ny, int nz, int nvol,
+                   const float* bval, const float* bvec,
+                   const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma,
+                   float* odf, float* peak1, float* peak2, float* peak3,
+                   float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu);
+
+/* dsi_rec: src/dsi.jl:171-270 (work set-up :59-143).  pdf: [nx,ny,nz,nvol]. */
+int fibers_dsi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask,
+                   int nx, int ny, int nz, int nvol,
+                   const float* bval, const float* bvec,
+                   const float* vertices, int nvert2, const int32_t* faces, int nface, int hann_width,
+                   float* pdf, float* odf, float* peak1, float* peak2, float* peak3,
+                   float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu);
+
+/* ---- device-resident entry points (kernel-only timing, slab pipelines, batch drivers) ---
+ * A plan holds the per-protocol constants on ONE device (reconstruction matrix, neighbour
+ * table, vertex table, pinv of the design matrix): the GPU analogue of GQIwork / DSIwork /
+ * DTIwork (src/gqi.jl:32-82, src/dsi.jl:41-143, src/dti.jl:101-155).
+ * All d_* pointers are device pointers on the plan's device.  Frame f of an array starts at
+ * base + f*pitch (pitch in ELEMENTS, >= nvox): a z-slab of a larger volume is addressed by
+ * offsetting base and keeping the full-volume pitch.  Calls are asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream). */
+typedef struct fibers_plan fibers_plan;
+
+int  fibers_dti_plan_create(fibers_plan** plan, int device, int nvol, const float* bval, const float* bvec);
+int  fibers_adc_plan_create(fibers_plan** plan, int device, int nvol, const float* bval);
+int  fibers_gqi_plan_create(fibers_plan** plan, int device, int nvol, const float* bval, const float* bvec,
+                            const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma);
+int  fibers_dsi_plan_create(fibers_plan** plan, int device, int nvol, const float* bval, const float* bvec,
+                            const float* vertices, int nvert2, const int32_t* faces, int nface, int hann_width);
+void fibers_plan_destroy(fibers_plan* plan);
+/* Introspection for tests: copies the plan's reconstruction matrix (row-major [rows, nvol],
+ * float32) to host.  GQI: rows = nvert (A of src/gqi.jl:69); DSI: rows = nvert + nvol (Mo;Mp);
+ * DTI/ADC: rows = 7 / 2 (pinv(A), src/dti.jl:143,72).  Returns rows, or <0 on error. */
+int  fibers_plan_matrix(const fibers_plan* plan, float* out, int64_t capacity);
+/* Which kernel the plan's recon calls will launch (FIBERS_KERNEL_SIMT or FIBERS_KERNEL_TC). */
+int  fibers_plan_kernel(const fibers_plan* plan);
+
+int fibers_dti_fit_device(fibers_plan* plan, const float* d_dwi, int64_t dwi_pitch,
+                          const uint8_t* d_mask, int64_t nvox, int64_t out_pitch,
+                          float* d_s0, float* d_eval1, float* d_eval2, float* d_eval3,
+                          float* d_evec1, float* d_evec2, float* d_evec3,
+                          float* d_rd, float* d_md, float* d_fa, uint8_t* d_valid, void* stream);
+int fibers_adc_fit_device(fibers_plan* plan, const float* d_dwi, int64_t dwi_pitch,
+                          const uint8_t* d_mask, int64_t nvox, float* d_adc, float* d_s0, void* stream);
+
+/* GQI / DSI on a device-resident slab.  d_pdf is used by DSI plans only (NULL for GQI).
+ * d_peak_idx may be NULL.  d_stats: 2 x int32 device scratch owned by the caller:
+ *   [0] = max over the slab's voxels of mean_v(odf), as an order-preserving int encoding
+ *   [1] = reserved.
+ * If `finalize` != 0 the call zero-initialises d_stats, runs the slab and divides the three QA
+ * planes by the slab's own odfmax on the same stream (single-slab use, src/gqi.jl:164-168).
+ * If `finalize` == 0 the caller initialises d_stats once with fibers_stats_init_device, may
+ * run several slabs into it, and then calls fibers_qa_scale_device. */
+int fibers_recon_device(fibers_plan* plan, const float* d_dwi, int64_t dwi_pitch,
+                        const uint8_t* d_mask, int64_t nvox, int64_t out_pitch,
+                        float* d_pdf, float* d_odf,
+                        float* d_peak1, float* d_peak2, float* d_peak3,
+                        float* d_qa1, float* d_qa2, float* d_qa3,
+                        int16_t* d_peak_idx, int32_t* d_stats, int finalize, void* stream);
+int fibers_stats_init_device(int32_t* d_stats, void* stream);
+/* qa_k[v] /= odfmax for v < nvox.  If d_stats != NULL the divisor is decoded from d_stats[0]
+ * on the device (no host sync) and `odfmax` is ignored. */
+int fibers_qa_scale_device(float* d_qa1, float* d_qa2, float* d_qa3, int64_t nvox,
+                           const int32_t* d_stats, float odfmax, void* stream);
+/* Decode helper for hosts that combine several slabs: order-preserving int -> float. */
+float fibers_stats_decode_max(int32_t encoded);
+/* Number of kernel launches the library has issued in this process (all devices). */
+int64_t fibers_cuda_launch_count(void);
+
+/* ---- host-only set-up helpers (no device needed; exercised by the CPU test-suite) -------
+ * fibers_host_build_matrix: kind 1 = DTI pinv [7,nvol], 2 = ADC pinv [2,nvol], 3 = GQI A [M,nvol]
+ * (src/gqi.jl:66-69), 4 = DSI [Mo;Mp] [M+nvol,nvol] with *cvol / *dscale (den = dscale*s+[cvol]).
+ * Writes row-major float32 into out (capacity in elements), returns the row count or <0. */
+int fibers_host_build_matrix(int kind, int nvol, const float* bval, const float* bvec,
+                             const float* vertices, int nvert2, float sigma, int hann_width,
+                             float* out, int64_t capacity, int* cvol, float* dscale);
+/* Folded-mesh neighbour table: out is uint16 [nvert, 8] row-major, 0xFFFF = none. */
+int fibers_host_build_neighbours(const int32_t* faces, int nface, int nvert, uint16_t* out);
+/* z-slab partition used by the host entry points: out[2g], out[2g+1] = voxel range of shard g. */
+int fibers_host_partition_slabs(const uint8_t* mask, int64_t nxny, int nz, int ngpu, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIBERS_CUDA_H */

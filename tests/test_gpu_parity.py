@@ -1,0 +1,196 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libfibers_cuda.so via the host
+mirror of the reference API), against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import fibers_oracle as O
+import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fibers_jl_b200 as F
+    assert F.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return F
+
+
+def _mri(F, ph):
+    return F.MRI(ph["dwi"], ph["bval"], ph["bvec"]), F.MRI(ph["mask"])
+
+
+# ---------------------------------------------------------------- DTI / ADC
+@pytest.mark.parametrize("shape,ndir,b", [((24, 24, 10), 30, 1000.0), ((20, 16, 8), 64, 2500.0)])
+def test_dti_parity(F, shape, ndir, b):
+    from fibers_jl_b200 import phantom
+    ph = phantom.dti_phantom(shape, ndir=ndir, b=b, seed=11)
+    dwi, mask = _mri(F, ph)
+    got = F.dti_fit(dwi, mask)
+    r32 = O.dti_fit(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], np.float32)
+    r64 = O.dti_fit(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], np.float64)
+    # valid-voxel set: bit exact (pure integer logic on s > 0)
+    assert np.array_equal(got.valid, r32["valid"])
+    assert set(np.unique(r32["kind"])) == {0, 1, 2}, "phantom must exercise full, partial and zero branches"
+    v = P.flat(r32["valid"])
+    full = P.flat(r32["kind"]) == 1
+    # untouched voxels exactly zero
+    for name in ("s0", "eigval1", "rd", "md", "fa"):
+        assert np.all(P.flat(getattr(got, name).vol)[~v] == 0)
+    for name in ("s0", "eigval1", "md", "fa"):
+        assert P.rel_err(getattr(got, name).vol, r64[name], full) < P.SCALAR_TOL, name
+    # lambda2/3, rd: relative to lambda1 scale where nearly degenerate (conditioning-aware)
+    l1 = np.abs(P.flat(r64["eigval1"]))[full]
+    for name in ("eigval2", "eigval3", "rd"):
+        d = np.abs(P.flat(getattr(got, name).vol)[full].astype(np.float64) - P.flat(r64[name])[full]) / l1
+        assert d.max() < P.SCALAR_TOL, name
+    # V1: |dot| >= 0.9999 where lambda1 is separated from lambda2
+    gap = (P.flat(r64["eigval1"]) - P.flat(r64["eigval2"]))[full] / l1
+    dots = np.abs((P.flat(got.eigvec1.vol, 3)[full].astype(np.float64) * P.flat(r64["eigvec1"], 3)[full]).sum(axis=1))
+    sep = gap > 2e-2
+    assert sep.mean() > 0.9
+    assert dots[sep].min() >= P.V1_DOT
+    # eigenvectors orthonormal
+    V = np.stack([P.flat(getattr(got, f"eigvec{k}").vol, 3)[full] for k in (1, 2, 3)], axis=2).astype(np.float64)
+    G = np.einsum("nik,nil->nkl", V, V)
+    assert np.abs(G - np.eye(3)).max() < 1e-4
+    # partial-sample branch (per-voxel pinv): looser conditioning, compare with the float64 oracle
+    part = P.flat(r32["kind"]) == 2
+    assert part.sum() > 0
+    assert P.rel_err(got.md.vol, r64["md"], part) < 1e-3
+    assert P.rel_err(got.fa.vol, r64["fa"], part) < 1e-3
+
+
+def test_adc_parity(F):
+    from fibers_jl_b200 import phantom
+    ph = phantom.dti_phantom((20, 20, 8), ndir=30, seed=5)
+    dwi, mask = _mri(F, ph)
+    adc, s0 = F.adc_fit(dwi, mask)
+    a64, s64 = O.adc_fit(ph["dwi"], ph["mask"], ph["bval"], np.float64)
+    nz = P.flat(a64) != 0
+    assert np.array_equal(P.flat(adc.vol) != 0, nz)
+    assert P.rel_err(adc.vol, a64, nz) < P.SCALAR_TOL
+    assert P.rel_err(s0.vol, s64, nz) < P.SCALAR_TOL
+
+
+def test_dti_noise_free_kat(F):
+    """Known answer: noise-free single tensor -> exact eigenvalues / V1."""
+    from fibers_jl_b200 import phantom
+    ph = phantom.dti_phantom((16, 16, 8), snr=0, inject=False, seed=3)
+    ph["mask"][:] = 1
+    dwi, mask = _mri(F, ph)
+    got = F.dti_fit(dwi, mask)
+    assert np.abs(P.flat(got.eigval1.vol) - ph["l1"]).max() / 1e-3 < 2e-4
+    dots = np.abs((P.flat(got.eigvec1.vol, 3) * ph["e1"]).sum(axis=1))
+    assert dots.min() > 0.9999
+    l = np.stack([ph["l1"], ph["l2"], ph["l3"]], 1); md = l.mean(1)
+    fa = np.sqrt(1.5 * ((l - md[:, None]) ** 2).sum(1) / (l ** 2).sum(1))
+    assert np.abs(P.flat(got.fa.vol) - fa).max() < 2e-4
+
+
+# ---------------------------------------------------------------- GQI
+def _check_recon(got, r32, r64, vertices, faces, M, what):
+    nbr = O.neighbour_table(O.fold_faces(faces, M), M)
+    assert P.odf_rel_err(got.odf.vol, r64["odf"]) < P.ODF_TOL, what
+    nbad, nun = P.peak_mismatch_report(got.peak_idx, r64, nbr)
+    nvox = r64["computed"].size
+    assert nun == 0, f"{what}: {nun} unexplained peak mismatches ({nbad} total of {nvox})"
+    assert nbad <= max(2, 2e-3 * nvox), f"{what}: too many tie-explained mismatches: {nbad}"
+    # peak vectors are verbatim vertex rows of the reported indices
+    idx = P.flat(got.peak_idx, 3)
+    for k in range(3):
+        pk = P.flat(got.peak[k].vol, 3)
+        ok = idx[:, k] >= 0
+        assert np.array_equal(pk[ok], vertices[idx[ok, k]])
+        assert np.all(pk[~ok] == 0)
+    # QA: where indices agree, within 1e-4 of the voxel's max ODF / odfmax
+    same = (idx == P.flat(r64["peak_idx"], 3)).all(axis=1)
+    scale = np.abs(P.flat(r64["odf"], M)).max(axis=1) / float(r64["odfmax"])
+    for k in range(3):
+        d = np.abs(P.flat(got.qa[k].vol).astype(np.float64) - P.flat(r64["qa"][k]))[same]
+        assert np.all(d <= 2 * P.ODF_TOL * scale[same] + 1e-12), what
+    return nbad
+
+
+@pytest.mark.parametrize("nsphere", [642, 362, 724])
+def test_gqi_parity(F, nsphere):
+    from fibers_jl_b200 import phantom
+    v, f = O.load_sphere(nsphere)
+    odf_dirs = F.ODF(v, f)
+    ph = phantom.gqi_phantom((24, 20, 12) if nsphere == 642 else (12, 10, 6), seed=2, mask_fill=0.6)
+    dwi, mask = _mri(F, ph)
+    got = F.gqi_rec(dwi, mask, odf_dirs)
+    r32 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float32)
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    _check_recon(got, r32, r64, v, f, v.shape[0] // 2, f"gqi sphere_{nsphere}")
+    assert (~r64["computed"]).sum() > 0, "phantom must contain skipped voxels"
+
+
+def test_gqi_int16_input_and_sigma(F, sphere642):
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.gqi_phantom((10, 8, 6), seed=9)
+    ph["dwi"] = np.asfortranarray(np.round(ph["dwi"]).astype(np.int16))
+    dwi, mask = _mri(F, ph)
+    got = F.gqi_rec(dwi, mask, F.sphere_642, 1.0)
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.0, np.float64)
+    _check_recon(got, None, r64, v, f, 321, "gqi int16")
+
+
+def test_gqi_multichunk_pipeline(F, sphere642):
+    """> 2^18 voxels: exercises the slab pipeline (several chunks, stream ring) and odfmax reduce."""
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.gqi_phantom((80, 80, 48), nb0=1, shells=((1500.0, 20),), seed=4, mask_fill=0.5)
+    dwi, mask = _mri(F, ph)
+    got = F.gqi_rec(dwi, mask, F.sphere_642)
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    _check_recon(got, None, r64, v, f, 321, "gqi multichunk")
+
+
+def test_gqi_edge_cases(F, sphere642):
+    v, f = sphere642
+    from fibers_jl_b200 import phantom
+    bval, bvec = phantom.shells_table(1, [(2000.0, 15)])
+    # all-zero mask, all-non-positive data, single voxel, ragged (non multiple of 64) sizes
+    for shape in [(1, 1, 1), (5, 3, 2), (7, 9, 3)]:
+        rng = np.random.default_rng(0)
+        dwi = np.asfortranarray(rng.uniform(10, 100, shape + (16,)).astype(np.float32))
+        mask = np.ones(shape, np.uint8, order="F")
+        if shape != (1, 1, 1):
+            mask[0, 0, 0] = 0
+            dwi[-1, -1, -1, :] = -1
+        got = F.gqi_rec(F.MRI(dwi, bval, bvec), F.MRI(mask))
+        r64 = O.gqi_rec(dwi, mask, bval, bvec, v, f, 1.25, np.float64)
+        _check_recon(got, None, r64, v, f, 321, f"gqi edge {shape}")
+    # nothing computed: odfmax = 0 -> QA = 0/0 = NaN in the reference; ODF and peaks stay 0
+    dwi = np.zeros((4, 4, 2, 16), np.float32, order="F")
+    got = F.gqi_rec(F.MRI(dwi, bval, bvec), F.MRI(np.ones((4, 4, 2), np.uint8)))
+    assert np.all(got.odf.vol == 0) and np.all(got.peak_idx == -1)
+    assert np.all(np.isnan(got.qa[0].vol))
+
+
+def test_missing_tables_raise(F):
+    dwi = F.MRI(np.zeros((2, 2, 2, 4), np.float32))
+    with pytest.raises(RuntimeError, match="Missing b-value table"):
+        F.gqi_rec(dwi, F.MRI(np.ones((2, 2, 2), np.uint8)))
+    dwi = F.MRI(np.zeros((2, 2, 2, 4), np.float32), bval=np.ones(4, np.float32))
+    with pytest.raises(RuntimeError, match="Missing gradient table"):
+        F.dti_fit(dwi, F.MRI(np.ones((2, 2, 2), np.uint8)))
+
+
+# ---------------------------------------------------------------- DSI
+def test_dsi_parity(F, sphere642):
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.dsi_phantom((12, 10, 6), seed=3, mask_fill=0.7)
+    dwi, mask = _mri(F, ph)
+    got = F.dsi_rec(dwi, mask)
+    r64 = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 32, np.float64)
+    _check_recon(got, None, r64, v, f, 321, "dsi")
+    assert P.odf_rel_err(got.pdf.vol, r64["pdf"]) < P.ODF_TOL
+    # hann_width = 0 (no window)
+    got0 = F.dsi_rec(dwi, mask, F.sphere_642, 0)
+    r0 = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 0, np.float64)
+    _check_recon(got0, None, r0, v, f, 321, "dsi hann0")
+    assert P.odf_rel_err(got0.pdf.vol, r0["pdf"]) < P.ODF_TOL
