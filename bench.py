@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Fibers.jl reconstruction path.
+
+Metric (BASELINE.json): voxels/s of GQI ODF reconstruction + peak extraction on the synthetic
+HCP-shaped volume 145 x 174 x 145 x 288 (18 b0 + 90 x b=1000/2000/3000), mask == 1, sphere_642.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape nx,ny,nz]
+
+One process per GPU (torchrun for N > 1).  The path shards by voxel/z-slab with NO collective, so
+N ranks each reconstruct one HCP-shaped subject (weak scaling, cfg4-style batch); torch.distributed
+is used only for the barrier and the max-over-ranks of the timed region.
+
+  value     : device-resident throughput (inputs already in HBM), K steps, CUDA events, max over ranks
+  e2e       : same metric through the host-pointer C-ABI call fibers_gqi_rec (what Julia ccalls):
+              pinned HOST buffers in, HOST buffers out, H2D + D2H inside the timed region
+  roofline  : dominant kernel (fused GQI contraction + peak epilogue) against the measured HBM peak
+  cpu_baseline / --impl reference : the C/OpenMP port of the reference voxel loop (oracle/), all host
+              cores, on a bounded z-sub-slab of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+HCP_SHAPE = (145, 174, 145)
+NB0, SHELLS = 18, ((1000.0, 90), (2000.0, 90), (3000.0, 90))
+M_VERT = 321
+
+
+def algorithmic_bytes_per_voxel(nvol, nvert):      # 4N + 4M + 36 + 12 + 1
+    return 4 * nvol + 4 * nvert + 36 + 12 + 1
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic HCP-shaped data, generated on the device (same signal model as phantom.gqi_phantom)
+# ----------------------------------------------------------------------------------------------
+def make_tables():
+    from fibers_jl_b200 import phantom
+    return phantom.shells_table(NB0, list(SHELLS))
+
+
+def synth_dwi_device(torch, nvox, bval, bvec, seed, device, snr=30.0, chunk=1 << 19):
+    """[nvol, nvox] float32 on `device`: two fibres + isotropic compartment, Rician noise, ~0.1 % negatives."""
+    g = torch.Generator(device=device); g.manual_seed(seed)
+    b = torch.tensor(bval, device=device, dtype=torch.float32)[:, None]
+    G = torch.tensor(bvec, device=device, dtype=torch.float32)
+    nvol = b.shape[0]
+    out = torch.empty((nvol, nvox), device=device, dtype=torch.float32)
+    for c0 in range(0, nvox, chunk):
+        n = min(chunk, nvox - c0)
+        def dirs():
+            v = torch.randn((3, n), generator=g, device=device)
+            return v / v.norm(dim=0, keepdim=True)
+        e1, e2 = dirs(), dirs()
+        f1 = (0.3 + 0.4 * torch.rand((1, n), generator=g, device=device)) * 0.9
+        f2 = 0.9 - f1
+        S0 = 500 + 1000 * torch.rand((1, n), generator=g, device=device)
+        sig = S0 / snr
+        s = (f1 * torch.exp(-b * (2.0e-4 + 1.5e-3 * (G @ e1) ** 2)) + f2 * torch.exp(-b * (2.0e-4 + 1.5e-3 * (G @ e2) ** 2))
+             + 0.1 * torch.exp(-b * 3.0e-3)) * S0
+        s = torch.sqrt((s + sig * torch.randn((nvol, n), generator=g, device=device)) ** 2
+                       + (sig * torch.randn((nvol, n), generator=g, device=device)) ** 2)
+        neg = torch.rand((nvol, n), generator=g, device=device) < 1e-3
+        s = torch.where(neg, -0.1 * s, s)
+        out[:, c0:c0 + n] = s
+        del s, neg, e1, e2
+    return out
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: C/OpenMP port of the reference voxel loop on a bounded sub-slab
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(shape, bval, bvec, nz_sample, seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from fibers_jl_b200 import phantom
+    rng = np.random.default_rng(seed)
+    nx, ny, _ = shape
+    nv = nx * ny * nz_sample
+    S, *_ = phantom.multifibre_signal(rng, nv, bval, bvec, 30.0, lpar=1.7e-3, lperp=2.0e-4)
+    dwi = np.asfortranarray(S.astype(np.float32).reshape((nx, ny, nz_sample, bval.shape[0]), order="F"))
+    mask = np.ones((nx, ny, nz_sample), np.uint8, order="F")
+    return dwi, mask
+
+
+def run_cpu_reference(shape, steps, warmup, nz_sample=None, budget_s=12.0):
+    """Times oracle/fibers_oracle.c (gqi voxel loop + peaks + odfmax post-pass) with all host threads.
+    Returns (voxels_per_s, ms_per_step, cores, sample_description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as CO
+    import fibers_oracle as O
+    bval, bvec = make_tables()
+    v, f = O.load_sphere(642)
+    cores = CO.max_threads()
+    setup = CO.GqiSetup(bval, bvec, v, f, 1.25)
+    nx, ny, nz = shape
+    if nz_sample is None:
+        # calibrate on one slice, then size the sample for ~budget_s of CPU work in total
+        dwi, mask = cpu_sample(shape, bval, bvec, 1, 7)
+        outs = CO._recon_outputs(nx, ny, 1, 321)
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
+        t = time.perf_counter(); CO.gqi_rec(dwi, mask, setup=setup, outputs=outs); dt = time.perf_counter() - t
+        nz_sample = int(max(cores, min(nz, budget_s / max(dt, 1e-6) / max(1, steps + warmup))))
+        nz_sample = max(cores, nz_sample // cores * cores)      # static z partition: keep threads balanced
+    dwi, mask = cpu_sample(shape, bval, bvec, nz_sample, 11)
+    outs = CO._recon_outputs(nx, ny, nz_sample, 321)
+    for _ in range(warmup):
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for o in (outs[0], *outs[1], *outs[2]):
+            o.fill(0)                                   # the reference allocates zero-filled outputs per call
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
+    dt = (time.perf_counter() - t0) / steps
+    nv = nx * ny * nz_sample
+    return nv / dt, dt * 1e3, cores, f"z-sub-slab {nx}x{ny}x{nz_sample} of {nx}x{ny}x{nz} ({nv} voxels/step), C/OpenMP port of the reference loop, {cores} threads"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default=",".join(map(str, HCP_SHAPE)))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    shape = tuple(int(x) for x in args.shape.split(","))
+    nvox = int(np.prod(shape))
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+    bval, bvec = make_tables()
+    nvol = bval.shape[0]
+    workload = f"cfg2 GQI recon+peaks {shape[0]}x{shape[1]}x{shape[2]}x{nvol} (18 b0 + 90x b=1000/2000/3000), sphere_642, mask==1"
+    config = {"workload": workload, "per_gpu": "one HCP-shaped subject per GPU (weak; cfg4-style batch)",
+              "l2_policy": "inputs (4.2 GB/step) larger than L2 (126 MB); no explicit flush", "sigma": 1.25}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        vps, ms, cores, sample = run_cpu_reference(shape, steps, max(warmup, 1))
+        line = {"impl": "reference", "metric": "voxels/sec (GQI recon+peaks)", "value": vps, "unit": "voxels/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "Fibers.jl is pure Julia and Julia is not installed: this is the C/OpenMP restatement of its voxel loop, not Fibers.jl itself"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import fibers_jl_b200 as F
+    from fibers_jl_b200 import device as D
+    if not torch.cuda.is_available() or F.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libfibers_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    D.set_kernel(args.kernel)
+    D.set_devices([local_rank])
+
+    dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000 + rank, dev)
+    mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
+    odf = torch.empty((M_VERT, nvox), dtype=torch.float32, device=dev)
+    peak = [torch.empty((3, nvox), dtype=torch.float32, device=dev) for _ in range(3)]
+    qa = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
+    stats = torch.zeros(2, dtype=torch.int32, device=dev)
+    plan = D.Plan("gqi", local_rank, bval, bvec, F.sphere_642, 1.25)
+    stream = torch.cuda.current_stream().cuda_stream
+    pk = [p.data_ptr() for p in peak]; qp = [q.data_ptr() for q in qa]
+
+    def step(ev=None):
+        D.stats_init(stats.data_ptr(), stream)
+        if ev: ev[0].record()
+        plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, nvox, odf.data_ptr(), pk, qp, stats.data_ptr(),
+                   finalize=False, stream=stream)
+        if ev: ev[1].record()
+        D.qa_scale(qp, nvox, d_stats=stats.data_ptr(), stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = D.launch_count()
+    barrier()
+    e0.record()
+    for i in range(steps):
+        step(kev[i])
+    e1.record()
+    barrier()
+    launches = D.launch_count() - l0
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / steps
+    value = world * nvox / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-pointer C ABI (what the Julia wrapper ccalls) ----------
+    e2e = None
+    if not args.no_e2e:
+        h_dwi = torch.empty((nvol, nvox), dtype=torch.float32, pin_memory=True)
+        h_dwi.copy_(dwi)
+        torch.cuda.synchronize()
+        del dwi, odf, peak
+        torch.cuda.empty_cache()
+        h_mask = torch.ones(nvox, dtype=torch.uint8, pin_memory=True)
+        h_odf = torch.empty((M_VERT, nvox), dtype=torch.float32, pin_memory=True)
+        h_peak = [torch.empty((3, nvox), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        h_qa = [torch.empty(nvox, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+        L = F._lib.lib()
+        V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces)
+        bv = np.asfortranarray(bvec)
+
+        def e2e_step():
+            F._lib.check(L.fibers_gqi_rec(h_dwi.data_ptr(), 0, h_mask.data_ptr(), shape[0], shape[1], shape[2], nvol,
+                                          F._lib.ptr(bval), F._lib.ptr(bv), F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc),
+                                          Fc.shape[0], 1.25, h_odf.data_ptr(), *[p.data_ptr() for p in h_peak],
+                                          *[q.data_ptr() for q in h_qa], None, 1))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox * (4 * nvol + 1),
+               "d2h_bytes_per_step": nvox * 4 * (M_VERT + 9 + 3), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "api": "fibers_gqi_rec (host pointers, pinned buffers)"}
+
+    if rank == 0:
+        peak_gbs, peak_src = measured_peaks()
+        abytes = algorithmic_bytes_per_voxel(nvol, M_VERT) * nvox
+        achieved = abytes / (kern_ms * 1e-3) / 1e9
+        line = {"metric": "voxels/sec (GQI recon+peaks)", "value": value, "unit": "voxels/s", "n_gpus": world,
+                "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "kernel": plan.kernel, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                             "kernel_ms": kern_ms, "algorithmic_bytes_per_voxel": algorithmic_bytes_per_voxel(nvol, M_VERT),
+                             "algorithmic_tflops": 2.0 * nvol * M_VERT * nvox / (kern_ms * 1e-3) / 1e12}}
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu:
+            vps, ms, cores, sample = run_cpu_reference(shape, 2, 1, budget_s=12.0)
+            line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -34,6 +34,21 @@ static int nthreads_eff(int req) {
 
 int oracle_max_threads(void) { return nthreads_eff(0); }
 
+/* Dot product the way an optimised BLAS sgemv computes it (OpenBLAS behind Julia's mul!,
+ * src/gqi.jl:144, src/dti.jl:296): 16 independent partial sums (vector lanes) with fused
+ * multiply-add, reduced at the end.  Keeps the CPU baseline honest: a strictly sequential scalar
+ * sum would not vectorise and would understate the reference's speed. */
+static inline float dot_blas(const float* __restrict a, const float* __restrict b, int n) {
+    float acc[16] = {0};
+    int j = 0;
+    for (; j + 16 <= n; j += 16)
+        for (int l = 0; l < 16; ++l) acc[l] = __builtin_fmaf(a[j + l], b[j + l], acc[l]);
+    float tail = 0.f;
+    for (; j < n; ++j) tail = __builtin_fmaf(a[j], b[j], tail);
+    for (int w = 8; w > 0; w >>= 1) for (int l = 0; l < w; ++l) acc[l] += acc[l + w];
+    return acc[0] + tail;
+}
+
 /* ---------------------------------------------------------------- 3x3 symmetric eigen (StaticArrays closed form) */
 static void cross3(const float a[3], const float b[3], float c[3]) {
     c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
@@ -166,7 +181,7 @@ int oracle_linfit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz,
                     float d[7] = {0, 0, 0, 0, 0, 0, 0};
                     if (npos == nvol) {
                         for (int j = 0; j < nvol; ++j) lg[j] = logf(s[j]);
-                        for (int k = 0; k < nc; ++k) { float a = 0; const float* row = pA + (int64_t)k * nvol; for (int j = 0; j < nvol; ++j) a += row[j] * lg[j]; d[k] = a; }
+                        for (int k = 0; k < nc; ++k) d[k] = dot_blas(pA + (int64_t)k * nvol, lg, nvol);
                     } else if (npos > 6 && b0pos) {
                         int m = 0;
                         for (int j = 0; j < nvol; ++j) if (s[j] > 0) { for (int k = 0; k < nc; ++k) Asub[m * nc + k] = A[j * nc + k]; lg[m] = logf(s[j]); ++m; }
@@ -256,7 +271,7 @@ int oracle_gqi_rec(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
                     float mx = 0.f;
                     for (int j = 0; j < nvol; ++j) { float v = dwi[vox + (int64_t)j * nvox]; v = v < 0 ? 0 : v; s[j] = v; if (v > mx) mx = v; }
                     if (mx == 0.f) continue;
-                    for (int i = 0; i < M; ++i) { float a = 0; const float* row = A + (int64_t)i * nvol; for (int j = 0; j < nvol; ++j) a += row[j] * s[j]; o[i] = a; }
+                    for (int i = 0; i < M; ++i) o[i] = dot_blas(A + (int64_t)i * nvol, s, nvol);
                     float mn = o[0];
                     for (int i = 0; i < M; ++i) { odf[vox + (int64_t)i * nvox] = o[i]; if (o[i] < mn) mn = o[i]; }
                     int nvalid = find_peaks(o, op, isort, tmp, M, faces, nface);

@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""Generate the committed golden fixtures under tests/golden/ from the float64 oracle.
+
+The reference ships no golden vectors (test/runtests.jl is empty) and cannot be run here (no
+Julia), so these fixtures pin the ORACLE (oracle/fibers_oracle.py, float64 "truth" variant) on
+small seeded phantoms; tests/test_oracle.py re-derives them and tests/test_gpu_golden.py checks
+the CUDA path against them.  Re-run only when the oracle's semantics are deliberately changed:
+    python tools/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import fibers_oracle as O                      # noqa: E402
+from fibers_jl_b200 import phantom             # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    v, f = O.load_sphere(642)
+    # DTI (cfg1-shaped, scaled down): includes partial-sample and zero voxels
+    ph = phantom.dti_phantom((10, 9, 6), seed=101)
+    r = O.dti_fit(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], np.float64)
+    a, s = O.adc_fit(ph["dwi"], ph["mask"], ph["bval"], np.float64)
+    np.savez_compressed(os.path.join(OUT, "dti_small.npz"), dwi=ph["dwi"], mask=ph["mask"], bval=ph["bval"],
+                        bvec=ph["bvec"], adc=a, adc_s0=s,
+                        **{k: r[k] for k in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "rd", "md", "fa", "valid", "kind")})
+    # GQI (cfg2 protocol: 18 b0 + 3 x 90)
+    ph = phantom.gqi_phantom((6, 5, 4), seed=102, mask_fill=0.8)
+    r = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    np.savez_compressed(os.path.join(OUT, "gqi_small.npz"), dwi=ph["dwi"], mask=ph["mask"], bval=ph["bval"],
+                        bvec=ph["bvec"], odf=r["odf"].astype(np.float32), peak_idx=r["peak_idx"],
+                        qa=np.stack(r["qa"]).astype(np.float32), odfmax=np.float64(r["odfmax"]), computed=r["computed"])
+    # DSI (cfg3 protocol: 515-point grid)
+    ph = phantom.dsi_phantom((5, 4, 3), seed=103)
+    r = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 32, np.float64)
+    np.savez_compressed(os.path.join(OUT, "dsi_small.npz"), dwi=ph["dwi"], mask=ph["mask"], bval=ph["bval"],
+                        bvec=ph["bvec"], odf=r["odf"].astype(np.float32), pdf=r["pdf"].astype(np.float32),
+                        peak_idx=r["peak_idx"], qa=np.stack(r["qa"]).astype(np.float32), computed=r["computed"])
+    # find_peaks! known-answer vectors (hand-built edge cases, evaluated with the LITERAL face-based rule)
+    M = 321
+    ff = O.fold_faces(f, M)
+    nbr = O.neighbour_table(ff, M)
+    rng = np.random.default_rng(7)
+    cases = []
+    o = np.full(M, 1.0, np.float32); cases.append(o)                                   # global plateau: no peaks
+    o = np.zeros(M, np.float32); o[10] = 5; cases.append(o)                            # single peak
+    o = np.zeros(M, np.float32); o[10] = 5; o[nbr[10, 0]] = 5; cases.append(o)         # adjacent tie kills both
+    o = -np.ones(M, np.float32); o[7] = -0.5; cases.append(o)                          # negative local max never counts
+    o = np.zeros(M, np.float32); o[[3, 200, 310]] = 2.0; cases.append(o)               # equal non-adjacent peaks: index order
+    o = np.zeros(M, np.float32); o[[5, 100, 150, 250]] = [1, 4, 2, 3]; cases.append(o)  # > 3 peaks: top 3 by value
+    for _ in range(26):
+        cases.append((np.round(rng.normal(size=M) * 3) / 2).astype(np.float32))        # tie-rich, partly negative
+    cases = np.stack(cases)
+    exp = []
+    for o in cases:
+        isort, nvalid = O.find_peaks_literal(o, ff)
+        exp.append([isort[k] if k < min(nvalid, 3) else -1 for k in range(3)] + [nvalid])
+    np.savez_compressed(os.path.join(OUT, "peaks_kat.npz"), odf=cases, expected=np.asarray(exp, np.int32))
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+if __name__ == "__main__":
+    main()
