@@ -31,6 +31,7 @@ struct SimtParams {
     int64_t out_pitch; float* out;      // odf (ODF mode) or pdf (plain mode)
     float* peak[3]; float* qa[3]; int16_t* peak_idx; int32_t* stats;
     const uint16_t* nbr; const float* vert; int M;
+    const int* tile_list; const int* tile_count; int tile_cap;   // list mode (fix-up of selected 64-voxel tiles)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -51,7 +52,7 @@ __device__ __forceinline__ void top3_insert(float val, int idx, float tv[3], int
 }
 
 template <int J, bool ODF>
-__global__ void __launch_bounds__(NT, (J <= 23 ? 2 : 1)) recon_simt_kernel(const SimtParams p) {
+__device__ __forceinline__ void simt_tile(const SimtParams& p, const int64_t tile_x, const int panel_y) {
     constexpr int RP = 16 * J;                       // rows per panel
     extern __shared__ __align__(16) float sm[];
     // pipeline view
@@ -71,8 +72,8 @@ __global__ void __launch_bounds__(NT, (J <= 23 ? 2 : 1)) recon_simt_kernel(const
     const int t = threadIdx.x;
     const int tx = t & 15, ty = t >> 4;
     const int lv = t & (VT - 1), part = t >> 6;      // loader / epilogue mapping
-    const int64_t v0 = (int64_t)blockIdx.x * VT;
-    const int row0 = p.row_base + blockIdx.y * RP;   // first matrix row of this panel
+    const int64_t v0 = tile_x * VT;
+    const int row0 = p.row_base + panel_y * RP;      // first matrix row of this panel
     const int64_t myvox = v0 + lv;
     const bool inside = myvox < p.nvox && p.mask[myvox] != 0;
 
@@ -241,6 +242,16 @@ __global__ void __launch_bounds__(NT, (J <= 23 ? 2 : 1)) recon_simt_kernel(const
 }
 
 template <int J, bool ODF>
+__global__ void __launch_bounds__(NT, (J <= 23 ? 2 : 1)) recon_simt_kernel(const SimtParams p) {
+    if (p.tile_list == nullptr) { simt_tile<J, ODF>(p, blockIdx.x, blockIdx.y); return; }
+    const int n = min(*p.tile_count, p.tile_cap);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        simt_tile<J, ODF>(p, p.tile_list[i], 0);
+        __syncthreads();
+    }
+}
+
+template <int J, bool ODF>
 size_t simt_smem(int M) {
     constexpr int RP = 16 * J;
     size_t pipe = 2 * KC * VT + 2 * KC * RP;
@@ -254,6 +265,7 @@ int launch_one(const SimtParams& sp, int npanels, cudaStream_t st) {
     size_t smem = simt_smem<J, ODF>(sp.M);
     FB_CUDA(cudaFuncSetAttribute(recon_simt_kernel<J, ODF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((sp.nvox + VT - 1) / VT), (unsigned)npanels);
+    if (sp.tile_list) grid = dim3((unsigned)std::min<int64_t>((sp.nvox + VT - 1) / VT, 148 * 2), 1);
     recon_simt_kernel<J, ODF><<<grid, NT, smem, st>>>(sp);
     count_launch(1);
     FB_CUDA(cudaGetLastError());
@@ -277,9 +289,10 @@ __global__ void convert_kernel(const T* __restrict__ src, float* __restrict__ ds
 
 }  // namespace
 
-int launch_recon_simt(Plan* p, const ReconArgs& a, cudaStream_t st) {
+static int launch_recon_simt_impl(Plan* p, const ReconArgs& a, const int* d_list, const int* d_count, cudaStream_t st) {
     if (a.nvox <= 0) return 0;
     SimtParams sp{};
+    sp.tile_list = d_list; sp.tile_count = d_count; sp.tile_cap = (int)std::min<int64_t>(2 * ((a.nvox + VT - 1) / VT), 0x7FFFFFFF);
     sp.dwi = a.dwi; sp.dwi_pitch = a.dwi_pitch; sp.mask = a.mask; sp.nvox = a.nvox;
     sp.K = p->nvol; sp.mt = p->d_mt; sp.rows_pad = p->rows_pad;
     sp.row_base = 0; sp.nrows = p->nvert;
@@ -298,7 +311,7 @@ int launch_recon_simt(Plan* p, const ReconArgs& a, cudaStream_t st) {
     else if (M <= 16 * 32) rc = launch_one<32, true>(sp, 1, st);
     else return fail(FIBERS_ERR_ARG, "ODF tessellations with more than 512 half-sphere vertices are not supported");
     if (rc) return rc;
-    if (p->kind == PLAN_DSI && a.pdf) {
+    if (p->kind == PLAN_DSI && a.pdf && !d_list) {
         // pdf rows: matrix rows M .. M+nvol-1.  Row panels must start on a 16-row boundary of the
         // padded matrix; the plan stores Mp starting at row_pdf = round_up(M, 16).
         SimtParams pp = sp;
@@ -307,6 +320,13 @@ int launch_recon_simt(Plan* p, const ReconArgs& a, cudaStream_t st) {
         rc = launch_one<21, false>(pp, npan, st);
     }
     return rc;
+}
+
+int launch_recon_simt(Plan* p, const ReconArgs& a, cudaStream_t st) { return launch_recon_simt_impl(p, a, nullptr, nullptr, st); }
+
+// Recompute the 64-voxel tiles listed in d_list[0 .. *d_count) (device-side list; GQI ODF mode only).
+int launch_recon_simt_list(Plan* p, const ReconArgs& a, const int* d_list, const int* d_count, cudaStream_t st) {
+    return launch_recon_simt_impl(p, a, d_list, d_count, st);
 }
 
 int launch_stats_init(int32_t* d_stats, cudaStream_t st) {

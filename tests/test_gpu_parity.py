@@ -112,9 +112,30 @@ def _check_recon(got, r32, r64, vertices, faces, M, what):
     return nbad
 
 
-@pytest.mark.parametrize("nsphere", [642, 362, 724])
-def test_gqi_parity(F, nsphere):
+@pytest.fixture(params=["tc", "simt"])
+def kernel(request, F):
+    """Runs the test once per reconstruction kernel (both are CUDA paths behind the same ABI)."""
+    F.device.set_kernel(request.param)
+    yield request.param
+    F.device.set_kernel("auto")
+
+
+def test_auto_selects_tensor_core_kernel(F):
     from fibers_jl_b200 import phantom
+    bval, bvec = phantom.shells_table(18, [(1000.0, 90), (2000.0, 90), (3000.0, 90)])
+    F.device.set_kernel("auto")
+    assert F.device.Plan("gqi", 0, bval, bvec).kernel == "tc"
+    assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_362).kernel == "tc"
+    assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_724).kernel == "simt"     # 362 half-sphere vertices: tile too big
+    bq, gq = phantom.dsi_grid_table()
+    assert F.device.Plan("dsi", 0, bq, gq).kernel == "simt"
+
+
+@pytest.mark.parametrize("nsphere", [642, 362, 724])
+def test_gqi_parity(F, nsphere, kernel):
+    from fibers_jl_b200 import phantom
+    if kernel == "tc" and nsphere == 724:
+        pytest.skip("sphere_724 (M = 362) is served by the SIMT kernel")
     v, f = O.load_sphere(nsphere)
     odf_dirs = F.ODF(v, f)
     ph = phantom.gqi_phantom((24, 20, 12) if nsphere == 642 else (12, 10, 6), seed=2, mask_fill=0.6)
@@ -126,7 +147,7 @@ def test_gqi_parity(F, nsphere):
     assert (~r64["computed"]).sum() > 0, "phantom must contain skipped voxels"
 
 
-def test_gqi_int16_input_and_sigma(F, sphere642):
+def test_gqi_int16_input_and_sigma(F, sphere642, kernel):
     from fibers_jl_b200 import phantom
     v, f = sphere642
     ph = phantom.gqi_phantom((10, 8, 6), seed=9)
@@ -137,7 +158,30 @@ def test_gqi_int16_input_and_sigma(F, sphere642):
     _check_recon(got, None, r64, v, f, 321, "gqi int16")
 
 
-def test_gqi_multichunk_pipeline(F, sphere642):
+def test_gqi_tc_overflow_fixup(F, sphere642):
+    """A few voxels 1000x brighter than the sampled maximum overflow the scaled fp16 operand; the
+    tensor-core kernel must detect them and the SIMT fix-up must restore fp32-accurate results."""
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.gqi_phantom((40, 33, 9), seed=31)          # 11880 voxels; the sample sees runs of 32 every 2048
+    dwi = ph["dwi"]
+    flat = dwi.reshape(-1, dwi.shape[3], order="F")
+    hot = [700, 5000, 9001]                                  # none of them inside a sampled run
+    for h in hot:
+        assert h % 2048 >= 32
+        flat[h] *= 3000.0
+    ph["dwi"] = np.asfortranarray(flat.reshape(dwi.shape, order="F"))
+    F.device.set_kernel("tc")
+    try:
+        got = F.gqi_rec(*_mri(F, ph))
+    finally:
+        F.device.set_kernel("auto")
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    assert np.isfinite(got.odf.vol).all()
+    _check_recon(got, None, r64, v, f, 321, "gqi tc overflow fix-up")
+
+
+def test_gqi_multichunk_pipeline(F, sphere642, kernel):
     """> 2^18 voxels: exercises the slab pipeline (several chunks, stream ring) and odfmax reduce."""
     from fibers_jl_b200 import phantom
     v, f = sphere642
@@ -148,7 +192,7 @@ def test_gqi_multichunk_pipeline(F, sphere642):
     _check_recon(got, None, r64, v, f, 321, "gqi multichunk")
 
 
-def test_gqi_edge_cases(F, sphere642):
+def test_gqi_edge_cases(F, sphere642, kernel):
     v, f = sphere642
     from fibers_jl_b200 import phantom
     bval, bvec = phantom.shells_table(1, [(2000.0, 15)])
