@@ -121,6 +121,13 @@ static int plan_upload_recon(Plan* p, const std::vector<float>& mat, const float
     std::string e = build_neighbours(faces, nface, M, nbr);
     if (!e.empty()) return fail(FIBERS_ERR_ARG, e);
     if ((rc = upload(&p->d_nbr, nbr))) return rc;
+    p->h_nbr = nbr;
+    p->nbr_width = 0;
+    for (int v = 0; v < M; ++v) {
+        int d = 0;
+        while (d < NBR_W && nbr[(size_t)v * NBR_W + d] != NBR_NONE) ++d;
+        p->nbr_width = std::max(p->nbr_width, d);
+    }
     std::vector<float> vert((size_t)M * 3);
     for (int i = 0; i < M; ++i)
         for (int c = 0; c < 3; ++c) vert[(size_t)i * 3 + c] = vertices[(size_t)c * nvert2 + i];   // first half rows

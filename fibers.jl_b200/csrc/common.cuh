@@ -44,12 +44,14 @@ struct Plan {
     int   cvol = -1;
     float dscale = 0.f;
     std::vector<float> h_matrix;   // row-major [rows][nvol] (host copy, for tests / introspection)
+    std::vector<uint16_t> h_nbr;   // host copy of the neighbour table [nvert][NBR_W]
     // device buffers
     float*    d_mt = nullptr;      // transposed, zero padded: [nvol][rows_pad]  (SIMT path operand)
     float*    d_pinv = nullptr;    // DTI/ADC: [rows][nvol]
     float*    d_design = nullptr;  // DTI/ADC: design matrix A [nvol][rows] (partial-sample path)
     uint8_t*  d_ib0 = nullptr;     // DTI/ADC: [nvol]
     uint16_t* d_nbr = nullptr;     // [nvert][NBR_W]
+    int       nbr_width = NBR_W;   // max folded-mesh degree actually present
     float*    d_vert = nullptr;    // first-half vertices [nvert][3] row-major (peak vectors)
     int*      d_list = nullptr;    // DTI partial-path voxel list (grown on demand)
     int64_t   list_cap = 0;

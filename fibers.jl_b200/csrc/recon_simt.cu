@@ -198,9 +198,10 @@ __device__ __forceinline__ void simt_tile(const SimtParams& p, const int64_t til
             sum += val;
             bool cand = val > 0.f;
 #pragma unroll
-            for (int k = 0; k < NBR_W; ++k) {
-                unsigned n = s_nbr[v * NBR_W + k];
-                if (n != NBR_NONE) cand = cand && (val > stage[n * VT + lv]);
+            for (int k = 0; k < NBR_W; ++k) {                       // branch-free: loads are unconditional
+                const unsigned n = s_nbr[v * NBR_W + k];
+                const float x = stage[(n != NBR_NONE ? n : (unsigned)v) * VT + lv];
+                cand = cand & ((n == NBR_NONE) | (val > x));
             }
             if (cand) top3_insert(val, v, tv, ti);
         }

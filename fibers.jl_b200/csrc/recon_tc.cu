@@ -24,6 +24,10 @@
 #include <math_constants.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include <mutex>
 #include "common.cuh"
 
 namespace fibers {
@@ -34,12 +38,18 @@ namespace {
 
 constexpr int TC_THREADS = 576;
 constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = 10;
-constexpr int NSTAGE = 4;            // B ring: K16 chunks
+constexpr int NSTAGE = 2;            // B ring: K32 chunks (two K16 sub-tiles each)
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
 constexpr int VOX_CTA = 128;
 constexpr int EPI_THREADS = 256;
 constexpr float FP16_TARGET = 8192.f;   // the sampled maximum is scaled to <= 8192 (8x headroom to 65504)
+
+// Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * 512) into the staged tile,
+// 8 per vertex (missing neighbours -> the -inf sentinel row M).  The vertex index is warp-uniform,
+// so the offsets arrive through the uniform datapath and each neighbour costs one LDS.128.
+constexpr int TC_MAX_VERT = 385;
+__constant__ uint32_t c_nbr_off[TC_MAX_VERT * NBR_W];
 
 struct TcParams {
     const float* dwi; int64_t dwi_pitch; const uint8_t* mask; int64_t nvox;
@@ -50,12 +60,16 @@ struct TcParams {
     const int* maxbits;          // device: bit pattern of the sampled max(s) (>= 0)
     int* fix_list; int* fix_count; int fix_cap;
     int ntiles;                  // 256-voxel tiles
+    int nbw;                     // max neighbour count of the folded mesh (<= 8)
+    long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
 struct TcState {
     __half* d_split = nullptr;   // [2 ranks][hi Nh rows | lo Nh rows][Kpad]
     CUtensorMap tmap;
-    int Kpad = 0, Npad = 0, N1 = 0, N2 = 0;
+    int Kpad = 0, Npad = 0, N1 = 0, N2 = 0, nbw = 8;
+    unsigned long long uid = 0;              // identifies the neighbour table in the per-device constant-memory cache
+    std::vector<uint32_t> h_nbr_off;         // [M + 1][NBR_W] byte offsets
     size_t smem = 0;
     int* d_scratch = nullptr;    // [0] maxbits, [1] fix_count, [2..] fix list
     int64_t scratch_cap = 0;
@@ -79,15 +93,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // arrive on the barrier at cluster-shared address `addr` (own CTA or the pair's leader)
+// (relaxed: the data these arrivals publish lives in tensor memory and is ordered by tcgen05.wait /
+//  tcgen05.fence, not by the generic-proxy memory model; a release.cluster costs a full MEMBAR)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+// kBackoff: non-critical waiters sleep between polls so that they do not steal issue slots
+template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (kBackoff && !ok) __nanosleep(64);
         if (spin > (1u << 26)) __trap();        // never hang the GPU: a lost signal becomes a launch error
     }
 }
@@ -124,6 +143,9 @@ __device__ __forceinline__ uint64_t make_sdesc_sw32(uint32_t saddr) {          /
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
 
+#define TRACE(slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] = clock64(); } while (0)
+#define TRACE_ADD(slot, dt) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] += (dt); } while (0)
+
 __device__ __forceinline__ void top3_insert(float val, int idx, float tv[3], int ti[3]) {
     if (val > tv[2]) {
         if (val > tv[1]) {
@@ -159,6 +181,12 @@ __global__ void sample_max_kernel(const float* __restrict__ dwi, int64_t pitch, 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {          // one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -166,19 +194,24 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     const uint32_t rank = cluster_rank();
     const int cluster_id = blockIdx.x >> 1, ncluster = gridDim.x >> 1;
     const int Nh = (p.N1 + p.N2) >> 1, N1h = p.N1 >> 1;
-    const uint32_t stage_bytes = (uint32_t)(2 * Nh * 32);
-    const int nk16 = p.Kpad >> 4, nk32 = p.Kpad >> 5;
+    const uint32_t sub_bytes = (uint32_t)(2 * Nh * 32);          // one K16 sub-tile: hi rows then lo rows (SWIZZLE_32B)
+    const uint32_t stage_bytes = 2 * sub_bytes;                  // K32 stage
+    const int nk32 = p.Kpad >> 5;
 
     // ---- shared memory carve-up -------------------------------------------------------------
-    uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the __shared__ array itself, so that the compiler keeps the shared
+    //  address space and emits LDS/STS instead of generic LD/ST)
+    //  The kernel has no static shared memory, so the 1024-byte alignment requested on the extern
+    //  array holds for the dynamic window; a misaligned base would corrupt the swizzled tiles: trap.
+    uint8_t* base = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
-    float* stage = (float*)(sB + NSTAGE * stage_bytes);                   // [M][128]
-    float* s_topv = stage + (size_t)p.M * VOX_CTA;                        // [2][128][3]
-    int* s_topi = (int*)(s_topv + 2 * VOX_CTA * 3);                       // [2][128][3]
-    float* s_min = (float*)(s_topi + 2 * VOX_CTA * 3);                    // [2][128]
+    float* stage = (float*)(sB + NSTAGE * stage_bytes);                   // [M + 1][128]; row M = -inf sentinel
+    unsigned long long* s_top = (unsigned long long*)(stage + (size_t)(p.M + 1) * VOX_CTA);   // [3][128] packed (value, ~index)
+    float* s_min = (float*)(s_top + 3 * VOX_CTA);                         // [2][128]
     float* s_sum = s_min + 2 * VOX_CTA;                                   // [2][128]
-    uint16_t* s_nbr = (uint16_t*)(s_sum + 2 * VOX_CTA);                   // [M][NBR_W], 16-byte aligned rows
-    uint64_t* bars = (uint64_t*)(s_nbr + (size_t)p.M * NBR_W);
+    uint16_t* s_nbr = (uint16_t*)(s_sum + 2 * VOX_CTA);                   // [M + 1][NBR_W], 16-byte aligned rows
+    uint64_t* bars = (uint64_t*)(s_nbr + (size_t)(p.M + 1) * NBR_W);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
     uint32_t* tmem_ptr_s = (uint32_t*)(d_empty + 1);
@@ -193,7 +226,12 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.M * NBR_W; i += TC_THREADS) s_nbr[i] = p.nbr[i];
+    for (int i = threadIdx.x; i < p.M * NBR_W; i += TC_THREADS) {         // missing neighbours -> sentinel row M (-inf)
+        const uint16_t n = p.nbr[i];
+        s_nbr[i] = n == NBR_NONE ? (uint16_t)p.M : n;
+    }
+    for (int i = threadIdx.x; i < NBR_W; i += TC_THREADS) s_nbr[p.M * NBR_W + i] = (uint16_t)p.M;   // sentinel vertex M
+    for (int i = threadIdx.x; i < VOX_CTA; i += TC_THREADS) stage[(size_t)p.M * VOX_CTA + i] = -CUDART_INF_F;
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -212,56 +250,73 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 
     if (warp == 0) {
         // ===== TMA producer: this CTA's half of the split matrix rows, K16 per stage ===========
-        if (lane == 0) {
-            const uint32_t full0 = mapa(smem_u32(&b_full[0]), 0);
-            uint32_t g = 0;
-            for (int tile = cluster_id; tile < p.ntiles; tile += ncluster) {
-                for (int c = 0; c < nk16; ++c, ++g) {
-                    const int s = g % NSTAGE; const uint32_t use = g / NSTAGE;
-                    mbar_wait(&b_empty[s], (use & 1) ^ 1);
+        // (the whole warp runs the loop so that control flow stays uniform; one elected lane issues)
+        const uint32_t full0 = mapa(smem_u32(&b_full[0]), 0);
+        uint32_t g = 0, it = 0;
+        for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
+            TRACE(13);
+            for (int c = 0; c < nk32; ++c, ++g) {
+                const int s = g % NSTAGE; const uint32_t use = g / NSTAGE;
+                mbar_wait<true>(&b_empty[s], (use & 1) ^ 1);
+                if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * stage_bytes);       // both CTAs' bytes land on the leader's barrier
                     const uint32_t dst = smem_u32(sB + s * stage_bytes);
                     const uint32_t bar = full0 + s * 8;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 4; ++h)                                       // (sub-tile, hi/lo)
                         asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                     ::"r"(dst + h * Nh * 32), "l"(&tmapB), "r"(c * 16), "r"((int)(rank * 2 * Nh + h * Nh)), "r"(bar) : "memory");
+                                     ::"r"(dst + (h >> 1) * sub_bytes + (h & 1) * Nh * 32), "l"(&tmapB), "r"(c * 32 + (h >> 1) * 16),
+                                       "r"((int)(rank * 2 * Nh + (h & 1) * Nh)), "r"(bar) : "memory");
                 }
+                __syncwarp();
             }
+            TRACE(14);
         }
     } else if (warp == W_MMA) {
-        // ===== MMA issuer (leader CTA, one lane) ================================================
-        if (rank == 0 && lane == 0) {
+        // ===== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) ==============
+        if (rank == 0) {
             const uint32_t idesc1 = make_idesc_f16(256, p.N1);
             const uint32_t idesc2 = p.N2 ? make_idesc_f16(256, p.N2) : 0u;
-            uint32_t g16 = 0, g32 = 0, it = 0;
+            uint32_t g32 = 0, it = 0;
             for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
                 mbar_wait(d_empty, (it & 1) ^ 1);                    // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
-                for (int c = 0; c < nk16; ++c, ++g16) {
-                    const int s = g16 % NSTAGE;
+                TRACE(0);
+                for (int c = 0; c < nk32; ++c, ++g32) {
+                    const int s = g32 % NSTAGE;
                     const int slot = g32 % ASLOT;
-                    mbar_wait(&b_full[s], (g16 / NSTAGE) & 1);
-                    if ((c & 1) == 0) mbar_wait(&a_full[slot], (g32 / ASLOT) & 1);
+                    long long t0 = p.trace ? clock64() : 0;
+                    mbar_wait(&b_full[s], (g32 / NSTAGE) & 1);
+                    long long t1 = p.trace ? clock64() : 0;
+                    mbar_wait(&a_full[slot], (g32 / ASLOT) & 1);
+                    if (p.trace) { long long t2 = clock64(); TRACE_ADD(15, t1 - t0); TRACE_ADD(16, t2 - t1); }
                     tc_fence_after();
-                    const uint32_t a_hi = tmem_base + TMEM_A_COL + slot * 32 + (c & 1) * 8;
-                    const uint32_t a_lo = a_hi + 16;
+                    const uint32_t a_base = tmem_base + TMEM_A_COL + slot * 32;
                     const uint32_t bs = smem_u32(sB + s * stage_bytes);
-                    const uint64_t bhi1 = make_sdesc_sw32(bs), blo1 = make_sdesc_sw32(bs + Nh * 32);
-                    const uint32_t acc = c > 0 ? 1u : 0u;
-                    mma_ts2(tmem_base, a_lo, bhi1, idesc1, acc);       // small terms first
-                    mma_ts2(tmem_base, a_hi, blo1, idesc1, 1u);
-                    mma_ts2(tmem_base, a_hi, bhi1, idesc1, 1u);
-                    if (p.N2) {
-                        const uint64_t bhi2 = make_sdesc_sw32(bs + N1h * 32), blo2 = make_sdesc_sw32(bs + Nh * 32 + N1h * 32);
-                        mma_ts2(tmem_base + p.N1, a_lo, bhi2, idesc2, acc);
-                        mma_ts2(tmem_base + p.N1, a_hi, blo2, idesc2, 1u);
-                        mma_ts2(tmem_base + p.N1, a_hi, bhi2, idesc2, 1u);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int sub = 0; sub < 2; ++sub) {
+                            const uint32_t a_hi = a_base + sub * 8, a_lo = a_hi + 16;
+                            const uint32_t b0 = bs + sub * sub_bytes;
+                            const uint32_t acc = (c | sub) ? 1u : 0u;
+                            const uint64_t bhi1 = make_sdesc_sw32(b0), blo1 = make_sdesc_sw32(b0 + Nh * 32);
+                            mma_ts2(tmem_base, a_lo, bhi1, idesc1, acc);       // small terms first
+                            mma_ts2(tmem_base, a_hi, blo1, idesc1, 1u);
+                            mma_ts2(tmem_base, a_hi, bhi1, idesc1, 1u);
+                            if (p.N2) {
+                                const uint64_t bhi2 = make_sdesc_sw32(b0 + N1h * 32), blo2 = make_sdesc_sw32(b0 + Nh * 32 + N1h * 32);
+                                mma_ts2(tmem_base + p.N1, a_lo, bhi2, idesc2, acc);
+                                mma_ts2(tmem_base + p.N1, a_hi, blo2, idesc2, 1u);
+                                mma_ts2(tmem_base + p.N1, a_hi, bhi2, idesc2, 1u);
+                            }
+                        }
+                        mma_commit2(&b_empty[s]);                          // B stage and A slot reusable once these MMAs retire
+                        mma_commit2(&a_empty[slot]);
+                        if (c == nk32 - 1) mma_commit2(d_full);
                     }
-                    mma_commit2(&b_empty[s]);                          // stage reusable once these MMAs retire
-                    if (c & 1) { mma_commit2(&a_empty[slot]); ++g32; }
+                    __syncwarp();
                 }
-                mma_commit2(d_full);
+                TRACE(1);
             }
         }
     } else if (warp < W_EPI0) {
@@ -275,6 +330,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool inside = vox < p.nvox && p.mask[vox] != 0;
             const float* src = p.dwi + vox;
+            if (warp == W_CONV0) TRACE(9);
             for (int c = grp; c < nk32; c += 2) {
                 float x[32];
 #pragma unroll
@@ -294,7 +350,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 }
                 const uint32_t g32 = it * nk32 + c;
                 const int slot = g32 % ASLOT;
-                mbar_wait(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
+                if (warp == W_CONV0 && c == grp) TRACE(10);
+                mbar_wait<true>(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
+                if (warp == W_CONV0 && c == grp) TRACE(11);
                 tc_fence_after();
                 const uint32_t col = lane_addr + TMEM_A_COL + slot * 32;
                 tmem_st8(col, hi); tmem_st8(col + 8, hi + 8); tmem_st8(col + 16, lo); tmem_st8(col + 24, lo + 8);
@@ -303,92 +361,171 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(afull0 + slot * 8);
             }
+            if (warp == W_CONV0) TRACE(12);
         }
     } else {
         // ===== epilogue ==========================================================================
-        const int ew = warp - W_EPI0, part = ew >> 2, q = warp & 3;
+        // phase 1 roles: warp quarter q owns TMEM lanes 32q..32q+31, `half` selects the column half
+        // phase 2 roles: 8 vertex ranges (one per warp); lane owns voxels 4*lane .. 4*lane+3 (float4)
+        const int ew = warp - W_EPI0, half = ew >> 2, q = warp & 3;
+        const int et = ew * 32 + lane;                                  // 0..255 within the epilogue group
         const int vl = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t dempty0 = mapa(smem_u32(d_empty), 0);
         const int csplit = p.N2 ? p.N1 : ((p.Npad / 2 + 15) & ~15);
-        const int c_begin = part ? csplit : 0, c_end = part ? p.Npad : csplit;
         const int M = p.M;
-        const int vhalf = (M + 1) >> 1;
+        const int c_begin = half ? csplit : 0, c_end = min(half ? p.Npad : csplit, (M + 15) & ~15);
+        const int vper = (M + 7) >> 3;
+        const int va = ew * vper, vb = min(M, va + vper);
         uint32_t it = 0;
         for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool vok = vox < p.nvox;
-            mbar_wait(d_full, it & 1);
+            for (int i = et; i < 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
+            mbar_wait<true>(d_full, it & 1);
             tc_fence_after();
+            if (warp == W_EPI0) TRACE(2);
+            // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + staging ----
             float mn = CUDART_INF_F, sum = 0.f;
-            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(lane_addr + c0, r);
-                tmem_wait_ld();
+            {
+                float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
+                float* sp = stage + c_begin * VOX_CTA + vl;
+                auto process = [&](const uint32_t (&r)[16], int c0) {
+                    if (c0 + 16 <= M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = c0 + j;
-                    if (col < M) {
-                        const float val = __uint_as_float(r[j]) * inv_scale;
-                        stage[col * VOX_CTA + vl] = val;
-                        if (vok) p.odf[(int64_t)col * p.out_pitch + vox] = val;
-                        mn = fminf(mn, val); sum += val;
+                        for (int j = 0; j < 16; ++j) {
+                            const float val = __uint_as_float(r[j]) * inv_scale;
+                            sp[j * VOX_CTA] = val;
+                            if (vok) gp[(int64_t)j * p.out_pitch] = val;
+                            mn = fminf(mn, val); sum += val;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (c0 + j < M) {
+                                const float val = __uint_as_float(r[j]) * inv_scale;
+                                sp[j * VOX_CTA] = val;
+                                if (vok) gp[(int64_t)j * p.out_pitch] = val;
+                                mn = fminf(mn, val); sum += val;
+                            }
+                        }
+                    }
+                    gp += 16 * p.out_pitch; sp += 16 * VOX_CTA;
+                };
+                uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
+                if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    tmem_wait_ld();
+                    if (c0 + 16 < c_end) tmem_ld16(lane_addr + c0 + 16, rb);
+                    process(ra, c0);
+                    if (c0 + 16 < c_end) {
+                        tmem_wait_ld();
+                        if (c0 + 32 < c_end) tmem_ld16(lane_addr + c0 + 32, ra);
+                        process(rb, c0 + 16);
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
-            s_min[part * VOX_CTA + vl] = mn; s_sum[part * VOX_CTA + vl] = sum;
+            if (warp == W_EPI0) TRACE(3);
+            s_min[half * VOX_CTA + vl] = mn; s_sum[half * VOX_CTA + vl] = sum;
             named_bar(1, EPI_THREADS);
-            // ---- local maxima of the folded mesh: strictly greater than every neighbour, > 0 ----
+            if (warp == W_EPI0) TRACE(4);
+            // ---- phase 2: local maxima of the folded mesh (strictly greater than every neighbour, > 0)
+            //      4 voxels per thread (float4 rows), every shared-memory load issued up front ----
+            float tv[4][3]; int ti[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tv[j][0] = tv[j][1] = tv[j][2] = 0.f; ti[j][0] = ti[j][1] = ti[j][2] = -1; }
+            // two vertices per iteration; neighbour offsets come from constant memory (uniform datapath)
             {
-                const int va = part * vhalf, vb = min(M, va + vhalf);
-                float tv[3] = {0.f, 0.f, 0.f}; int ti[3] = {-1, -1, -1};
-                for (int v = va; v < vb; ++v) {
-                    const float val = stage[v * VOX_CTA + vl];
-                    const uint4 nb = *reinterpret_cast<const uint4*>(s_nbr + v * NBR_W);
-                    bool cand = val > 0.f;
-                    const uint32_t w[4] = {nb.x, nb.y, nb.z, nb.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t n0 = w[k] & 0xFFFFu, n1 = w[k] >> 16;
-                        if (n0 != NBR_NONE) cand = cand && (val > stage[n0 * VOX_CTA + vl]);
-                        if (n1 != NBR_NONE) cand = cand && (val > stage[n1 * VOX_CTA + vl]);
+                const char* svb = reinterpret_cast<const char*>(stage) + lane * 16;
+                auto ld = [&](uint32_t off) { return *reinterpret_cast<const float4*>(svb + off); };
+                auto max6 = [](float a, float b, float c, float d, float e, float f) {
+                    return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(fmaxf(d, e), f));
+                };
+                for (int v = va; v < vb; v += 2) {
+                    const int vB = (v + 1 < vb) ? v + 1 : M;           // past the range -> sentinel row (never a peak)
+                    const uint4 oA0 = *reinterpret_cast<const uint4*>(&c_nbr_off[v * NBR_W]);
+                    const uint4 oA1 = *reinterpret_cast<const uint4*>(&c_nbr_off[v * NBR_W + 4]);
+                    const uint4 oB0 = *reinterpret_cast<const uint4*>(&c_nbr_off[vB * NBR_W]);
+                    const uint4 oB1 = *reinterpret_cast<const uint4*>(&c_nbr_off[vB * NBR_W + 4]);
+                    const float4 cA = ld(v * 512), cB = ld(vB * 512);
+                    const float4 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
+                    const float4 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
+                    float4 mA, mB;
+                    mA.x = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x); mA.y = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
+                    mA.z = max6(a0.z, a1.z, a2.z, a3.z, a4.z, a5.z); mA.w = max6(a0.w, a1.w, a2.w, a3.w, a4.w, a5.w);
+                    mB.x = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x); mB.y = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
+                    mB.z = max6(b0.z, b1.z, b2.z, b3.z, b4.z, b5.z); mB.w = max6(b0.w, b1.w, b2.w, b3.w, b4.w, b5.w);
+                    if (p.nbw > 6) {                                    // warp-uniform (meshes with degree 7-8)
+                        const float4 a6 = ld(oA1.z), a7 = ld(oA1.w), b6 = ld(oB1.z), b7 = ld(oB1.w);
+                        mA.x = fmaxf(mA.x, fmaxf(a6.x, a7.x)); mA.y = fmaxf(mA.y, fmaxf(a6.y, a7.y));
+                        mA.z = fmaxf(mA.z, fmaxf(a6.z, a7.z)); mA.w = fmaxf(mA.w, fmaxf(a6.w, a7.w));
+                        mB.x = fmaxf(mB.x, fmaxf(b6.x, b7.x)); mB.y = fmaxf(mB.y, fmaxf(b6.y, b7.y));
+                        mB.z = fmaxf(mB.z, fmaxf(b6.z, b7.z)); mB.w = fmaxf(mB.w, fmaxf(b6.w, b7.w));
                     }
-                    if (cand) top3_insert(val, v, tv, ti);
+                    // candidate <=> value > 0 and value > every neighbour  (value > max(nmax, 0))
+                    const bool pA0 = cA.x > fmaxf(mA.x, 0.f), pA1 = cA.y > fmaxf(mA.y, 0.f), pA2 = cA.z > fmaxf(mA.z, 0.f), pA3 = cA.w > fmaxf(mA.w, 0.f);
+                    const bool pB0 = cB.x > fmaxf(mB.x, 0.f), pB1 = cB.y > fmaxf(mB.y, 0.f), pB2 = cB.z > fmaxf(mB.z, 0.f), pB3 = cB.w > fmaxf(mB.w, 0.f);
+                    if (__any_sync(0xffffffffu, pA0 | pA1 | pA2 | pA3 | pB0 | pB1 | pB2 | pB3)) {   // local maxima are rare
+                        if (pA0) top3_insert(cA.x, v, tv[0], ti[0]);
+                        if (pA1) top3_insert(cA.y, v, tv[1], ti[1]);
+                        if (pA2) top3_insert(cA.z, v, tv[2], ti[2]);
+                        if (pA3) top3_insert(cA.w, v, tv[3], ti[3]);
+                        if (pB0) top3_insert(cB.x, v + 1, tv[0], ti[0]);
+                        if (pB1) top3_insert(cB.y, v + 1, tv[1], ti[1]);
+                        if (pB2) top3_insert(cB.z, v + 1, tv[2], ti[2]);
+                        if (pB3) top3_insert(cB.w, v + 1, tv[3], ti[3]);
+                    }
                 }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { s_topv[(part * VOX_CTA + vl) * 3 + k] = tv[k]; s_topi[(part * VOX_CTA + vl) * 3 + k] = ti[k]; }
             }
-            named_bar(1, EPI_THREADS);
-            if (part == 0) {
-                float tv[3], ti_f; int ti[3];
-                (void)ti_f;
+            if (warp == W_EPI0) TRACE(5);
+            // ---- merge the 8 vertex ranges: three rounds of 64-bit atomicMax on (value, ~index) keys:
+            //      larger value wins, equal values -> smaller index wins (the reference's stable order) ----
+            unsigned long long k0[4], k1[4], k2[4];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { tv[k] = s_topv[vl * 3 + k]; ti[k] = s_topi[vl * 3 + k]; }
+            for (int j = 0; j < 4; ++j) {
+                k0[j] = ti[j][0] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][0]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][0]) : 0ull;
+                k1[j] = ti[j][1] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][1]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][1]) : 0ull;
+                k2[j] = ti[j][2] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][2]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][2]) : 0ull;
+            }
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int idx = s_topi[(VOX_CTA + vl) * 3 + k];
-                    if (idx >= 0) top3_insert(s_topv[(VOX_CTA + vl) * 3 + k], idx, tv, ti);
+            for (int rnd = 0; rnd < 3; ++rnd) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (k0[j]) atomicMax(&s_top[rnd * VOX_CTA + 4 * lane + j], k0[j]);
+                named_bar(1, EPI_THREADS);
+                if (rnd < 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (k0[j] && s_top[rnd * VOX_CTA + 4 * lane + j] == k0[j]) { k0[j] = k1[j]; k1[j] = k2[j]; k2[j] = 0ull; }
                 }
-                const float omin = fminf(s_min[vl], s_min[VOX_CTA + vl]);
-                const float osum = s_sum[vl] + s_sum[VOX_CTA + vl];
+            }
+            if (warp == W_EPI0) TRACE(6);
+            // ---- outputs: one thread per voxel (epilogue warps 0-3) ----
+            if (ew < 4) {
+                const int ov = ew * 32 + lane;                          // voxel within the CTA
+                const int64_t ovox = (int64_t)tile * 256 + rank * VOX_CTA + ov;
+                const bool ook = ovox < p.nvox;
+                const float omin = fminf(s_min[ov], s_min[VOX_CTA + ov]);
+                const float osum = s_sum[ov] + s_sum[VOX_CTA + ov];
                 float mean = osum / (float)M;
-                const bool bad = vok && !(fabsf(osum) < CUDART_INF_F);   // fp16 overflow of the scaled signal (or non-finite input)
-                if (vok) {
+                const bool bad = ook && !(fabsf(osum) < CUDART_INF_F);   // fp16 overflow of the scaled signal (or non-finite input)
+                if (ook) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const bool ok = ti[k] >= 0;
-                        const int id = ok ? ti[k] : 0;
-                        p.peak[k][vox]                   = ok ? __ldg(p.vert + id * 3 + 0) : 0.f;
-                        p.peak[k][vox + p.out_pitch]     = ok ? __ldg(p.vert + id * 3 + 1) : 0.f;
-                        p.peak[k][vox + 2 * p.out_pitch] = ok ? __ldg(p.vert + id * 3 + 2) : 0.f;
-                        p.qa[k][vox] = ok ? tv[k] - omin : 0.f;
-                        if (p.peak_idx) p.peak_idx[vox + k * p.out_pitch] = (int16_t)ti[k];
+                        const unsigned long long key = s_top[k * VOX_CTA + ov];
+                        const bool ok = key != 0ull;
+                        const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
+                        const float val = __uint_as_float((uint32_t)(key >> 32));
+                        p.peak[k][ovox]                   = ok ? __ldg(p.vert + id * 3 + 0) : 0.f;
+                        p.peak[k][ovox + p.out_pitch]     = ok ? __ldg(p.vert + id * 3 + 1) : 0.f;
+                        p.peak[k][ovox + 2 * p.out_pitch] = ok ? __ldg(p.vert + id * 3 + 2) : 0.f;
+                        p.qa[k][ovox] = ok ? val - omin : 0.f;
+                        if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
                     }
                 }
-                if (!vok || bad) mean = -CUDART_INF_F;
+                if (!ook || bad) mean = -CUDART_INF_F;
                 const unsigned anybad = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mean = fmaxf(mean, __shfl_xor_sync(0xffffffffu, mean, o));
@@ -396,11 +533,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     if (mean > -CUDART_INF_F) atomicMax(p.stats, f2ord(mean));
                     if (anybad) {                                       // recompute this 64-voxel tile with the SIMT kernel
                         const int slot = atomicAdd(p.fix_count, 1);
-                        if (slot < p.fix_cap) p.fix_list[slot] = (int)(((int64_t)tile * 256 + rank * VOX_CTA + q * 32) >> 6);
+                        if (slot < p.fix_cap) p.fix_list[slot] = (int)(((int64_t)tile * 256 + rank * VOX_CTA + ew * 32) >> 6);
                     }
                 }
             }
+            if (warp == W_EPI0) TRACE(7);
             named_bar(1, EPI_THREADS);                                  // staging / scratch free for the next tile
+            if (warp == W_EPI0) TRACE(8);
         }
     }
 
@@ -414,10 +553,15 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 }
 
 size_t tc_smem_bytes(int M, int Nh) {
-    size_t b = (size_t)NSTAGE * 2 * Nh * 32 + (size_t)M * VOX_CTA * 4 + 2 * VOX_CTA * 3 * 8 + 2 * VOX_CTA * 2 * 4 +
-               (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16 + (size_t)M * NBR_W * 2;
+    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 1) * VOX_CTA * 4 + 3 * VOX_CTA * 8 + 2 * VOX_CTA * 2 * 4 +
+               (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16 + (size_t)(M + 1) * NBR_W * 2;
     return b + 1024 + 64;
 }
+
+struct ConstCache { unsigned long long uid[64]; };
+ConstCache g_const_cache{};
+std::mutex g_const_mu;
+std::atomic<unsigned long long> g_next_uid{1};
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -431,7 +575,7 @@ int tc_plan_init(Plan* p) {
     if (p->kind != PLAN_GQI) { set_error("tensor-core path: GQI only (DSI uses the SIMT kernel)"); return 1; }
     const int M = p->nvert, K = p->nvol;
     const int Npad = (M + 15) / 16 * 16;
-    if (Npad > TMEM_A_COL) { set_error("tensor-core path: more than 384 half-sphere vertices"); return 1; }
+    if (Npad > TMEM_A_COL || M + 1 > TC_MAX_VERT) { set_error("tensor-core path: more than 384 half-sphere vertices"); return 1; }
     int N1 = Npad, N2 = 0;
     if (Npad > 256) { N1 = (Npad / 2 + 15) / 16 * 16; N2 = Npad - N1; }
     const int Nh = (N1 + N2) / 2, N1h = N1 / 2, N2h = N2 / 2;
@@ -461,7 +605,14 @@ int tc_plan_init(Plan* p) {
         }
     }
     TcState* st = new TcState();
-    st->Kpad = Kpad; st->Npad = Npad; st->N1 = N1; st->N2 = N2; st->smem = smem;
+    st->Kpad = Kpad; st->Npad = Npad; st->N1 = N1; st->N2 = N2; st->smem = smem; st->nbw = p->nbr_width;
+    st->uid = g_next_uid.fetch_add(1);
+    st->h_nbr_off.assign((size_t)(M + 1) * NBR_W, (uint32_t)M * 512u);          // sentinel row M everywhere ...
+    for (int v = 0; v < M; ++v)
+        for (int k = 0; k < NBR_W; ++k) {
+            const uint16_t n = p->h_nbr[(size_t)v * NBR_W + k];
+            if (n != NBR_NONE) st->h_nbr_off[(size_t)v * NBR_W + k] = (uint32_t)n * 512u;
+        }
     if (cudaMalloc(&st->d_split, split.size() * sizeof(__half)) != cudaSuccess ||
         cudaMemcpy(st->d_split, split.data(), split.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("tensor-core path: device allocation failed"); cudaGetLastError(); delete st; return 1;
@@ -507,6 +658,15 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         st->scratch_cap = need;
     }
     FB_CUDA(cudaMemsetAsync(st->d_scratch, 0, 2 * sizeof(int), stream));
+    {   // neighbour offsets -> constant memory of this device (skipped when this plan's table is already resident;
+        // launches of DIFFERENT plans on one device must not overlap in time)
+        std::lock_guard<std::mutex> lk(g_const_mu);
+        if (p->device < 64 && g_const_cache.uid[p->device] != st->uid) {
+            FB_CUDA(cudaMemcpyToSymbolAsync(c_nbr_off, st->h_nbr_off.data(), st->h_nbr_off.size() * sizeof(uint32_t), 0,
+                                            cudaMemcpyHostToDevice, stream));
+            g_const_cache.uid[p->device] = st->uid;
+        }
+    }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
     sample_max_kernel<<<nsm * 8, 256, 0, stream>>>(a.dwi, a.dwi_pitch, a.nvox, p->nvol, st->d_scratch);
@@ -519,10 +679,25 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     tp.maxbits = st->d_scratch; tp.fix_count = st->d_scratch + 1; tp.fix_list = st->d_scratch + 2;
     tp.fix_cap = (int)(2 * ntile64);
     tp.ntiles = (int)((a.nvox + 255) / 256);
+    tp.nbw = st->nbw;
     const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
+    const char* trace_path = getenv("FIBERS_TC_TRACE");
+    long long* d_trace = nullptr;
+    if (trace_path && *trace_path) {
+        FB_CUDA(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
+        FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
+        tp.trace = d_trace;
+    }
     recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, st->tmap);
     count_launch(2);
     FB_CUDA(cudaGetLastError());
+    if (d_trace) {
+        std::vector<long long> h(16 * 32);
+        FB_CUDA(cudaStreamSynchronize(stream));
+        FB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
+    }
     // voxels whose scaled signal overflowed fp16 (rare): recompute their 64-voxel tiles in fp32
     return launch_recon_simt_list(p, a, tp.fix_list, tp.fix_count, stream);
 }

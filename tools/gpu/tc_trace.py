@@ -1,0 +1,37 @@
+"""Debug aid: run the tensor-core kernel once with FIBERS_TC_TRACE and print the per-role clock
+trace of CTA 0 (cycles relative to the first MMA of the first tile)."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+os.environ["FIBERS_TC_TRACE"] = "/tmp/tc_trace.bin"
+import torch
+import bench
+import fibers_jl_b200 as F
+from fibers_jl_b200 import device as D
+
+shape = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "145,174,145").split(","))
+nvox = int(np.prod(shape))
+bval, bvec = bench.make_tables()
+dev = torch.device("cuda", 0)
+dwi = bench.synth_dwi_device(torch, nvox, bval, bvec, 1, dev)
+mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
+odf = torch.empty((321, nvox), dtype=torch.float32, device=dev)
+peak = [torch.empty((3, nvox), dtype=torch.float32, device=dev) for _ in range(3)]
+qa = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
+stats = torch.zeros(2, dtype=torch.int32, device=dev)
+D.set_kernel("tc")
+plan = D.Plan("gqi", 0, bval, bvec, F.sphere_642, 1.25)
+for _ in range(2):
+    plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, nvox, odf.data_ptr(), [p.data_ptr() for p in peak],
+               [q.data_ptr() for q in qa], stats.data_ptr(), finalize=True, stream=0)
+torch.cuda.synchronize()
+t = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64).reshape(16, 32)
+t0 = t[0, 0]
+names = {0: "mma:start", 1: "mma:done", 2: "epi:d_full", 3: "epi:tmem_read_done", 4: "epi:bar1", 5: "epi:peaks_done", 6: "epi:bar2",
+         7: "epi:merge_done", 8: "epi:bar3", 9: "conv:tile_start", 10: "conv:first_loads_issued", 11: "conv:a_empty_ok", 12: "conv:tile_end",
+         13: "tma:tile_start", 14: "tma:tile_end"}
+for it in range(8):
+    ev = sorted((int(t[it, k] - t0), names[k]) for k in names if t[it, k])
+    print(f"tile {it}: " + "  ".join(f"{n}@{c}" for c, n in ev))
+    print(f"         mma wait b_full {int(t[it,15])} cyc, wait a_full {int(t[it,16])} cyc")
