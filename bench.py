@@ -41,6 +41,19 @@ def algorithmic_bytes_per_voxel(nvol, nvert):      # 4N + 4M +
     return 4 * nvol + 4 * nvert + 36 + 12 + 1
 
 
+def profiled_traffic(kernel, nvox):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/roofline_traffic.json), or None when no capture exists for this kernel / size."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        d = json.load(open(p)).get(kernel)
+        if d and int(d["nvox"]) == int(nvox):
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -86,44 +99,78 @@ def synth_dwi_device(torch, nvox, bval, bvec, seed, device, snr=30.0, chunk=1 <<
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, 10 ms period; falls back to
+    `nvidia-smi -lms 100` when pynvml is unavailable)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+               "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.bits, self.stop_flag, self.thread, self.mx = index, [], 0, False, None, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except (ValueError, IndexError):
+                pass
+        return index
+
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
+        if self.nvml:
+            try:
+                self.mx = self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM)
+            except Exception:
+                self.mx = None
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        else:
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            reasons = sorted(k for k, b in self.REASONS.items() if self.bits & b)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.mx,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml"}
+        if not getattr(self, "proc", None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        time.sleep(0.15); self.proc.terminate()
+        sm, mx = [], None
+        for l in self.proc.stdout:
             f = [x.strip() for x in l.split(",")]
-            if len(f) < 6:
-                continue
             try:
                 sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": [], "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -220,6 +267,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libfibers_cuda has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -266,10 +314,7 @@ def main():
     clocks = sampler.stop()
     elapsed_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = F.batch.reduce_max(elapsed_ms, dist if world > 1 else None, dev)      # max over ranks
     ms_per_step = elapsed_ms / steps
     value = world * nvox / (ms_per_step * 1e-3)
 
@@ -301,10 +346,7 @@ def main():
             e2e_step()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.e2e_steps
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = F.batch.reduce_max(dt, dist if world > 1 else None, dev)
         e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox * (4 * nvol + 1),
                "d2h_bytes_per_step": nvox * 4 * (M_VERT + 9 + 3), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
                "api": "fibers_gqi_rec (host pointers, pinned buffers)"}
@@ -318,7 +360,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "kernel": plan.kernel, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                             "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak_gbs, "traffic": profiled_traffic(plan.kernel, nvox), "peak_source": peak_src,
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_voxel": algorithmic_bytes_per_voxel(nvol, M_VERT),
                              "algorithmic_tflops": 2.0 * nvol * M_VERT * nvox / (kern_ms * 1e-3) / 1e12}}
         if e2e:

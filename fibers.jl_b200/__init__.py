@@ -5,7 +5,7 @@ libfibers_cuda.so), the host-side mirror of the reference's function signatures 
 the MRI / ODF containers those signatures take, and synthetic phantoms.  Import as
 `fibers_jl_b200` (see the loader module at the repo root: the directory name contains a dot).
 """
-from . import _lib, device
+from . import _lib, device, batch
 from ._lib import FibersCudaError, device_count
 from .mri import MRI
 from .odf import ODF, sphere_362, sphere_642, sphere_724

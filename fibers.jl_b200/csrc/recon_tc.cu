@@ -10,14 +10,16 @@
 //   kernel -- see launch_recon_tc.)
 //
 // One persistent CTA PAIR (cta_group::2, M = 256) per two SMs; every CTA owns 128 voxels of a tile:
-//   warp 0      TMA producer: streams K16 chunks of the split matrix (this CTA's half of the rows)
-//               from L2 into a 4-stage SWIZZLE_32B shared-memory ring
+//   warp 0      TMA producer: streams K32 chunks of the split matrix (this CTA's half of the rows)
+//               from L2 into a 2-stage SWIZZLE_32B shared-memory ring (two K16 sub-tiles per stage)
 //   warp 1      MMA issuer (leader CTA): tcgen05.mma.cta_group::2, A operand from TENSOR MEMORY,
 //               B from shared memory; accumulators D[128 x Npad] fp32 in TMEM columns [0, Npad)
 //   warps 2-9   converters: coalesced fp32 loads of the DWI slab (voxel-contiguous), clamp, scale,
 //               hi/lo fp16 split, tcgen05.st into a 4-slot TMEM ring (columns 384..511)
 //   warps 10-17 epilogue: tcgen05.ld, un-scale, coalesced ODF store, stage the 128 x M tile in shared
-//               memory, local-maximum search on the folded mesh + top-3 + QA, per-voxel mean -> atomicMax
+//               memory; local-maximum search on the folded mesh (4 voxels per thread as float4 rows,
+//               neighbour offsets from constant memory), top-3 by three rounds of 64-bit shared
+//               atomicMax on (value, ~index) keys, QA, per-voxel mean -> atomicMax
 // The full ODF never round-trips HBM: it is written once and the peaks come from the staged tile.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -36,13 +38,15 @@ int launch_recon_simt_list(Plan* p, const ReconArgs& a, const int* d_list, const
 
 namespace {
 
-constexpr int TC_THREADS = 576;
+constexpr int N_EPI = 8;             // epilogue warps (multiple of 4: one per TMEM lane quarter)
 constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = 10;
+constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
+constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
 constexpr int NSTAGE = 2;            // B ring: K32 chunks (two K16 sub-tiles each)
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
 constexpr int VOX_CTA = 128;
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_THREADS = N_EPI * 32;
 constexpr float FP16_TARGET = 8192.f;   // the sampled maximum is scaled to <= 8192 (8x headroom to 65504)
 
 // Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * 512) into the staged tile,
@@ -208,9 +212,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
     float* stage = (float*)(sB + NSTAGE * stage_bytes);                   // [M + 1][128]; row M = -inf sentinel
     unsigned long long* s_top = (unsigned long long*)(stage + (size_t)(p.M + 1) * VOX_CTA);   // [3][128] packed (value, ~index)
-    float* s_min = (float*)(s_top + 3 * VOX_CTA);                         // [2][128]
-    float* s_sum = s_min + 2 * VOX_CTA;                                   // [2][128]
-    uint16_t* s_nbr = (uint16_t*)(s_sum + 2 * VOX_CTA);                   // [M + 1][NBR_W], 16-byte aligned rows
+    float* s_min = (float*)(s_top + 3 * VOX_CTA);                         // [N_CPART][128]
+    float* s_sum = s_min + N_CPART * VOX_CTA;                             // [N_CPART][128]
+    uint16_t* s_nbr = (uint16_t*)(s_sum + N_CPART * VOX_CTA);                   // [M + 1][NBR_W], 16-byte aligned rows
     uint64_t* bars = (uint64_t*)(s_nbr + (size_t)(p.M + 1) * NBR_W);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
@@ -219,7 +223,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < ASLOT; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }   // 4 converter warps x 2 CTAs
-        mbar_init(d_full, 1); mbar_init(d_empty, 16);                                             // 8 epilogue warps x 2 CTAs
+        mbar_init(d_full, 1); mbar_init(d_empty, 2 * N_EPI);                                      // epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {
@@ -249,7 +253,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     }
 
     if (warp == 0) {
-        // ===== TMA producer: this CTA's half of the split matrix rows, K16 per stage ===========
+        // ===== TMA producer: this CTA's half of the split matrix rows, K32 per stage ===========
         // (the whole warp runs the loop so that control flow stays uniform; one elected lane issues)
         const uint32_t full0 = mapa(smem_u32(&b_full[0]), 0);
         uint32_t g = 0, it = 0;
@@ -365,17 +369,17 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         }
     } else {
         // ===== epilogue ==========================================================================
-        // phase 1 roles: warp quarter q owns TMEM lanes 32q..32q+31, `half` selects the column half
-        // phase 2 roles: 8 vertex ranges (one per warp); lane owns voxels 4*lane .. 4*lane+3 (float4)
-        const int ew = warp - W_EPI0, half = ew >> 2, q = warp & 3;
+        // phase 1 roles: warp quarter q owns TMEM lanes 32q..32q+31, `cpart` selects the column range
+        // phase 2 roles: N_EPI vertex ranges (one per warp); lane owns voxels 4*lane .. 4*lane+3 (float4)
+        const int ew = warp - W_EPI0, cpart = ew >> 2, q = warp & 3;
         const int et = ew * 32 + lane;                                  // 0..255 within the epilogue group
         const int vl = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t dempty0 = mapa(smem_u32(d_empty), 0);
-        const int csplit = p.N2 ? p.N1 : ((p.Npad / 2 + 15) & ~15);
         const int M = p.M;
-        const int c_begin = half ? csplit : 0, c_end = min(half ? p.Npad : csplit, (M + 15) & ~15);
-        const int vper = (M + 7) >> 3;
+        const int cper = ((p.Npad + N_CPART - 1) / N_CPART + 15) & ~15;
+        const int c_begin = cpart * cper, c_end = min(min(c_begin + cper, p.Npad), (M + 15) & ~15);
+        const int vper = (M + N_EPI - 1) / N_EPI;
         const int va = ew * vper, vb = min(M, va + vper);
         uint32_t it = 0;
         for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
@@ -429,7 +433,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
             if (warp == W_EPI0) TRACE(3);
-            s_min[half * VOX_CTA + vl] = mn; s_sum[half * VOX_CTA + vl] = sum;
+            s_min[cpart * VOX_CTA + vl] = mn; s_sum[cpart * VOX_CTA + vl] = sum;
             named_bar(1, EPI_THREADS);
             if (warp == W_EPI0) TRACE(4);
             // ---- phase 2: local maxima of the folded mesh (strictly greater than every neighbour, > 0)
@@ -507,8 +511,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 const int ov = ew * 32 + lane;                          // voxel within the CTA
                 const int64_t ovox = (int64_t)tile * 256 + rank * VOX_CTA + ov;
                 const bool ook = ovox < p.nvox;
-                const float omin = fminf(s_min[ov], s_min[VOX_CTA + ov]);
-                const float osum = s_sum[ov] + s_sum[VOX_CTA + ov];
+                float omin = s_min[ov], osum = s_sum[ov];
+#pragma unroll
+                for (int cp = 1; cp < N_CPART; ++cp) { omin = fminf(omin, s_min[cp * VOX_CTA + ov]); osum += s_sum[cp * VOX_CTA + ov]; }
                 float mean = osum / (float)M;
                 const bool bad = ook && !(fabsf(osum) < CUDART_INF_F);   // fp16 overflow of the scaled signal (or non-finite input)
                 if (ook) {
@@ -553,7 +558,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 }
 
 size_t tc_smem_bytes(int M, int Nh) {
-    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 1) * VOX_CTA * 4 + 3 * VOX_CTA * 8 + 2 * VOX_CTA * 2 * 4 +
+    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 1) * VOX_CTA * 4 + 3 * VOX_CTA * 8 + N_CPART * VOX_CTA * 2 * 4 +
                (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16 + (size_t)(M + 1) * NBR_W * 2;
     return b + 1024 + 64;
 }

@@ -192,6 +192,30 @@ def test_gqi_multichunk_pipeline(F, sphere642, kernel):
     _check_recon(got, None, r64, v, f, 321, "gqi multichunk")
 
 
+def test_multi_gpu_zslab_sharding(F, sphere642):
+    """ngpu = 2 inside one process (what the Julia ccall uses): z-slabs on two devices, host gather,
+    host-side odfmax reduce.  Results must be identical to the single-GPU call."""
+    if F.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.gqi_phantom((20, 18, 11), seed=17, mask_fill=0.6)
+    F.device.set_devices([0, 1])
+    try:
+        g1 = F.gqi_rec(*_mri(F, ph), ngpu=1)
+        g2 = F.gqi_rec(*_mri(F, ph), ngpu=2)
+        assert np.array_equal(g1.odf.vol, g2.odf.vol) and np.array_equal(g1.peak_idx, g2.peak_idx)
+        for k in range(3):
+            assert np.array_equal(g1.qa[k].vol, g2.qa[k].vol, equal_nan=True)
+        r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+        _check_recon(g2, None, r64, v, f, 321, "gqi 2 gpus")
+        pt = phantom.dti_phantom((16, 14, 9), seed=18)
+        d1 = F.dti_fit(*_mri(F, pt), ngpu=1); d2 = F.dti_fit(*_mri(F, pt), ngpu=2)
+        assert np.array_equal(d1.fa.vol, d2.fa.vol, equal_nan=True) and np.array_equal(d1.valid, d2.valid)
+    finally:
+        F.device.set_devices([0])
+
+
 def test_gqi_edge_cases(F, sphere642, kernel):
     v, f = sphere642
     from fibers_jl_b200 import phantom
