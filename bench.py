@@ -242,7 +242,8 @@ def main():
     nvol = bval.shape[0]
     workload = f"cfg2 GQI recon+peaks {shape[0]}x{shape[1]}x{shape[2]}x{nvol} (18 b0 + 90x b=1000/2000/3000), sphere_642, mask==1"
     config = {"workload": workload, "per_gpu": "one HCP-shaped subject per GPU (weak; cfg4-style batch)",
-              "l2_policy": "inputs (4.2 GB/step) larger than L2 (126 MB); no explicit flush", "sigma": 1.25}
+              "l2_policy": "inputs (4.2 GB/step) larger than L2 (126 MB); no explicit flush", "sigma": 1.25,
+              "layout": "frame-major [frame][voxel]; dwi pitch = nvox, output pitch = nvox rounded up to 64"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -276,8 +277,9 @@ def main():
 
     dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000 + rank, dev)
     mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
-    odf = torch.empty((M_VERT, nvox), dtype=torch.float32, device=dev)
-    peak = [torch.empty((3, nvox), dtype=torch.float32, device=dev) for _ in range(3)]
+    pitch = (nvox + 63) // 64 * 64          # output frame pitch: 256-byte aligned rows (lets the ODF tile leave by TMA)
+    odf = torch.empty((M_VERT, pitch), dtype=torch.float32, device=dev)
+    peak = [torch.empty((3, pitch), dtype=torch.float32, device=dev) for _ in range(3)]
     qa = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
     stats = torch.zeros(2, dtype=torch.int32, device=dev)
     plan = D.Plan("gqi", local_rank, bval, bvec, F.sphere_642, 1.25)
@@ -287,7 +289,7 @@ def main():
     def step(ev=None):
         D.stats_init(stats.data_ptr(), stream)
         if ev: ev[0].record()
-        plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, nvox, odf.data_ptr(), pk, qp, stats.data_ptr(),
+        plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, pitch, odf.data_ptr(), pk, qp, stats.data_ptr(),
                    finalize=False, stream=stream)
         if ev: ev[1].record()
         D.qa_scale(qp, nvox, d_stats=stats.data_ptr(), stream=stream)

@@ -28,6 +28,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <atomic>
 #include <mutex>
 #include "common.cuh"
@@ -65,12 +66,14 @@ struct TcParams {
     int* fix_list; int* fix_count; int fix_cap;
     int ntiles;                  // 256-voxel tiles
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
+    int odf_tma, odf_box_rows, odf_nbox;   // ODF tile leaves through TMA stores of the staged tile (else per-thread STG)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
 struct TcState {
     __half* d_split = nullptr;   // [2 ranks][hi Nh rows | lo Nh rows][Kpad]
     CUtensorMap tmap;
+    void* encode = nullptr;      // cuTensorMapEncodeTiled
     int Kpad = 0, Npad = 0, N1 = 0, N2 = 0, nbw = 8;
     unsigned long long uid = 0;              // identifies the neighbour table in the per-device constant-memory cache
     std::vector<uint32_t> h_nbr_off;         // [M + 1][NBR_W] byte offsets
@@ -192,7 +195,7 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
+recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapO) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -214,8 +217,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     unsigned long long* s_top = (unsigned long long*)(stage + (size_t)(p.M + 1) * VOX_CTA);   // [3][128] packed (value, ~index)
     float* s_min = (float*)(s_top + 3 * VOX_CTA);                         // [N_CPART][128]
     float* s_sum = s_min + N_CPART * VOX_CTA;                             // [N_CPART][128]
-    uint16_t* s_nbr = (uint16_t*)(s_sum + N_CPART * VOX_CTA);                   // [M + 1][NBR_W], 16-byte aligned rows
-    uint64_t* bars = (uint64_t*)(s_nbr + (size_t)(p.M + 1) * NBR_W);
+    uint64_t* bars = (uint64_t*)(s_sum + N_CPART * VOX_CTA);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
     uint32_t* tmem_ptr_s = (uint32_t*)(d_empty + 1);
@@ -230,11 +232,6 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < p.M * NBR_W; i += TC_THREADS) {         // missing neighbours -> sentinel row M (-inf)
-        const uint16_t n = p.nbr[i];
-        s_nbr[i] = n == NBR_NONE ? (uint16_t)p.M : n;
-    }
-    for (int i = threadIdx.x; i < NBR_W; i += TC_THREADS) s_nbr[p.M * NBR_W + i] = (uint16_t)p.M;   // sentinel vertex M
     for (int i = threadIdx.x; i < VOX_CTA; i += TC_THREADS) stage[(size_t)p.M * VOX_CTA + i] = -CUDART_INF_F;
     tc_fence_before();
     __syncthreads();
@@ -392,6 +389,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + staging ----
             float mn = CUDART_INF_F, sum = 0.f;
             {
+                const bool st_direct = vok && !p.odf_tma;
                 float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
                 float* sp = stage + c_begin * VOX_CTA + vl;
                 auto process = [&](const uint32_t (&r)[16], int c0) {
@@ -400,7 +398,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                         for (int j = 0; j < 16; ++j) {
                             const float val = __uint_as_float(r[j]) * inv_scale;
                             sp[j * VOX_CTA] = val;
-                            if (vok) gp[(int64_t)j * p.out_pitch] = val;
+                            if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                             mn = fminf(mn, val); sum += val;
                         }
                     } else {
@@ -409,7 +407,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                             if (c0 + j < M) {
                                 const float val = __uint_as_float(r[j]) * inv_scale;
                                 sp[j * VOX_CTA] = val;
-                                if (vok) gp[(int64_t)j * p.out_pitch] = val;
+                                if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                                 mn = fminf(mn, val); sum += val;
                             }
                         }
@@ -434,7 +432,20 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
             if (warp == W_EPI0) TRACE(3);
             s_min[cpart * VOX_CTA + vl] = mn; s_sum[cpart * VOX_CTA + vl] = sum;
+            if (p.odf_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tile -> visible to the TMA engine
             named_bar(1, EPI_THREADS);
+            if (p.odf_tma && warp == W_EPI0) {
+                // the ODF tile leaves as bulk tensor stores (rows = vertices, 128 voxels each; rows >= M and
+                // voxels >= nvox are clipped by the tensor map): no per-thread store instructions at all
+                if (elect_one()) {
+                    const int x0 = (int)((int64_t)tile * 256 + rank * VOX_CTA);
+                    for (int b = 0; b < p.odf_nbox; ++b)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmapO), "r"(x0), "r"(b * p.odf_box_rows), "r"(smem_u32(stage + (size_t)b * p.odf_box_rows * VOX_CTA)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                __syncwarp();
+            }
             if (warp == W_EPI0) TRACE(4);
             // ---- phase 2: local maxima of the folded mesh (strictly greater than every neighbour, > 0)
             //      4 voxels per thread (float4 rows), every shared-memory load issued up front ----
@@ -543,12 +554,14 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 }
             }
             if (warp == W_EPI0) TRACE(7);
+            if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staged tile fully read
             named_bar(1, EPI_THREADS);                                  // staging / scratch free for the next tile
             if (warp == W_EPI0) TRACE(8);
         }
     }
 
     // ---- teardown --------------------------------------------------------------------------
+    if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -559,7 +572,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 
 size_t tc_smem_bytes(int M, int Nh) {
     size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 1) * VOX_CTA * 4 + 3 * VOX_CTA * 8 + N_CPART * VOX_CTA * 2 * 4 +
-               (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16 + (size_t)(M + 1) * NBR_W * 2;
+               (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
 
@@ -630,6 +643,7 @@ int tc_plan_init(Plan* p) {
     cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
     cuuint32_t box[2] = {16, (cuuint32_t)Nh};
     cuuint32_t estr[2] = {1, 1};
+    st->encode = fn;
     CUresult r = ((EncodeFn)fn)(&st->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, st->d_split, gdim, gstr, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -685,6 +699,26 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     tp.fix_cap = (int)(2 * ntile64);
     tp.ntiles = (int)((a.nvox + 255) / 256);
     tp.nbw = st->nbw;
+    // ODF output tensor map (per call: pointer / pitch belong to the caller).  TMA needs a 16-byte aligned
+    // base and row pitch; otherwise the epilogue falls back to per-thread coalesced stores.
+    CUtensorMap tmapO; memset(&tmapO, 0, sizeof(tmapO));
+    tp.odf_tma = 0;
+    {
+        const int nbox = (p->nvert + 255) / 256, rows = (p->nvert + nbox - 1) / nbox;
+        const bool aligned = ((uintptr_t)a.odf % 16 == 0) && ((a.out_pitch * 4) % 16 == 0) && a.nvox < (1ll << 31);
+        const char* env = getenv("FIBERS_TC_ODF_TMA");
+        if (aligned && nbox * rows <= p->nvert + 1 && !(env && env[0] == '0')) {
+            cuuint64_t gdim[2] = {(cuuint64_t)a.nvox, (cuuint64_t)p->nvert};
+            cuuint64_t gstr[1] = {(cuuint64_t)a.out_pitch * 4};
+            cuuint32_t box[2] = {(cuuint32_t)VOX_CTA, (cuuint32_t)rows};
+            cuuint32_t estr[2] = {1, 1};
+            if (st->encode && ((EncodeFn)st->encode)(&tmapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.odf, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                tp.odf_tma = 1; tp.odf_box_rows = rows; tp.odf_nbox = nbox;
+            }
+        }
+    }
     const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
     const char* trace_path = getenv("FIBERS_TC_TRACE");
     long long* d_trace = nullptr;
@@ -693,7 +727,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
         tp.trace = d_trace;
     }
-    recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, st->tmap);
+    recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, st->tmap, tmapO);
     count_launch(2);
     FB_CUDA(cudaGetLastError());
     if (d_trace) {
