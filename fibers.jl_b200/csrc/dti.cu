@@ -177,58 +177,151 @@ __device__ void dti_zero(int64_t vox, const DtiOut& o) {
     if (o.valid) o.valid[vox] = 0;
 }
 
-// NC = 7 (DTI) or 2 (ADC).  Full-sample path; voxels needing the partial path are appended
-// to `list` and handled by fit_partial_kernel.
+// NC = 7 (DTI) or 2 (ADC).  One thread per voxel streams its N samples (coalesced across the warp).
+//
+// Full-sample voxels: d = pinv(A) * ln s.
+// Partly non-positive voxels (src/dti.jl:297-298: d = pinv(A[ipos,:]) * ln s[ipos]): with r removed
+// rows U = A[removed,:]' the normal matrix is a rank-r downdate, G_pos = G - U U', so by Woodbury
+//     d = x0 + P_r (I - U' P_r)^-1 U' x0,   x0 = pinv(A) * (ln s with zeros at removed rows),
+// where P_r = pinv(A)[:, removed] (= G^-1 U for a full-column-rank design).  x0 falls out of the main
+// loop for free; the r x r system (r <= RMAX) is solved per thread in float64.  Voxels with more
+// removed samples, or a singular downdate, go to the general per-voxel pinv kernel via a device list.
+// ln(s) for normal positive s in ~8 branch-free instructions: s = m * 2^e with m in [0.75, 1.5); MUFU.LG2
+// on the mantissa only (absolute error ~1e-7 because |log2 m| <= 0.585), exponent added with a two-term
+// ln 2.  About 0.5 ulp at typical DWI magnitudes, i.e. as accurate as logf at a third of the instructions.
+// Denormal / inf inputs are detected by the caller (fast_ln_range) and sent to the library-logf path.
+__device__ __forceinline__ float fast_ln(float s) {
+    const uint32_t b = __float_as_uint(s);
+    const uint32_t eb = (b - 0x3F400000u) & 0xFF800000u;              // exponent part to strip: floor(log2(s / 0.75)) << 23
+    const float m = __uint_as_float(b - eb);                          // in [0.75, 1.5)
+    const float ef = (float)((int)eb >> 23);
+    float l2m;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2m) : "f"(m));
+    return fmaf(ef, 0.693145752f, fmaf(ef, 1.42860677e-6f, l2m * 0.693147182f));
+}
+// (bits - min_normal) as unsigned is >= 0x7F000000 exactly for denormals, zero, negatives, inf and NaN
+__device__ __forceinline__ uint32_t fast_ln_range(float s) { return __float_as_uint(s) - 0x00800000u; }
+
+constexpr int RMAX = 6;
+constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] = pinv(A)' padded (2 x LDS.128 per sample)
+
 template <int NC>
-__global__ void __launch_bounds__(DTI_THREADS)
+__global__ void __launch_bounds__(DTI_THREADS, 8)      // <= 64 registers: the rare float64 downdate may spill, the stream must not
 fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __restrict__ mask, int64_t nvox,
-                int nvol, const float* __restrict__ pinv, const uint8_t* __restrict__ ib0,
+                int nvol, const float* __restrict__ pinv, const float* __restrict__ design, const uint8_t* __restrict__ ib0,
                 DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
                 int* __restrict__ list, int* __restrict__ count) {
-    extern __shared__ float sm[];
-    float* spa = sm;                                    // [NC][nvol]
-    uint8_t* sb0 = (uint8_t*)(spa + (size_t)NC * nvol);  // [nvol]
-    for (int i = threadIdx.x; i < NC * nvol; i += blockDim.x) spa[i] = pinv[i];
-    for (int i = threadIdx.x; i < nvol; i += blockDim.x) sb0[i] = ib0[i];
+    extern __shared__ __align__(16) float sm[];
+    float* spa = sm;                                     // [nvol][CW]: column j of pinv(A), zero padded
+    for (int i = threadIdx.x; i < CW * nvol; i += blockDim.x) {
+        const int j = i / CW, k = i - j * CW;
+        spa[i] = k < NC ? pinv[k * nvol + j] : ((k == (NC > 2 ? 7 : 2) && ib0[j]) ? 1.f : 0.f);
+    }
     __syncthreads();
     const int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vox >= nvox) return;
-    bool inside = mask[vox] != 0;
+    const bool inside = mask[vox] != 0;
     float d[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) d[k] = 0.f;
-    int npos = 0;
-    bool b0pos = false;
+    int npos = 0, nrem = 0;
+    int rem[RMAX];
+    float b0acc = 0.f;                                  // > 0 iff some minimum-b volume is positive (flag rides in the padded coefficient row)
+    uint32_t odd = 0u;                                  // max over POSITIVE samples of fast_ln_range: flags denormal / inf input
+    auto sample = [&](float s, int j) {
+        const bool pos = s > 0.f;
+        npos += pos;
+        odd = max(odd, pos ? fast_ln_range(s) : 0u);
+        const float lg = pos ? fast_ln(s) : 0.f;        // select, not a branch: garbage for s <= 0 is discarded
+        const float4 c0 = *reinterpret_cast<const float4*>(spa + j * CW);
+        d[0] = fmaf(c0.x, lg, d[0]); d[1] = fmaf(c0.y, lg, d[1]);
+        if (NC > 2) {
+            const float4 c1 = *reinterpret_cast<const float4*>(spa + j * CW + 4);
+            d[2 % NC] = fmaf(c0.z, lg, d[2 % NC]); d[3 % NC] = fmaf(c0.w, lg, d[3 % NC]);
+            d[4 % NC] = fmaf(c1.x, lg, d[4 % NC]); d[5 % NC] = fmaf(c1.y, lg, d[5 % NC]); d[6 % NC] = fmaf(c1.z, lg, d[6 % NC]);
+            b0acc = fmaf(c1.w, pos ? 1.f : 0.f, b0acc);
+        } else {
+            b0acc = fmaf(c0.z, pos ? 1.f : 0.f, b0acc);
+        }
+    };
     if (inside) {
-        const float* src = dwi + vox;
+        // UNROLL running pointers, one per sample of the group (64-bit add per load instead of a 64-bit multiply-add)
+        const float* ptr[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) ptr[u] = dwi + vox + (int64_t)u * pitch;
+        const int64_t step = (int64_t)UNROLL * pitch;
         int j = 0;
         for (; j + UNROLL <= nvol; j += UNROLL) {
             float s[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) s[u] = __ldg(src + (int64_t)(j + u) * pitch);
+            for (int u = 0; u < UNROLL; ++u) { s[u] = __ldg(ptr[u]); ptr[u] += step; }
+            const int before = npos;
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                bool pos = s[u] > 0.f;
-                npos += pos;
-                b0pos |= pos && sb0[j + u];
-                float lg = pos ? logf(s[u]) : 0.f;
+            for (int u = 0; u < UNROLL; ++u) sample(s[u], j + u);
+            if (npos - before != UNROLL) {                          // rare: remember which samples were dropped
 #pragma unroll
-                for (int k = 0; k < NC; ++k) d[k] = fmaf(spa[k * nvol + j + u], lg, d[k]);
+                for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) { if (nrem < RMAX) rem[nrem] = j + u; ++nrem; }
             }
         }
-        for (; j < nvol; ++j) {
-            float s = __ldg(src + (int64_t)j * pitch);
-            bool pos = s > 0.f;
-            npos += pos;
-            b0pos |= pos && sb0[j];
-            float lg = pos ? logf(s) : 0.f;
-#pragma unroll
-            for (int k = 0; k < NC; ++k) d[k] = fmaf(spa[k * nvol + j], lg, d[k]);
+        for (int u = 0; j < nvol; ++j, ++u) {
+            const float sv = __ldg(ptr[0] + (int64_t)u * pitch);
+            sample(sv, j);
+            if (!(sv > 0.f)) { if (nrem < RMAX) rem[nrem] = j; ++nrem; }
         }
     }
+    const bool b0pos = b0acc > 0.f;
     const bool full = inside && npos == nvol;                       // src/dti.jl:294
-    const bool part = inside && !full && npos > 6 && b0pos;         // :297 (ADC keeps the same rule, :206)
-    if (full) {
+    bool part = inside && !full && npos > 6 && b0pos;               // :297 (ADC keeps the same rule, :206)
+    bool solved = full;
+    if (odd >= 0x7F000000u && (full || part)) { solved = false; part = true; nrem = RMAX + 1; }   // denormal / inf sample: exact-log path
+    if (part && nrem <= RMAX) {
+        // rank-nrem downdate in float64
+        double S[RMAX][RMAX], z[RMAX];
+        for (int i = 0; i < nrem; ++i) {
+            const float* ai = design + (size_t)rem[i] * NC;
+            double r = 0;
+            for (int k = 0; k < NC; ++k) r += (double)ai[k] * (double)d[k];
+            z[i] = r;                                                // U' x0
+            for (int jj = 0; jj < nrem; ++jj) {
+                const float* pj = spa + rem[jj] * CW;
+                double t = 0;
+                for (int k = 0; k < NC; ++k) t += (double)ai[k] * (double)pj[k];
+                S[i][jj] = (i == jj ? 1.0 : 0.0) - t;                // I - U' P_r
+            }
+        }
+        bool ok = true;
+        for (int c = 0; c < nrem && ok; ++c) {                       // Gaussian elimination, partial pivoting
+            int piv = c; double best = fabs(S[c][c]);
+            for (int i = c + 1; i < nrem; ++i) if (fabs(S[i][c]) > best) { best = fabs(S[i][c]); piv = i; }
+            if (!(best > 1e-9)) { ok = false; break; }               // (near-)singular downdate: general path decides
+            if (piv != c) { for (int k = 0; k < nrem; ++k) { double t = S[c][k]; S[c][k] = S[piv][k]; S[piv][k] = t; } double t = z[c]; z[c] = z[piv]; z[piv] = t; }
+            const double inv = 1.0 / S[c][c];
+            for (int i = c + 1; i < nrem; ++i) {
+                const double f = S[i][c] * inv;
+                for (int k = c; k < nrem; ++k) S[i][k] -= f * S[c][k];
+                z[i] -= f * z[c];
+            }
+        }
+        if (ok) {
+            for (int c = nrem - 1; c >= 0; --c) {
+                double t = z[c];
+                for (int k = c + 1; k < nrem; ++k) t -= S[c][k] * z[k];
+                z[c] = t / S[c][c];
+            }
+            double acc[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) acc[k] = (double)d[k];
+            for (int i = 0; i < nrem; ++i) {
+                const float* pj = spa + rem[i] * CW;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) acc[k] += (double)pj[k] * z[i];
+            }
+#pragma unroll
+            for (int k = 0; k < NC; ++k) d[k] = (float)acc[k];
+            solved = true; part = false;
+        }
+    }
+    if (solved) {
         if (NC == 7) dti_finish(d, vox, out);
         else { adc[vox] = d[0]; adc_s0[vox] = expf(d[1]); }
     } else {
@@ -331,11 +424,11 @@ int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_
     int rc = ensure_list(p, nvox);
     if (rc) return rc;
     FB_CUDA(cudaMemsetAsync(p->d_count, 0, sizeof(int), st));
-    size_t smem = sizeof(float) * NC * p->nvol + p->nvol;
+    size_t smem = sizeof(float) * CW * p->nvol + p->nvol + 16;
     if (smem > 48 * 1024)
         FB_CUDA(cudaFuncSetAttribute(fit_full_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)((nvox + DTI_THREADS - 1) / DTI_THREADS);
-    fit_full_kernel<NC><<<blocks, DTI_THREADS, smem, st>>>(d_dwi, dwi_pitch, d_mask, nvox, p->nvol, p->d_pinv,
+    fit_full_kernel<NC><<<blocks, DTI_THREADS, smem, st>>>(d_dwi, dwi_pitch, d_mask, nvox, p->nvol, p->d_pinv, p->d_design,
                                                            p->d_ib0, out, adc, adc_s0, p->d_list, p->d_count);
     // The partial path is rare: a fixed 4-CTA-per-SM grid strides over the device-side list
     // (no host sync needed to learn the count).  64-thread blocks: heavy per-thread state.
