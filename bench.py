@@ -196,26 +196,26 @@ def run_cpu_reference(shape, steps, warmup, nz_sample=None, budget_s=12.0):
     import fibers_oracle as O
     bval, bvec = make_tables()
     v, f = O.load_sphere(642)
-    cores = CO.max_threads()
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)   # torchrun pins OMP_NUM_THREADS=1: ask for all cores explicitly
     setup = CO.GqiSetup(bval, bvec, v, f, 1.25)
     nx, ny, nz = shape
     if nz_sample is None:
         # calibrate on one slice, then size the sample for ~budget_s of CPU work in total
         dwi, mask = cpu_sample(shape, bval, bvec, 1, 7)
         outs = CO._recon_outputs(nx, ny, 1, 321)
-        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
-        t = time.perf_counter(); CO.gqi_rec(dwi, mask, setup=setup, outputs=outs); dt = time.perf_counter() - t
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs, nthreads=cores)
+        t = time.perf_counter(); CO.gqi_rec(dwi, mask, setup=setup, outputs=outs, nthreads=cores); dt = time.perf_counter() - t
         nz_sample = int(max(cores, min(nz, budget_s / max(dt, 1e-6) / max(1, steps + warmup))))
         nz_sample = max(cores, nz_sample // cores * cores)      # static z partition: keep threads balanced
     dwi, mask = cpu_sample(shape, bval, bvec, nz_sample, 11)
     outs = CO._recon_outputs(nx, ny, nz_sample, 321)
     for _ in range(warmup):
-        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
         for o in (outs[0], *outs[1], *outs[2]):
             o.fill(0)                                   # the reference allocates zero-filled outputs per call
-        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs)
+        CO.gqi_rec(dwi, mask, setup=setup, outputs=outs, nthreads=cores)
     dt = (time.perf_counter() - t0) / steps
     nv = nx * ny * nz_sample
     return nv / dt, dt * 1e3, cores, f"z-sub-slab {nx}x{ny}x{nz_sample} of {nx}x{ny}x{nz} ({nv} voxels/step), C/OpenMP port of the reference loop, {cores} threads"
@@ -367,7 +367,7 @@ def main():
                              "algorithmic_tflops": 2.0 * nvol * M_VERT * nvox / (kern_ms * 1e-3) / 1e12}}
         if e2e:
             line["e2e"] = e2e
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:              # reported baseline: rank 0 at N = 1 only
             vps, ms, cores, sample = run_cpu_reference(shape, 2, 1, budget_s=12.0)
             line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
