@@ -44,6 +44,7 @@ SIGNATURES = {
     "fibers_cuda_last_error": (C.c_char_p, []),
     "fibers_cuda_set_devices": (_i, [_p, _i]),
     "fibers_cuda_set_kernel": (_i, [_i]),
+    "fibers_cuda_release_cache": (None, []),
     "fibers_dti_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 11 + [_i]),
     "fibers_adc_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _i]),
     "fibers_gqi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _f] + [_p] * 8 + [_i]),

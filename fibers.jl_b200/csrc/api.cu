@@ -353,6 +353,7 @@ struct HostJob {
     int64_t nvox, nxny; int nz;
     const void* dwi; const uint8_t* mask;
     std::function<int(Plan**, int)> make_plan;
+    uint64_t plan_key = 0;                          // hash of everything the plan depends on (context cache)
     // outputs (host)
     std::vector<std::pair<void*, int>> out_f32;     // (ptr, nframes) float outputs in kernel order
     float* qa[3] = {nullptr, nullptr, nullptr};
@@ -372,6 +373,24 @@ struct Rendezvous {       // cross-shard reduction of odfmax (host side; no devi
     }
 };
 
+// Per-device context cache: streams, slab ring, QA scratch and the last plan survive between host
+// calls (a batch of subjects with one protocol pays for set-up once).  One call at a time may own a
+// device's cache; concurrent calls on the same device fall back to private allocations.
+struct DeviceCache {
+    std::mutex mu; bool busy = false;
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
+    char* slab[3] = {nullptr, nullptr, nullptr}; size_t slab_bytes = 0;
+    float* qa = nullptr; size_t qa_bytes = 0; int32_t* stats = nullptr;
+    Plan* plan = nullptr; uint64_t plan_key = 0;
+};
+static DeviceCache g_cache[64];
+
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
 #define W_CUDA(expr)                                                                          \
     do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                    \
         err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
@@ -384,6 +403,11 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
     cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
     char* slab[NSLOT] = {nullptr, nullptr, nullptr};
     float* d_qa_all = nullptr; int32_t* d_stats = nullptr;
+    DeviceCache* dc = nullptr;
+    if (device >= 0 && device < 64) {
+        std::lock_guard<std::mutex> lk(g_cache[device].mu);
+        if (!g_cache[device].busy) { g_cache[device].busy = true; dc = &g_cache[device]; }
+    }
     const int64_t n = sh.v1 - sh.v0;
     const bool recon = job.kind == PLAN_GQI || job.kind == PLAN_DSI;
     bool reached_rv = false;
@@ -392,8 +416,13 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
     {
         W_CUDA(cudaSetDevice(device));
         if (n > 0) {
-            code = job.make_plan(&plan, device);
-            if (code) { err = g_err; goto done; }
+            if (dc && dc->plan && dc->plan_key == job.plan_key && job.plan_key != 0) plan = dc->plan;
+            else {
+                if (dc && dc->plan) { plan_free(dc->plan); dc->plan = nullptr; }
+                code = job.make_plan(&plan, device);
+                if (code) { err = g_err; goto done; }
+                if (dc) { dc->plan = plan; dc->plan_key = job.plan_key; }
+            }
             // per-voxel device bytes of one pipeline slot
             int out_frames = 0;
             for (auto& o : job.out_f32) out_frames += o.second;
@@ -405,13 +434,33 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
             while (chunk > 4096 && (double)chunk * per_vox * NSLOT > 0.6 * (double)free_b) chunk /= 2;
             chunk = (chunk + 63) / 64 * 64;
             const int64_t cp = chunk;                  // device pitch (elements) inside a slot
-            for (int s = 0; s < NSLOT; ++s) {
-                W_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-                W_CUDA(cudaMalloc(&slab[s], (size_t)(per_vox * cp + 1024)));
+            const size_t slab_need = (size_t)(per_vox * cp + 1024);
+            if (dc) {
+                for (int s = 0; s < NSLOT; ++s) if (!dc->st[s]) W_CUDA(cudaStreamCreateWithFlags(&dc->st[s], cudaStreamNonBlocking));
+                if (dc->slab_bytes < slab_need) {
+                    for (int s = 0; s < NSLOT; ++s) { if (dc->slab[s]) cudaFree(dc->slab[s]); dc->slab[s] = nullptr; }
+                    dc->slab_bytes = 0;
+                    for (int s = 0; s < NSLOT; ++s) W_CUDA(cudaMalloc(&dc->slab[s], slab_need));
+                    dc->slab_bytes = slab_need;
+                }
+                for (int s = 0; s < NSLOT; ++s) { st[s] = dc->st[s]; slab[s] = dc->slab[s]; }
+            } else {
+                for (int s = 0; s < NSLOT; ++s) {
+                    W_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
+                    W_CUDA(cudaMalloc(&slab[s], slab_need));
+                }
             }
             if (recon) {
-                W_CUDA(cudaMalloc(&d_qa_all, sizeof(float) * 3 * (size_t)n));
-                W_CUDA(cudaMalloc(&d_stats, 2 * sizeof(int32_t)));
+                const size_t qa_need = sizeof(float) * 3 * (size_t)n;
+                if (dc) {
+                    if (dc->qa_bytes < qa_need) { if (dc->qa) cudaFree(dc->qa); dc->qa = nullptr; dc->qa_bytes = 0;
+                                                   W_CUDA(cudaMalloc(&dc->qa, qa_need)); dc->qa_bytes = qa_need; }
+                    if (!dc->stats) W_CUDA(cudaMalloc(&dc->stats, 2 * sizeof(int32_t)));
+                    d_qa_all = dc->qa; d_stats = dc->stats;
+                } else {
+                    W_CUDA(cudaMalloc(&d_qa_all, qa_need));
+                    W_CUDA(cudaMalloc(&d_stats, 2 * sizeof(int32_t)));
+                }
                 code = launch_stats_init(d_stats, st[0]);
                 if (code) { err = g_err; goto done; }
                 W_CUDA(cudaStreamSynchronize(st[0]));
@@ -492,10 +541,16 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
     }
 done:
     if (recon && !reached_rv) rv->wait_max(-INFINITY, false);
-    for (int s = 0; s < NSLOT; ++s) { if (slab[s]) cudaFree(slab[s]); if (st[s]) cudaStreamDestroy(st[s]); }
-    if (d_qa_all) cudaFree(d_qa_all);
-    if (d_stats) cudaFree(d_stats);
-    if (plan) plan_free(plan);
+    if (dc) {                                            // everything stays in the cache for the next call
+        if (code) for (int s = 0; s < NSLOT; ++s) if (dc->st[s]) cudaStreamSynchronize(dc->st[s]);
+        std::lock_guard<std::mutex> lk(dc->mu);
+        dc->busy = false;
+    } else {
+        for (int s = 0; s < NSLOT; ++s) { if (slab[s]) cudaFree(slab[s]); if (st[s]) cudaStreamDestroy(st[s]); }
+        if (d_qa_all) cudaFree(d_qa_all);
+        if (d_stats) cudaFree(d_stats);
+        if (plan) plan_free(plan);
+    }
     *out_code = code; *out_err = err;
 }
 
@@ -524,6 +579,22 @@ static int run_host_job(const HostJob& job, int ngpu) {
 }  // namespace fibers
 
 extern "C" {
+
+void fibers_cuda_release_cache(void) {
+    for (int d = 0; d < 64; ++d) {
+        DeviceCache& c = g_cache[d];
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.busy) continue;
+        bool any = c.plan || c.qa || c.stats || c.slab[0] || c.st[0];
+        if (!any) continue;
+        int cur = 0; cudaGetDevice(&cur); cudaSetDevice(d);
+        for (int s = 0; s < 3; ++s) { if (c.slab[s]) cudaFree(c.slab[s]); if (c.st[s]) cudaStreamDestroy(c.st[s]); c.slab[s] = nullptr; c.st[s] = nullptr; }
+        if (c.qa) cudaFree(c.qa); if (c.stats) cudaFree(c.stats);
+        if (c.plan) plan_free(c.plan);
+        c.qa = nullptr; c.stats = nullptr; c.plan = nullptr; c.slab_bytes = c.qa_bytes = 0; c.plan_key = 0;
+        cudaSetDevice(cur);
+    }
+}
 
 int fibers_host_build_matrix(int kind, int nvol, const float* bval, const float* bvec, const float* vertices,
                              int nvert2, float sigma, int hann_width, float* out, int64_t capacity, int* cvol,
@@ -581,6 +652,7 @@ int fibers_dti_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
     job.make_plan = [=](Plan** p, int dev) {
         return fibers_dti_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval, bvec);
     };
+    job.plan_key = fnv1a(fnv1a(fnv1a(1469598103934665603ull, "dti", 3), bval, sizeof(float) * nvol), bvec, sizeof(float) * 3 * nvol);
     return run_host_job(job, ngpu);
 }
 
@@ -597,6 +669,7 @@ int fibers_adc_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
     job.make_plan = [=](Plan** p, int dev) {
         return fibers_adc_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval);
     };
+    job.plan_key = fnv1a(fnv1a(1469598103934665603ull, "adc", 3), bval, sizeof(float) * nvol);
     return run_host_job(job, ngpu);
 }
 
@@ -623,6 +696,14 @@ static int recon_host(int kind, const void* dwi, int dwi_dtype, const uint8_t* m
             ? fibers_gqi_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval, bvec, vertices, nvert2, faces, nface, sigma)
             : fibers_dsi_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval, bvec, vertices, nvert2, faces, nface, hann_width);
     };
+    if (vertices && faces && nvert2 > 0 && nface > 0) {
+        uint64_t h = fnv1a(1469598103934665603ull, kind == PLAN_GQI ? "gqi" : "dsi", 3);
+        h = fnv1a(h, bval, sizeof(float) * nvol); h = fnv1a(h, bvec, sizeof(float) * 3 * nvol);
+        h = fnv1a(h, vertices, sizeof(float) * 3 * (size_t)nvert2); h = fnv1a(h, faces, sizeof(int32_t) * 3 * (size_t)nface);
+        h = fnv1a(h, &sigma, sizeof(sigma)); h = fnv1a(h, &hann_width, sizeof(hann_width));
+        const int kc = kernel_choice(); h = fnv1a(h, &kc, sizeof(kc));
+        job.plan_key = h;
+    }
     return run_host_job(job, ngpu);
 }
 

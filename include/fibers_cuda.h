@@ -67,6 +67,9 @@ const char* fibers_cuda_last_error(void);              /* thread-local, never NU
 /* Device ordinals used by the host entry points for shards 0..n-1 (default 0,1,2,...; the env
  * var FIBERS_CUDA_DEVICES="3,1" is read at first use). */
 int         fibers_cuda_set_devices(const int* devices, int n);
+/* The host entry points keep per-device streams, slab buffers and the last plan between calls (a batch
+ * of subjects with one protocol pays for set-up once); this frees them (optional, e.g. before exit). */
+void        fibers_cuda_release_cache(void);
 /* Force a reconstruction kernel for subsequently created plans / host calls (FIBERS_KERNEL_*). */
 int         fibers_cuda_set_kernel(int kernel);
 
