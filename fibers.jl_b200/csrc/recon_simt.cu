@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NT, (J <= 23 ? 2 : 1)) recon_simt_kernel(const
     if (p.tile_list == nullptr) { simt_tile<J, ODF>(p, blockIdx.x, blockIdx.y); return; }
     const int n = min(*p.tile_count, p.tile_cap);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        simt_tile<J, ODF>(p, p.tile_list[i], 0);
+        simt_tile<J, ODF>(p, p.tile_list[i], blockIdx.y);
         __syncthreads();
     }
 }
@@ -266,7 +266,7 @@ int launch_one(const SimtParams& sp, int npanels, cudaStream_t st) {
     size_t smem = simt_smem<J, ODF>(sp.M);
     FB_CUDA(cudaFuncSetAttribute(recon_simt_kernel<J, ODF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((sp.nvox + VT - 1) / VT), (unsigned)npanels);
-    if (sp.tile_list) grid = dim3((unsigned)std::min<int64_t>((sp.nvox + VT - 1) / VT, 148 * 2), 1);
+    if (sp.tile_list) grid = dim3((unsigned)std::min<int64_t>((sp.nvox + VT - 1) / VT, 148 * 2), (unsigned)npanels);
     recon_simt_kernel<J, ODF><<<grid, NT, smem, st>>>(sp);
     count_launch(1);
     FB_CUDA(cudaGetLastError());
@@ -312,7 +312,7 @@ static int launch_recon_simt_impl(Plan* p, const ReconArgs& a, const int* d_list
     else if (M <= 16 * 32) rc = launch_one<32, true>(sp, 1, st);
     else return fail(FIBERS_ERR_ARG, "ODF tessellations with more than 512 half-sphere vertices are not supported");
     if (rc) return rc;
-    if (p->kind == PLAN_DSI && a.pdf && !d_list) {
+    if (p->kind == PLAN_DSI && a.pdf) {
         // pdf rows: matrix rows M .. M+nvol-1.  Row panels must start on a 16-row boundary of the
         // padded matrix; the plan stores Mp starting at row_pdf = round_up(M, 16).
         SimtParams pp = sp;

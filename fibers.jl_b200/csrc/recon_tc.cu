@@ -67,14 +67,25 @@ struct TcParams {
     int ntiles;                  // 256-voxel tiles
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
     int odf_tma, odf_box_rows, odf_nbox;   // ODF tile leaves through TMA stores of the staged tile (else per-thread STG)
+    int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
+    int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
-struct TcState {
+// One launch of the kernel covers at most 336 matrix rows (TMEM columns).  GQI: a single pass (the ODF
+// rows).  DSI: the ODF rows, then the pdf rows in passes of <= 336 (plain mode).
+struct TcPass {
     __half* d_split = nullptr;   // [2 ranks][hi Nh rows | lo Nh rows][Kpad]
     CUtensorMap tmap;
+    int rows = 0, row0 = 0;      // matrix rows [row0, row0 + rows) of the plan's matrix
+    int Npad = 0, N1 = 0, N2 = 0;
+    int plain = 0;               // 1: pdf rows
+};
+
+struct TcState {
+    std::vector<TcPass> pass;
     void* encode = nullptr;      // cuTensorMapEncodeTiled
-    int Kpad = 0, Npad = 0, N1 = 0, N2 = 0, nbw = 8;
+    int Kpad = 0, nbw = 8;
     unsigned long long uid = 0;              // identifies the neighbour table in the per-device constant-memory cache
     std::vector<uint32_t> h_nbr_off;         // [M + 1][NBR_W] byte offsets
     size_t smem = 0;
@@ -382,6 +393,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool vok = vox < p.nvox;
+            // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol]; rows of voxels that are not computed
+            // (all accumulators exactly 0) stay 0 instead of 0 * inf
+            float inv_den = 1.f;
+            if (p.cvol >= 0) inv_den = 1.f / (p.dscale * fmaxf(vok ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f, 0.f));
             for (int i = et; i < 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
             mbar_wait<true>(d_full, it & 1);
             tc_fence_after();
@@ -396,7 +411,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     if (c0 + 16 <= M) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float val = __uint_as_float(r[j]) * inv_scale;
+                            float val = __uint_as_float(r[j]) * inv_scale;
+                            if (p.cvol >= 0) val = val == 0.f ? 0.f : val * inv_den;
                             sp[j * VOX_CTA] = val;
                             if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                             mn = fminf(mn, val); sum += val;
@@ -405,7 +421,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if (c0 + j < M) {
-                                const float val = __uint_as_float(r[j]) * inv_scale;
+                                float val = __uint_as_float(r[j]) * inv_scale;
+                                if (p.cvol >= 0) val = val == 0.f ? 0.f : val * inv_den;
                                 sp[j * VOX_CTA] = val;
                                 if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                                 mn = fminf(mn, val); sum += val;
@@ -447,6 +464,11 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 __syncwarp();
             }
             if (warp == W_EPI0) TRACE(4);
+            if (p.plain) {                                              // rows only (DSI pdf): the tile is on its way out
+                if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                named_bar(1, EPI_THREADS);
+                continue;
+            }
             // ---- phase 2: local maxima of the folded mesh (strictly greater than every neighbour, > 0)
             //      4 voxels per thread (float4 rows), every shared-memory load issued up front ----
             float tv[4][3]; int ti[4][3];
@@ -587,43 +609,35 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
 
 }  // namespace
 
-// Decide whether the tensor-core kernel can take this plan; build the split fp16 operand and its
-// tensor map.  Returns 0 when usable.
-int tc_plan_init(Plan* p) {
-    if (p->kind != PLAN_GQI) { set_error("tensor-core path: GQI only (DSI uses the SIMT kernel)"); return 1; }
-    const int M = p->nvert, K = p->nvol;
-    const int Npad = (M + 15) / 16 * 16;
-    if (Npad > TMEM_A_COL || M + 1 > TC_MAX_VERT) { set_error("tensor-core path: more than 384 half-sphere vertices"); return 1; }
-    int N1 = Npad, N2 = 0;
+// Decide whether the tensor-core kernel can take this plan; build the split fp16 operands and their
+// tensor maps.  Returns 0 when usable.
+static void split_dims(int rows, int& Npad, int& N1, int& N2) {
+    Npad = (rows + 15) / 16 * 16; N1 = Npad; N2 = 0;
     if (Npad > 256) { N1 = (Npad / 2 + 15) / 16 * 16; N2 = Npad - N1; }
-    const int Nh = (N1 + N2) / 2, N1h = N1 / 2, N2h = N2 / 2;
-    if (Nh > 256) { set_error("tensor-core path: TMA box too tall"); return 1; }
-    const size_t smem = tc_smem_bytes(M, Nh);
-    int dev_smem = 0;
-    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess ||
-        smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); return 1; }
+}
+
+static void tc_state_free(TcState* st) {
+    if (!st) return;
+    for (auto& ps : st->pass) cudaFree(ps.d_split);
+    cudaFree(st->d_scratch);
+    delete st;
+}
+
+int tc_plan_init(Plan* p) {
+    if (p->kind != PLAN_GQI && p->kind != PLAN_DSI) { set_error("tensor-core path: GQI / DSI plans only"); return 1; }
+    const int M = p->nvert, K = p->nvol;
+    if ((M + 15) / 16 * 16 > 336 || M + 1 > TC_MAX_VERT) { set_error("tensor-core path: more than 336 half-sphere vertices"); return 1; }
+    if (p->kind == PLAN_DSI && p->cvol < 0) { set_error("tensor-core path: DSI without a q-space origin sample"); return 1; }
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device);
     if (cc_major != 10) { set_error("tensor-core path needs sm_100"); return 1; }
-    const int Kpad = (K + 31) / 32 * 32;
-    // split operand, row order: rank 0 [hi: blk1 rows 0..N1h, blk2 rows 0..N2h][lo: same], then rank 1
-    std::vector<__half> split((size_t)4 * Nh * Kpad, __float2half(0.f));
-    auto row_of = [&](int n, int& rank, int& local) {
-        if (n < N1) { rank = n / N1h; local = n % N1h; }
-        else { int m = n - N1; rank = m / N2h; local = N1h + m % N2h; }
-    };
-    for (int n = 0; n < M; ++n) {
-        int rank, local; row_of(n, rank, local);
-        for (int k = 0; k < K; ++k) {
-            const float a = p->h_matrix[(size_t)n * K + k];
-            const __half h = __float2half_rn(a);
-            const __half l = __float2half_rn(a - __half2float(h));
-            split[((size_t)rank * 2 * Nh + local) * Kpad + k] = h;
-            split[((size_t)rank * 2 * Nh + Nh + local) * Kpad + k] = l;
-        }
+    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        set_error("tensor-core path: cuTensorMapEncodeTiled unavailable"); cudaGetLastError(); return 1;
     }
+    const int Kpad = (K + 31) / 32 * 32;
     TcState* st = new TcState();
-    st->Kpad = Kpad; st->Npad = Npad; st->N1 = N1; st->N2 = N2; st->smem = smem; st->nbw = p->nbr_width;
+    st->Kpad = Kpad; st->nbw = p->nbr_width; st->encode = fn;
     st->uid = g_next_uid.fetch_add(1);
     st->h_nbr_off.assign((size_t)(M + 1) * NBR_W, (uint32_t)M * 512u);          // sentinel row M everywhere ...
     for (int v = 0; v < M; ++v)
@@ -631,35 +645,58 @@ int tc_plan_init(Plan* p) {
             const uint16_t n = p->h_nbr[(size_t)v * NBR_W + k];
             if (n != NBR_NONE) st->h_nbr_off[(size_t)v * NBR_W + k] = (uint32_t)n * 512u;
         }
-    if (cudaMalloc(&st->d_split, split.size() * sizeof(__half)) != cudaSuccess ||
-        cudaMemcpy(st->d_split, split.data(), split.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("tensor-core path: device allocation failed"); cudaGetLastError(); delete st; return 1;
+    // passes: ODF rows, then (DSI) the pdf rows in blocks of <= 336
+    std::vector<std::pair<int, int>> ranges = {{0, M}};
+    if (p->kind == PLAN_DSI) for (int r0 = 0; r0 < K; r0 += 336) ranges.push_back({M + r0, std::min(336, K - r0)});
+    size_t smem = 0;
+    for (size_t i = 0; i < ranges.size(); ++i) {
+        TcPass ps;
+        ps.row0 = ranges[i].first; ps.rows = ranges[i].second; ps.plain = i > 0;
+        split_dims(ps.rows, ps.Npad, ps.N1, ps.N2);
+        const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
+        smem = std::max(smem, tc_smem_bytes(ps.rows, Nh));
+        // split operand, row order: rank 0 [hi: blk1 rows 0..N1h, blk2 rows 0..N2h][lo: same], then rank 1
+        std::vector<__half> split((size_t)4 * Nh * Kpad, __float2half(0.f));
+        for (int n = 0; n < ps.rows; ++n) {
+            int rank, local;
+            if (n < ps.N1) { rank = n / N1h; local = n % N1h; }
+            else { const int m = n - ps.N1; rank = m / N2h; local = N1h + m % N2h; }
+            const float* src = p->h_matrix.data() + (size_t)(ps.row0 + n) * K;
+            for (int k = 0; k < K; ++k) {
+                const __half h = __float2half_rn(src[k]);
+                const __half l = __float2half_rn(src[k] - __half2float(h));
+                split[((size_t)rank * 2 * Nh + local) * Kpad + k] = h;
+                split[((size_t)rank * 2 * Nh + Nh + local) * Kpad + k] = l;
+            }
+        }
+        if (cudaMalloc(&ps.d_split, split.size() * sizeof(__half)) != cudaSuccess ||
+            cudaMemcpy(ps.d_split, split.data(), split.size() * sizeof(__half), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("tensor-core path: device allocation failed"); cudaGetLastError(); tc_state_free(st); return 1;
+        }
+        st->pass.push_back(ps);
+        cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)(4 * Nh)};
+        cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
+        cuuint32_t box[2] = {16, (cuuint32_t)Nh};
+        cuuint32_t estr[2] = {1, 1};
+        if (((EncodeFn)fn)(&st->pass.back().tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ps.d_split, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            set_error("tensor-core path: cuTensorMapEncodeTiled failed"); tc_state_free(st); return 1;
+        }
     }
-    void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-        set_error("tensor-core path: cuTensorMapEncodeTiled unavailable"); cudaGetLastError(); cudaFree(st->d_split); delete st; return 1;
-    }
-    cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)(4 * Nh)};
-    cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
-    cuuint32_t box[2] = {16, (cuuint32_t)Nh};
-    cuuint32_t estr[2] = {1, 1};
-    st->encode = fn;
-    CUresult r = ((EncodeFn)fn)(&st->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, st->d_split, gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("tensor-core path: cuTensorMapEncodeTiled failed"); cudaFree(st->d_split); delete st; return 1; }
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess ||
+        smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
+    st->smem = smem;
     if (cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); cudaFree(st->d_split); delete st; return 1;
+        set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); tc_state_free(st); return 1;
     }
     p->tc = st;
     return 0;
 }
 
 void tc_plan_free(Plan* p) {
-    TcState* st = reinterpret_cast<TcState*>(p->tc);
-    if (!st) return;
-    cudaFree(st->d_split); cudaFree(st->d_scratch);
-    delete st;
+    tc_state_free(reinterpret_cast<TcState*>(p->tc));
     p->tc = nullptr;
 }
 
@@ -689,56 +726,64 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
     sample_max_kernel<<<nsm * 8, 256, 0, stream>>>(a.dwi, a.dwi_pitch, a.nvox, p->nvol, st->d_scratch);
-    TcParams tp{};
-    tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
-    tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = p->nvert; tp.Npad = st->Npad; tp.N1 = st->N1; tp.N2 = st->N2;
-    tp.odf = a.odf; tp.out_pitch = a.out_pitch;
-    for (int k = 0; k < 3; ++k) { tp.peak[k] = a.peak[k]; tp.qa[k] = a.qa[k]; }
-    tp.peak_idx = a.peak_idx; tp.stats = a.stats; tp.nbr = p->d_nbr; tp.vert = p->d_vert;
-    tp.maxbits = st->d_scratch; tp.fix_count = st->d_scratch + 1; tp.fix_list = st->d_scratch + 2;
-    tp.fix_cap = (int)(2 * ntile64);
-    tp.ntiles = (int)((a.nvox + 255) / 256);
-    tp.nbw = st->nbw;
-    // ODF output tensor map (per call: pointer / pitch belong to the caller).  TMA needs a 16-byte aligned
-    // base and row pitch; otherwise the epilogue falls back to per-thread coalesced stores.
-    CUtensorMap tmapO; memset(&tmapO, 0, sizeof(tmapO));
-    tp.odf_tma = 0;
-    {
-        const int nbox = (p->nvert + 255) / 256, rows = (p->nvert + nbox - 1) / nbox;
-        const bool aligned = ((uintptr_t)a.odf % 16 == 0) && ((a.out_pitch * 4) % 16 == 0) && a.nvox < (1ll << 31);
-        const char* env = getenv("FIBERS_TC_ODF_TMA");
-        if (aligned && nbox * rows <= p->nvert + 1 && !(env && env[0] == '0')) {
-            cuuint64_t gdim[2] = {(cuuint64_t)a.nvox, (cuuint64_t)p->nvert};
-            cuuint64_t gstr[1] = {(cuuint64_t)a.out_pitch * 4};
-            cuuint32_t box[2] = {(cuuint32_t)VOX_CTA, (cuuint32_t)rows};
-            cuuint32_t estr[2] = {1, 1};
-            if (st->encode && ((EncodeFn)st->encode)(&tmapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.odf, gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-                tp.odf_tma = 1; tp.odf_box_rows = rows; tp.odf_nbox = nbox;
+    count_launch(1);
+    const char* trace_path = getenv("FIBERS_TC_TRACE");
+    for (size_t ip = 0; ip < st->pass.size(); ++ip) {
+        const TcPass& ps = st->pass[ip];
+        float* out = ps.plain ? a.pdf + (int64_t)(ps.row0 - p->nvert) * a.out_pitch : a.odf;
+        if (ps.plain && !a.pdf) continue;
+        TcParams tp{};
+        tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
+        tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = ps.rows; tp.Npad = ps.Npad; tp.N1 = ps.N1; tp.N2 = ps.N2;
+        tp.odf = out; tp.out_pitch = a.out_pitch;
+        for (int k = 0; k < 3; ++k) { tp.peak[k] = a.peak[k]; tp.qa[k] = a.qa[k]; }
+        tp.peak_idx = a.peak_idx; tp.stats = a.stats; tp.nbr = p->d_nbr; tp.vert = p->d_vert;
+        tp.maxbits = st->d_scratch; tp.fix_count = st->d_scratch + 1; tp.fix_list = st->d_scratch + 2;
+        tp.fix_cap = (int)(2 * ntile64);
+        tp.ntiles = (int)((a.nvox + 255) / 256);
+        tp.nbw = st->nbw;
+        tp.plain = ps.plain;
+        tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
+        // output tensor map (per call: pointer / pitch belong to the caller).  TMA needs a 16-byte aligned base
+        // and row pitch; otherwise the epilogue falls back to per-thread coalesced stores.
+        CUtensorMap tmapO; memset(&tmapO, 0, sizeof(tmapO));
+        tp.odf_tma = 0;
+        {
+            const int nbox = (ps.rows + 255) / 256, rows = (ps.rows + nbox - 1) / nbox;
+            const bool aligned = ((uintptr_t)out % 16 == 0) && ((a.out_pitch * 4) % 16 == 0) && a.nvox < (1ll << 31);
+            const char* env = getenv("FIBERS_TC_ODF_TMA");
+            if (aligned && nbox * rows <= ps.rows + 1 && !(env && env[0] == '0')) {
+                cuuint64_t gdim[2] = {(cuuint64_t)a.nvox, (cuuint64_t)ps.rows};
+                cuuint64_t gstr[1] = {(cuuint64_t)a.out_pitch * 4};
+                cuuint32_t box[2] = {(cuuint32_t)VOX_CTA, (cuuint32_t)rows};
+                cuuint32_t estr[2] = {1, 1};
+                if (((EncodeFn)st->encode)(&tmapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                    tp.odf_tma = 1; tp.odf_box_rows = rows; tp.odf_nbox = nbox;
+                }
             }
         }
-    }
-    const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
-    const char* trace_path = getenv("FIBERS_TC_TRACE");
-    long long* d_trace = nullptr;
-    if (trace_path && *trace_path) {
-        FB_CUDA(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
-        FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
-        tp.trace = d_trace;
-    }
-    recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, st->tmap, tmapO);
-    count_launch(2);
-    FB_CUDA(cudaGetLastError());
-    if (d_trace) {
-        std::vector<long long> h(16 * 32);
-        FB_CUDA(cudaStreamSynchronize(stream));
-        FB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        cudaFree(d_trace);
-        if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
+        const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
+        long long* d_trace = nullptr;
+        if (trace_path && *trace_path && ip == 0) {
+            FB_CUDA(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
+            FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
+            tp.trace = d_trace;
+        }
+        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, tmapO);
+        count_launch(1);
+        FB_CUDA(cudaGetLastError());
+        if (d_trace) {
+            std::vector<long long> h(16 * 32);
+            FB_CUDA(cudaStreamSynchronize(stream));
+            FB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            cudaFree(d_trace);
+            if (FILE* f = fopen(trace_path, "wb")) { fwrite(h.data(), sizeof(long long), h.size(), f); fclose(f); }
+        }
     }
     // voxels whose scaled signal overflowed fp16 (rare): recompute their 64-voxel tiles in fp32
-    return launch_recon_simt_list(p, a, tp.fix_list, tp.fix_count, stream);
+    return launch_recon_simt_list(p, a, st->d_scratch + 2, st->d_scratch + 1, stream);
 }
 
 }  // namespace fibers

@@ -128,7 +128,7 @@ def test_auto_selects_tensor_core_kernel(F):
     assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_362).kernel == "tc"
     assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_724).kernel == "simt"     # 362 half-sphere vertices: tile too big
     bq, gq = phantom.dsi_grid_table()
-    assert F.device.Plan("dsi", 0, bq, gq).kernel == "simt"
+    assert F.device.Plan("dsi", 0, bq, gq).kernel == "tc"
 
 
 @pytest.mark.parametrize("nsphere", [642, 362, 724])
@@ -248,7 +248,7 @@ def test_missing_tables_raise(F):
 
 
 # ---------------------------------------------------------------- DSI
-def test_dsi_parity(F, sphere642):
+def test_dsi_parity(F, sphere642, kernel):
     from fibers_jl_b200 import phantom
     v, f = sphere642
     ph = phantom.dsi_phantom((12, 10, 6), seed=3, mask_fill=0.7)

@@ -75,7 +75,7 @@ def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642):
     if kind == "gqi":
         report(f"gqi_rec {tag} [{plan.kernel}]", nvox, ms, 4 * N + 4 * M + 49, 2 * N * M)
     else:
-        report(f"dsi_rec {tag} [{plan.kernel}]", nvox, ms, 8 * N + 4 * M + 49, 2 * N * (M + N), "tensor-bound in matrix form; SIMT kernel for now")
+        report(f"dsi_rec {tag} [{plan.kernel}]", nvox, ms, 8 * N + 4 * M + 49, 2 * N * (M + N), "tensor-bound in matrix form (3 kernel passes: odf rows, 2 x pdf rows)")
 
 
 b1, g1 = phantom.shells_table(1, [(1000.0, 30)])
@@ -88,4 +88,5 @@ b5, g5 = phantom.shells_table(8, [(4000.0, 120)])
 run_recon("gqi", (400, 400, 38), b5, g5, "tc", "cfg5 slab 400x400x38x128 (1/8 of 400x400x300)")
 run_recon("gqi", (145, 174, 73), b2, g2, "tc", "cfg2 half volume, sphere_362", F.sphere_362)
 b3, g3 = phantom.dsi_grid_table()
+run_recon("dsi", (96, 96, 60), b3, g3, "tc", "cfg3 96x96x60x515")
 run_recon("dsi", (96, 96, 60), b3, g3, "simt", "cfg3 96x96x60x515")
