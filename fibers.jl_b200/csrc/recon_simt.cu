@@ -150,8 +150,9 @@ __device__ __forceinline__ void simt_tile(const SimtParams& p, const int64_t til
         int64_t vox = v0 + tx * 4 + c;
         float sc = s_pos[tx * 4 + c] ? 1.f : 0.f;       // mask == 0 or max(s+) == 0 -> untouched (zeros)
         if (sc != 0.f && p.cvol >= 0) {
-            float den = p.dscale * fmaxf(__ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox), 0.f);
-            sc = 1.f / den;                               // den == 0 -> inf/NaN like the reference
+            // q = 0 sample <= 0: zeros (the reference either skips the voxel or divides by zero: undefined)
+            const float den = p.dscale * fmaxf(vox < p.nvox ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f, 0.f);
+            sc = den > 0.f ? 1.f / den : 0.f;
         }
         scale[c] = sc;
     }

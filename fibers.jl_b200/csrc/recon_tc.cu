@@ -64,7 +64,8 @@ struct TcParams {
     const uint16_t* nbr; const float* vert;
     const int* maxbits;          // device: bit pattern of the sampled max(s) (>= 0)
     int* fix_list; int* fix_count; int fix_cap;
-    int ntiles;                  // 256-voxel tiles
+    int ntiles;                  // 256-voxel tiles of the slab
+    const int* tile_list; const int* tile_count;   // tiles that contain at least one mask voxel (built by tile_scan_kernel)
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
     int odf_tma, odf_box_rows, odf_nbox;   // ODF tile leaves through TMA stores of the staged tile (else per-thread STG)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
@@ -197,6 +198,51 @@ __global__ void sample_max_kernel(const float* __restrict__ dwi, int64_t pitch, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// tile scan: one CTA per 256-voxel tile.  Tiles without a single mask voxel are zero-filled here (the
+// reference leaves them at the zero of its MRI constructor) and never reach the reconstruction kernel;
+// the others are appended to the work list.  On a brain-masked volume this removes most of the tiles.
+// ---------------------------------------------------------------------------------------------
+struct ScanOut { float* ptr[9]; int rows[9]; int n; int16_t* idx; };
+
+__global__ void __launch_bounds__(256) tile_scan_kernel(const uint8_t* __restrict__ mask, int64_t nvox, int64_t out_pitch, ScanOut o,
+                                                         int32_t* stats, int* tile_flag) {
+    const int64_t vox = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int inside = vox < nvox && mask[vox] != 0;
+    if (__syncthreads_or(inside)) {
+        if (threadIdx.x == 0) tile_flag[blockIdx.x] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) tile_flag[blockIdx.x] = 0;
+    if (vox < nvox) {
+        for (int a = 0; a < o.n; ++a)
+            for (int r = 0; r < o.rows[a]; ++r) o.ptr[a][(int64_t)r * out_pitch + vox] = 0.f;
+        if (o.idx) for (int r = 0; r < 3; ++r) o.idx[(int64_t)r * out_pitch + vox] = (int16_t)-1;
+    }
+    if (threadIdx.x == 0 && stats) atomicMax(stats, f2ord(0.f));      // skipped voxels count as mean(odf) = 0 in odfmax
+}
+
+// ordered compaction of the non-empty tiles (one block; ascending tile order keeps the DWI / ODF streams of
+// neighbouring clusters adjacent in memory)
+__global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restrict__ flag, int ntiles, int* list, int* count) {
+    __shared__ int s_part[1024];
+    const int per = (ntiles + 1023) / 1024;
+    const int t0 = threadIdx.x * per, t1 = min(ntiles, t0 + per);
+    int c = 0;
+    for (int t = t0; t < t1; ++t) c += flag[t];
+    s_part[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                  // inclusive scan
+        int v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int pos = s_part[threadIdx.x] - c;
+    for (int t = t0; t < t1; ++t) if (flag[t]) list[pos++] = t;
+    if (threadIdx.x == 1023) *count = s_part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool elect_one() {          // one lane of a converged warp
@@ -215,6 +261,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     const uint32_t sub_bytes = (uint32_t)(2 * Nh * 32);          // one K16 sub-tile: hi rows then lo rows (SWIZZLE_32B)
     const uint32_t stage_bytes = 2 * sub_bytes;                  // K32 stage
     const int nk32 = p.Kpad >> 5;
+    const int ntl = min(*p.tile_count, p.ntiles);      // non-empty tiles; every role walks the same list
+    const bool ident = ntl == p.ntiles;                // nothing skipped: the list is the identity
 
     // ---- shared memory carve-up -------------------------------------------------------------
     // (pointer arithmetic on the __shared__ array itself, so that the compiler keeps the shared
@@ -265,7 +313,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         // (the whole warp runs the loop so that control flow stays uniform; one elected lane issues)
         const uint32_t full0 = mapa(smem_u32(&b_full[0]), 0);
         uint32_t g = 0, it = 0;
-        for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
+        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
+            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             TRACE(13);
             for (int c = 0; c < nk32; ++c, ++g) {
                 const int s = g % NSTAGE; const uint32_t use = g / NSTAGE;
@@ -290,7 +339,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             const uint32_t idesc1 = make_idesc_f16(256, p.N1);
             const uint32_t idesc2 = p.N2 ? make_idesc_f16(256, p.N2) : 0u;
             uint32_t g32 = 0, it = 0;
-            for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
+            for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {             // (this role only needs the tile count)
                 mbar_wait(d_empty, (it & 1) ^ 1);                    // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 TRACE(0);
@@ -338,7 +387,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t afull0 = mapa(smem_u32(&a_full[0]), 0);
         uint32_t it = 0;
-        for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
+        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
+            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool inside = vox < p.nvox && p.mask[vox] != 0;
             const float* src = p.dwi + vox;
@@ -390,13 +440,18 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         const int vper = (M + N_EPI - 1) / N_EPI;
         const int va = ew * vper, vb = min(M, va + vper);
         uint32_t it = 0;
-        for (int tile = cluster_id; tile < p.ntiles; tile += ncluster, ++it) {
+        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
+            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool vok = vox < p.nvox;
-            // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol]; rows of voxels that are not computed
-            // (all accumulators exactly 0) stay 0 instead of 0 * inf
-            float inv_den = 1.f;
-            if (p.cvol >= 0) inv_den = 1.f / (p.dscale * fmaxf(vok ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f, 0.f));
+            // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol], folded into the un-scale factor.
+            // A voxel whose q = 0 sample is <= 0 gets zeros: either it is skipped by the reference as well (all
+            // samples <= 0) or the reference divides by zero there (undefined; excluded from parity).
+            float scl = inv_scale;
+            if (p.cvol >= 0) {
+                const float sc = vok ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f;
+                scl = sc > 0.f ? inv_scale * (1.f / (p.dscale * sc)) : 0.f;     // inv_scale is a power of two: exact
+            }
             for (int i = et; i < 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
             mbar_wait<true>(d_full, it & 1);
             tc_fence_after();
@@ -411,8 +466,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     if (c0 + 16 <= M) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float val = __uint_as_float(r[j]) * inv_scale;
-                            if (p.cvol >= 0) val = val == 0.f ? 0.f : val * inv_den;
+                            const float val = __uint_as_float(r[j]) * scl;
                             sp[j * VOX_CTA] = val;
                             if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                             mn = fminf(mn, val); sum += val;
@@ -421,8 +475,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if (c0 + j < M) {
-                                float val = __uint_as_float(r[j]) * inv_scale;
-                                if (p.cvol >= 0) val = val == 0.f ? 0.f : val * inv_den;
+                                const float val = __uint_as_float(r[j]) * scl;
                                 sp[j * VOX_CTA] = val;
                                 if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
                                 mn = fminf(mn, val); sum += val;
@@ -705,15 +758,16 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     if (!st) return fail(FIBERS_ERR_ARG, "plan has no tensor-core state");
     if (a.nvox <= 0) return 0;
     if (a.nvox > 0x7FFFFFFFLL * 32) return fail(FIBERS_ERR_ARG, "slab too large");
-    const int64_t ntile64 = (a.nvox + 63) / 64;
-    const int64_t need = 2 + 2 * ntile64 + 8;
+    const int64_t ntile64 = (a.nvox + 63) / 64, ntile256 = (a.nvox + 255) / 256;
+    const int64_t need = 4 + 2 * ntile64 + 2 * ntile256 + 8;   // [0] maxbits [1] fix_count [2] tile_count | fix list | tile list | tile flags
     if (st->scratch_cap < need) {
         if (st->d_scratch) cudaFree(st->d_scratch);
         st->d_scratch = nullptr; st->scratch_cap = 0;
         FB_CUDA(cudaMalloc(&st->d_scratch, sizeof(int) * (size_t)need));
         st->scratch_cap = need;
     }
-    FB_CUDA(cudaMemsetAsync(st->d_scratch, 0, 2 * sizeof(int), stream));
+    FB_CUDA(cudaMemsetAsync(st->d_scratch, 0, 4 * sizeof(int), stream));
+    int* d_fix_list = st->d_scratch + 4; int* d_tile_list = st->d_scratch + 4 + 2 * ntile64;
     {   // neighbour offsets -> constant memory of this device (skipped when this plan's table is already resident;
         // launches of DIFFERENT plans on one device must not overlap in time)
         std::lock_guard<std::mutex> lk(g_const_mu);
@@ -726,7 +780,18 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
     sample_max_kernel<<<nsm * 8, 256, 0, stream>>>(a.dwi, a.dwi_pitch, a.nvox, p->nvol, st->d_scratch);
-    count_launch(1);
+    {
+        ScanOut so{}; int n = 0;
+        so.ptr[n] = a.odf; so.rows[n++] = p->nvert;
+        if (p->kind == PLAN_DSI && a.pdf) { so.ptr[n] = a.pdf; so.rows[n++] = p->nvol; }
+        for (int k = 0; k < 3; ++k) { so.ptr[n] = a.peak[k]; so.rows[n++] = 3; }
+        for (int k = 0; k < 3; ++k) { so.ptr[n] = a.qa[k]; so.rows[n++] = 1; }
+        so.n = n; so.idx = a.peak_idx;
+        int* d_tile_flag = d_tile_list + ntile256;
+        tile_scan_kernel<<<(unsigned)ntile256, 256, 0, stream>>>(a.mask, a.nvox, a.out_pitch, so, a.stats, d_tile_flag);
+        tile_compact_kernel<<<1, 1024, 0, stream>>>(d_tile_flag, (int)ntile256, d_tile_list, st->d_scratch + 2);
+    }
+    count_launch(3);
     const char* trace_path = getenv("FIBERS_TC_TRACE");
     for (size_t ip = 0; ip < st->pass.size(); ++ip) {
         const TcPass& ps = st->pass[ip];
@@ -738,7 +803,8 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.odf = out; tp.out_pitch = a.out_pitch;
         for (int k = 0; k < 3; ++k) { tp.peak[k] = a.peak[k]; tp.qa[k] = a.qa[k]; }
         tp.peak_idx = a.peak_idx; tp.stats = a.stats; tp.nbr = p->d_nbr; tp.vert = p->d_vert;
-        tp.maxbits = st->d_scratch; tp.fix_count = st->d_scratch + 1; tp.fix_list = st->d_scratch + 2;
+        tp.maxbits = st->d_scratch; tp.fix_count = st->d_scratch + 1; tp.fix_list = d_fix_list;
+        tp.tile_list = d_tile_list; tp.tile_count = st->d_scratch + 2;
         tp.fix_cap = (int)(2 * ntile64);
         tp.ntiles = (int)((a.nvox + 255) / 256);
         tp.nbw = st->nbw;
@@ -783,7 +849,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         }
     }
     // voxels whose scaled signal overflowed fp16 (rare): recompute their 64-voxel tiles in fp32
-    return launch_recon_simt_list(p, a, st->d_scratch + 2, st->d_scratch + 1, stream);
+    return launch_recon_simt_list(p, a, d_fix_list, st->d_scratch + 1, stream);
 }
 
 }  // namespace fibers
