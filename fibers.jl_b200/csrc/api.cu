@@ -430,7 +430,9 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
                                   + 1 + (int64_t)out_frames * 4 + 6 + 1;
             size_t free_b = 0, total_b = 0;
             W_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            int64_t chunk = std::min<int64_t>(n, 1 << 18);
+            int64_t chunk_max = 1 << 18;
+            if (const char* cv = getenv("FIBERS_CUDA_CHUNK_VOXELS")) { long v = atol(cv); if (v >= 4096) chunk_max = v; }
+            int64_t chunk = std::min<int64_t>(n, chunk_max);
             while (chunk > 4096 && (double)chunk * per_vox * NSLOT > 0.6 * (double)free_b) chunk /= 2;
             chunk = (chunk + 63) / 64 * 64;
             const int64_t cp = chunk;                  // device pitch (elements) inside a slot

@@ -262,3 +262,27 @@ def test_dsi_parity(F, sphere642, kernel):
     r0 = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 0, np.float64)
     _check_recon(got0, None, r0, v, f, 321, "dsi hann0")
     assert P.odf_rel_err(got0.pdf.vol, r0["pdf"]) < P.ODF_TOL
+
+
+def test_dsi_tc_overflow_fixup_and_uint16(F, sphere642):
+    """DSI on the tensor-core kernel: voxels far brighter than the sampled maximum overflow the scaled fp16
+    operand in every pass; the epilogue of the ODF pass lists their tiles and the SIMT kernel recomputes ODF,
+    peaks AND the pdf rows.  Also exercises a non-float32 input type."""
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.dsi_phantom((30, 22, 9), seed=41)            # 5940 voxels
+    dwi = ph["dwi"]
+    flat = dwi.reshape(-1, dwi.shape[3], order="F")
+    for h in (300, 2500, 4200):
+        assert h % 2048 >= 32
+        flat[h] *= 40.0                                        # 1500 * 40 = 6e4 < 65535 keeps uint16 exact
+    ph["dwi"] = np.asfortranarray(np.clip(np.round(flat), 0, 65535).astype(np.uint16).reshape(dwi.shape, order="F"))
+    F.device.set_kernel("tc")
+    try:
+        got = F.dsi_rec(*_mri(F, ph))
+    finally:
+        F.device.set_kernel("auto")
+    r64 = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 32, np.float64)
+    assert np.isfinite(got.odf.vol).all() and np.isfinite(got.pdf.vol).all()
+    _check_recon(got, None, r64, v, f, 321, "dsi tc overflow fix-up")
+    assert P.odf_rel_err(got.pdf.vol, r64["pdf"]) < P.ODF_TOL

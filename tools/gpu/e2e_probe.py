@@ -20,9 +20,14 @@ def call():
     F._lib.check(L.fibers_gqi_rec(h_dwi.data_ptr(), 0, h_mask.data_ptr(), *shape, nvol, F._lib.ptr(bval), F._lib.ptr(bv), F._lib.ptr(V),
                                   V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25, h_odf.data_ptr(), *[p.data_ptr() for p in h_peak],
                                   *[q.data_ptr() for q in h_qa], None, 1))
-for label, env in (("tc+tma", {}), ("tc no tma", {"FIBERS_TC_ODF_TMA": "0"}), ("simt", {"FIBERS_CUDA_KERNEL": "simt"})):
-    for k in ("FIBERS_TC_ODF_TMA", "FIBERS_CUDA_KERNEL"): os.environ.pop(k, None)
+for label, env in (("chunk 2^18", {}), ("chunk 2^17", {"FIBERS_CUDA_CHUNK_VOXELS": str(1 << 17)}), ("chunk 2^16", {"FIBERS_CUDA_CHUNK_VOXELS": str(1 << 16)}),
+                   ("chunk 2^19", {"FIBERS_CUDA_CHUNK_VOXELS": str(1 << 19)})):
+    for k in ("FIBERS_TC_ODF_TMA", "FIBERS_CUDA_KERNEL", "FIBERS_CUDA_CHUNK_VOXELS"): os.environ.pop(k, None)
+    L.fibers_cuda_release_cache()
     os.environ.update(env)
-    call(); torch.cuda.synchronize()
-    t = time.perf_counter(); call(); call(); torch.cuda.synchronize(); dt = (time.perf_counter() - t) / 2
+    call(); call(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(4):
+        t = time.perf_counter(); call(); ts.append(time.perf_counter() - t)
+    dt = sorted(ts)[1]
     print(f"{label:12s} {dt*1e3:8.1f} ms/call  {nvox/dt:.3e} voxels/s", flush=True)
