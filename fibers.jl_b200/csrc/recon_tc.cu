@@ -16,11 +16,15 @@
 //               B from shared memory; accumulators D[128 x Npad] fp32 in TMEM columns [0, Npad)
 //   warps 2-9   converters: coalesced fp32 loads of the DWI slab (voxel-contiguous), clamp, scale,
 //               hi/lo fp16 split, tcgen05.st into a 4-slot TMEM ring (columns 384..511)
-//   warps 10-17 epilogue: tcgen05.ld, un-scale, coalesced ODF store, stage the 128 x M tile in shared
-//               memory; local-maximum search on the folded mesh (4 voxels per thread as float4 rows,
-//               neighbour offsets from constant memory), top-3 by three rounds of 64-bit shared
-//               atomicMax on (value, ~index) keys, QA, per-voxel mean -> atomicMax
-// The full ODF never round-trips HBM: it is written once and the peaks come from the staged tile.
+//   warps 10-17 epilogue: tcgen05.ld, un-scale, coalesced ODF store; every value is also quantised to a
+//               16-bit ORDER-PRESERVING key (fixed point relative to the voxel's mean ODF, which the MMA
+//               delivers as one extra matrix row) and staged as a 128 x M key tile in shared memory.
+//               The local-maximum scan of the folded mesh runs on the keys (4 voxels per thread, packed
+//               u16x2 max/min, neighbour offsets from constant memory) and only LISTS possible maxima;
+//               the few listed (voxel, vertex) pairs are then settled EXACTLY on the fp32 values just
+//               written (L2 hits), ranked by three rounds of 64-bit shared atomicMax on (value, ~index),
+//               QA, per-voxel mean -> atomicMax
+// The full ODF never round-trips HBM: it is written once; the scan reads 2 bytes per value from shared memory.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -39,21 +43,27 @@ int launch_recon_simt_list(Plan* p, const ReconArgs& a, const int* d_list, const
 
 namespace {
 
-constexpr int N_EPI = 8;             // epilogue warps (multiple of 4: one per TMEM lane quarter)
-constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = 10;
+constexpr int N_EPI = 12;            // epilogue warps (multiple of 4: one per TMEM lane quarter)
+constexpr int N_CONV = 4;            // converter warps (multiple of 4)
+constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = W_CONV0 + N_CONV;
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
 constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
-constexpr int NSTAGE = 2;            // B ring: K32 chunks (two K16 sub-tiles each)
+constexpr int NSTAGE = 3;            // B ring: K32 chunks (two K16 sub-tiles each)
+constexpr int DSTAGE = 3;            // raw DWI ring of the converters: K32 chunks of 128 voxels (16 KB each)
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
 constexpr int VOX_CTA = 128;
 constexpr int EPI_THREADS = N_EPI * 32;
 constexpr float FP16_TARGET = 8192.f;   // the sampled maximum is scaled to <= 8192 (8x headroom to 65504)
 
-// Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * 512) into the staged tile,
-// 8 per vertex (missing neighbours -> the -inf sentinel row M).  The vertex index is warp-uniform,
-// so the offsets arrive through the uniform datapath and each neighbour costs one LDS.128.
-constexpr int TC_MAX_VERT = 385;
+constexpr int KEY_ROW = VOX_CTA * 2;    // bytes per vertex row of the key tile
+constexpr int CAND_CAP = 2048;          // listed (voxel, vertex) pairs per 128-voxel tile; overflow -> SIMT fix-up
+constexpr float KEY_WINDOW = 8.f;       // keys cover [0, 8 x mean(ODF of the voxel)) in 32767 steps (bit 15 is always set)
+
+// Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * KEY_ROW) into the key tile,
+// 8 per vertex (missing neighbours -> the all-zero sentinel row M).  The vertex index is warp-uniform,
+// so the offsets arrive through the uniform datapath and each neighbour costs one LDS.64.
+constexpr int TC_MAX_VERT = 344;        // rows of the offset table: M + 1 sentinel rows up to M + 8 (prefetch overrun)
 __constant__ uint32_t c_nbr_off[TC_MAX_VERT * NBR_W];
 
 struct TcParams {
@@ -67,16 +77,16 @@ struct TcParams {
     int ntiles;                  // 256-voxel tiles of the slab
     const int* tile_list; const int* tile_count;   // tiles that contain at least one mask voxel (built by tile_scan_kernel)
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
-    int odf_tma, odf_box_rows, odf_nbox;   // ODF tile leaves through TMA stores of the staged tile (else per-thread STG)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
+    int dbg;                     // experiments only (FIBERS_TC_DEBUG)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
 // One launch of the kernel covers at most 336 matrix rows (TMEM columns).  GQI: a single pass (the ODF
 // rows).  DSI: the ODF rows, then the pdf rows in passes of <= 336 (plain mode).
 struct TcPass {
-    __half* d_split = nullptr;   // [2 ranks][hi Nh rows | lo Nh rows][Kpad]
+    __half* d_split = nullptr;   // [2 ranks][K32 chunks][shared-memory image of one stage]
     CUtensorMap tmap;
     int rows = 0, row0 = 0;      // matrix rows [row0, row0 + rows) of the plan's matrix
     int Npad = 0, N1 = 0, N2 = 0;
@@ -88,7 +98,7 @@ struct TcState {
     void* encode = nullptr;      // cuTensorMapEncodeTiled
     int Kpad = 0, nbw = 8;
     unsigned long long uid = 0;              // identifies the neighbour table in the per-device constant-memory cache
-    std::vector<uint32_t> h_nbr_off;         // [M + 1][NBR_W] byte offsets
+    std::vector<uint32_t> h_nbr_off;         // [M + 8][NBR_W] byte offsets (rows >= M: sentinel)
     size_t smem = 0;
     int* d_scratch = nullptr;    // [0] maxbits, [1] fix_count, [2..] fix list
     int64_t scratch_cap = 0;
@@ -117,15 +127,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-// kBackoff: non-critical waiters sleep between polls so that they do not steal issue slots
+// kBackoff: non-critical waiters let the hardware suspend them (try_wait with a time hint) instead of polling,
+// so that they do not steal issue slots from the working warps
 template <bool kBackoff = false>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (kBackoff && !ok) __nanosleep(64);
+        if (kBackoff)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
         if (spin > (1u << 26)) __trap();        // never hang the GPU: a lost signal becomes a launch error
     }
 }
@@ -141,6 +155,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t r; asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory"); return r;
+}
+__device__ __forceinline__ uint32_t umax2(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem], CTA pair
@@ -164,16 +182,6 @@ __device__ __forceinline__ uint64_t make_sdesc_sw32(uint32_t saddr) {          /
 
 #define TRACE(slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] = clock64(); } while (0)
 #define TRACE_ADD(slot, dt) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] += (dt); } while (0)
-
-__device__ __forceinline__ void top3_insert(float val, int idx, float tv[3], int ti[3]) {
-    if (val > tv[2]) {
-        if (val > tv[1]) {
-            tv[2] = tv[1]; ti[2] = ti[1];
-            if (val > tv[0]) { tv[1] = tv[0]; ti[1] = ti[0]; tv[0] = val; ti[0] = idx; }
-            else { tv[1] = val; ti[1] = idx; }
-        } else { tv[2] = val; ti[2] = idx; }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // strided sample of the slab: max over 32-voxel runs every 2048 voxels of every volume
@@ -252,15 +260,21 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapO) {
+recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index is rebuilt from warp votes so that the compiler can prove it warp-uniform (uniform registers,
+    // uniform branches, constant-bank loads and [R + UR] addressing in the role loops)
+    int warp = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) warp |= (__ballot_sync(0xffffffffu, (threadIdx.x >> (5 + b)) & 1u) & 1u) << b;
+    const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int cluster_id = blockIdx.x >> 1, ncluster = gridDim.x >> 1;
     const int Nh = (p.N1 + p.N2) >> 1, N1h = p.N1 >> 1;
     const uint32_t sub_bytes = (uint32_t)(2 * Nh * 32);          // one K16 sub-tile: hi rows then lo rows (SWIZZLE_32B)
     const uint32_t stage_bytes = 2 * sub_bytes;                  // K32 stage
     const int nk32 = p.Kpad >> 5;
+    const uint32_t stage_rows = stage_bytes >> 9;                // 512-byte rows of the pre-tiled global image
     const int ntl = min(*p.tile_count, p.ntiles);      // non-empty tiles; every role walks the same list
     const bool ident = ntl == p.ntiles;                // nothing skipped: the list is the identity
 
@@ -272,14 +286,19 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     uint8_t* base = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
-    float* stage = (float*)(sB + NSTAGE * stage_bytes);                   // [M + 1][128]; row M = -inf sentinel
-    unsigned long long* s_top = (unsigned long long*)(stage + (size_t)(p.M + 1) * VOX_CTA);   // [3][128] packed (value, ~index)
-    float* s_min = (float*)(s_top + 3 * VOX_CTA);                         // [N_CPART][128]
+    uint16_t* keys = (uint16_t*)(sB + NSTAGE * stage_bytes);              // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
+    const int Mk = p.plain ? 0 : p.M;                                     // plain passes stage no keys
+    unsigned long long* s_ckey = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [CAND_CAP] exact (value, ~index) keys
+    unsigned long long* s_top = s_ckey + CAND_CAP;                        // [3][128] winners per voxel
+    uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
+    float* s_min = (float*)(s_cand + CAND_CAP);                           // [N_CPART][128]
     float* s_sum = s_min + N_CPART * VOX_CTA;                             // [N_CPART][128]
-    uint64_t* bars = (uint64_t*)(s_sum + N_CPART * VOX_CTA);
+    float* s_dwi = s_sum + N_CPART * VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
+    uint64_t* bars = (uint64_t*)(s_dwi + DSTAGE * 32 * VOX_CTA);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
-    uint32_t* tmem_ptr_s = (uint32_t*)(d_empty + 1);
+    uint32_t* s_ncand = (uint32_t*)(d_empty + 1);
+    uint32_t* tmem_ptr_s = s_ncand + 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -291,7 +310,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < VOX_CTA; i += TC_THREADS) stage[(size_t)p.M * VOX_CTA + i] = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < 8 * VOX_CTA; i += TC_THREADS) keys[(size_t)Mk * VOX_CTA + i] = 0x8000;   // key 0
+    if (threadIdx.x == 0) *s_ncand = 0u;
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -321,13 +341,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 mbar_wait<true>(&b_empty[s], (use & 1) ^ 1);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * stage_bytes);       // both CTAs' bytes land on the leader's barrier
-                    const uint32_t dst = smem_u32(sB + s * stage_bytes);
-                    const uint32_t bar = full0 + s * 8;
-#pragma unroll
-                    for (int h = 0; h < 4; ++h)                                       // (sub-tile, hi/lo)
-                        asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                     ::"r"(dst + (h >> 1) * sub_bytes + (h & 1) * Nh * 32), "l"(&tmapB), "r"(c * 32 + (h >> 1) * 16),
-                                       "r"((int)(rank * 2 * Nh + (h & 1) * Nh)), "r"(bar) : "memory");
+                    // one bulk tensor copy per stage: the global image is already in shared-memory order
+                    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(smem_u32(sB + s * stage_bytes)), "l"(&tmapB), "r"(0), "r"((int)((rank * nk32 + c) * stage_rows)),
+                                   "r"(full0 + s * 8) : "memory");
                 }
                 __syncwarp();
             }
@@ -382,24 +399,54 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         }
     } else if (warp < W_EPI0) {
         // ===== converters: DWI fp32 -> clamp -> scale -> fp16 hi/lo -> TMEM ring ================
-        const int cw = warp - W_CONV0, grp = cw >> 2, q = warp & 3;
+        // One warp per TMEM lane quarter; thread == voxel.  The raw samples are staged through shared memory with
+        // 4-byte cp.async (any alignment / pitch, zero-fill for masked voxels and K padding): every thread reads back
+        // only what it copied itself, so the ring needs no barrier, holds no registers while the loads are in
+        // flight, and runs DSTAGE - 1 chunks (across tile boundaries) ahead of the conversion.
+        const int q = warp & 3;
         const int vl = q * 32 + lane;                                   // TMEM lane == voxel within the CTA's 128
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t afull0 = mapa(smem_u32(&a_full[0]), 0);
-        uint32_t it = 0;
-        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
-            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
-            const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
-            const bool inside = vox < p.nvox && p.mask[vox] != 0;
-            const float* src = p.dwi + vox;
-            if (warp == W_CONV0) TRACE(9);
-            for (int c = grp; c < nk32; c += 2) {
-                float x[32];
+        const uint32_t sd32 = smem_u32(s_dwi + vl);                     // [DSTAGE][32][128] floats
+        constexpr int PF = DSTAGE - 1;
+        // prefetch cursor
+        int p_ti = cluster_id, p_c = 0; uint32_t p_g = 0;
+        const float* p_src = p.dwi; bool p_inside = false;
+        auto prefetch = [&]() {
+            if (p_ti < ntl) {
+                if (p_c == 0) {
+                    const int ptile = ident ? p_ti : __ldg(p.tile_list + p_ti);
+                    const int64_t pvox = (int64_t)ptile * 256 + rank * VOX_CTA + vl;
+                    p_inside = pvox < p.nvox && p.mask[pvox] != 0;
+                    p_src = p.dwi + (p_inside ? pvox : 0);
+                }
+                const uint32_t dst = sd32 + (p_g % DSTAGE) * (32 * VOX_CTA * 4);
+                const float* src = p_src + (int64_t)(p_c * 32) * p.dwi_pitch;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int k = c * 32 + j;
-                    x[j] = (inside && k < p.K) ? __ldg(src + (int64_t)k * p.dwi_pitch) : 0.f;
+                    const int k = p_c * 32 + j;
+                    const uint32_t sz = (p_inside && k < p.K) ? 4u : 0u;                 // 0: zero-fill, nothing is read
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + j * (VOX_CTA * 4)), "l"(k < p.K ? src : p_src), "r"(sz) : "memory");
+                    src += p.dwi_pitch;
                 }
+                if (++p_c == nk32) { p_c = 0; p_ti += ncluster; }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");         // (an empty group keeps the group count in step)
+            ++p_g;
+        };
+#pragma unroll 1
+        for (int i = 0; i < PF; ++i) prefetch();
+        uint32_t it = 0, g32 = 0;
+        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
+            if (warp == W_CONV0) TRACE(9);
+#pragma unroll 1
+            for (int c = 0; c < nk32; ++c, ++g32) {
+                prefetch();
+                asm volatile("cp.async.wait_group %0;" ::"n"(PF) : "memory");
+                const uint32_t sbase = sd32 + (g32 % DSTAGE) * (32 * VOX_CTA * 4);
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(sbase + j * (VOX_CTA * 4)));
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -410,11 +457,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     hi[j] = *reinterpret_cast<const uint32_t*>(&h);
                     lo[j] = *reinterpret_cast<const uint32_t*>(&l);
                 }
-                const uint32_t g32 = it * nk32 + c;
                 const int slot = g32 % ASLOT;
-                if (warp == W_CONV0 && c == grp) TRACE(10);
+                if (warp == W_CONV0 && c == 0) TRACE(10);
                 mbar_wait<true>(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
-                if (warp == W_CONV0 && c == grp) TRACE(11);
+                if (warp == W_CONV0 && c == 0) TRACE(11);
                 tc_fence_after();
                 const uint32_t col = lane_addr + TMEM_A_COL + slot * 32;
                 tmem_st8(col, hi); tmem_st8(col + 8, hi + 8); tmem_st8(col + 16, lo); tmem_st8(col + 24, lo + 8);
@@ -425,10 +471,11 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             }
             if (warp == W_CONV0) TRACE(12);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         // ===== epilogue ==========================================================================
         // phase 1 roles: warp quarter q owns TMEM lanes 32q..32q+31, `cpart` selects the column range
-        // phase 2 roles: N_EPI vertex ranges (one per warp); lane owns voxels 4*lane .. 4*lane+3 (float4)
+        // phase 2 roles: N_EPI vertex ranges (one per warp); lane owns voxels 4*lane .. 4*lane+3 (4 packed keys)
         const int ew = warp - W_EPI0, cpart = ew >> 2, q = warp & 3;
         const int et = ew * 32 + lane;                                  // 0..255 within the epilogue group
         const int vl = q * 32 + lane;
@@ -437,12 +484,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         const int M = p.M;
         const int cper = ((p.Npad + N_CPART - 1) / N_CPART + 15) & ~15;
         const int c_begin = cpart * cper, c_end = min(min(c_begin + cper, p.Npad), (M + 15) & ~15);
-        const int vper = (M + N_EPI - 1) / N_EPI;
-        const int va = ew * vper, vb = min(M, va + vper);
+        const int vper = ((M + N_EPI - 1) / N_EPI + 1) & ~1;           // even: a vertex pair never straddles two warps
+        const int va = min(M, ew * vper), vb = min(M, va + vper);
         uint32_t it = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
-            const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
+            const int64_t vox0 = (int64_t)tile * 256 + rank * VOX_CTA;   // first voxel of this CTA's half
+            const int64_t vox = vox0 + vl;
             const bool vok = vox < p.nvox;
             // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol], folded into the un-scale factor.
             // A voxel whose q = 0 sample is <= 0 gets zeros: either it is skipped by the reference as well (all
@@ -456,33 +504,60 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             mbar_wait<true>(d_full, it & 1);
             tc_fence_after();
             if (warp == W_EPI0) TRACE(2);
-            // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + staging ----
+            // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + 16-bit key tile ----
+            // key(val) = clamp(ceil(val * ks), 0, 32767), ks = 32768 / (KEY_WINDOW * mean): monotone in val, key >= 1
+            // <=> val > 0.  Stored as 0x8000 | key = the low mantissa bits of fma.rp(val, ks, 2^23 + 2^15) (no
+            // conversion instruction); the always-set bit 15 lets one 32-bit subtraction compare two packed keys.
             float mn = CUDART_INF_F, sum = 0.f;
             {
-                const bool st_direct = vok && !p.odf_tma;
+                float ks = 0.f;
+                if (!p.plain) {
+                    const float meanv = __uint_as_float(tmem_ld1(lane_addr + M)) * scl;   // extra matrix row M: mean of the ODF rows
+                    tmem_wait_ld();
+                    ks = (meanv > 0.f && meanv < CUDART_INF_F) ? (32768.f / KEY_WINDOW) / meanv : 1e-30f;
+                }
                 float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
-                float* sp = stage + c_begin * VOX_CTA + vl;
+                uint16_t* kp = keys + c_begin * VOX_CTA + vl;
+                const int64_t pitch = p.out_pitch;
+                const bool plain = p.plain != 0;
+                const bool vst = vok && !(p.dbg & 1);
                 auto process = [&](const uint32_t (&r)[16], int c0) {
-                    if (c0 + 16 <= M) {
+                    const int nrow = min(16, M - c0);                   // warp-uniform
+                    if (plain) {
+                        float* g = gp;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (j < nrow && vok) *g = __uint_as_float(r[j]) * scl;
+                            g += pitch;
+                        }
+                    } else if (nrow == 16) {
+                        float* g = gp;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float val = __uint_as_float(r[j]) * scl;
-                            sp[j * VOX_CTA] = val;
-                            if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
+                            if (vst) *g = val;
+                            g += pitch;
+                            float y = __fmaf_ru(val, ks, 8421376.f);
+                            y = fminf(fmaxf(y, 8421376.f), 8421376.f + 32767.f);
+                            kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
                             mn = fminf(mn, val); sum += val;
                         }
                     } else {
+                        float* g = gp;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (c0 + j < M) {
+                            if (j < nrow) {
                                 const float val = __uint_as_float(r[j]) * scl;
-                                sp[j * VOX_CTA] = val;
-                                if (st_direct) gp[(int64_t)j * p.out_pitch] = val;
+                                if (vok) *g = val;
+                                float y = __fmaf_ru(val, ks, 8421376.f);
+                                y = fminf(fmaxf(y, 8421376.f), 8421376.f + 32767.f);
+                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
                                 mn = fminf(mn, val); sum += val;
                             }
+                            g += pitch;
                         }
                     }
-                    gp += 16 * p.out_pitch; sp += 16 * VOX_CTA;
+                    gp += 16 * pitch; kp += 16 * VOX_CTA;
                 };
                 uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
                 if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
@@ -501,107 +576,133 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
             if (warp == W_EPI0) TRACE(3);
+            if (p.plain) continue;                                      // rows only (DSI pdf): nothing is staged
             s_min[cpart * VOX_CTA + vl] = mn; s_sum[cpart * VOX_CTA + vl] = sum;
-            if (p.odf_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged tile -> visible to the TMA engine
-            named_bar(1, EPI_THREADS);
-            if (p.odf_tma && warp == W_EPI0) {
-                // the ODF tile leaves as bulk tensor stores (rows = vertices, 128 voxels each; rows >= M and
-                // voxels >= nvox are clipped by the tensor map): no per-thread store instructions at all
-                if (elect_one()) {
-                    const int x0 = (int)((int64_t)tile * 256 + rank * VOX_CTA);
-                    for (int b = 0; b < p.odf_nbox; ++b)
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                     ::"l"(&tmapO), "r"(x0), "r"(b * p.odf_box_rows), "r"(smem_u32(stage + (size_t)b * p.odf_box_rows * VOX_CTA)) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                __syncwarp();
-            }
+            named_bar(1, EPI_THREADS);                                  // key tile + this tile's ODF stores visible to the group
             if (warp == W_EPI0) TRACE(4);
-            if (p.plain) {                                              // rows only (DSI pdf): the tile is on its way out
-                if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                named_bar(1, EPI_THREADS);
-                continue;
-            }
-            // ---- phase 2: local maxima of the folded mesh (strictly greater than every neighbour, > 0)
-            //      4 voxels per thread (float4 rows), every shared-memory load issued up front ----
-            float tv[4][3]; int ti[4][3];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { tv[j][0] = tv[j][1] = tv[j][2] = 0.f; ti[j][0] = ti[j][1] = ti[j][2] = -1; }
-            // two vertices per iteration; neighbour offsets come from constant memory (uniform datapath)
+            // ---- phase 2: scan.  A vertex can only be a local maximum (value > 0, > every mesh neighbour) if its
+            //      key is >= max(neighbour keys, 1); equality means "cannot tell from the keys".  Both kinds are
+            //      listed.  Two vertices per iteration; software-pipelined: the keys of pair i+1 and the offsets of
+            //      pair i+2 are in flight while pair i is tested.  (Prefetches past the warp's range touch rows
+            //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
             {
-                const char* svb = reinterpret_cast<const char*>(stage) + lane * 16;
-                auto ld = [&](uint32_t off) { return *reinterpret_cast<const float4*>(svb + off); };
-                auto max6 = [](float a, float b, float c, float d, float e, float f) {
-                    return fmaxf(fmaxf(fmaxf(a, b), c), fmaxf(fmaxf(d, e), f));
+                const uint32_t kb = smem_u32(keys) + lane * 8;
+                auto ld = [&](uint32_t off) {
+                    uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
                 };
-                for (int v = va; v < vb; v += 2) {
-                    const int vB = (v + 1 < vb) ? v + 1 : M;           // past the range -> sentinel row (never a peak)
-                    const uint4 oA0 = *reinterpret_cast<const uint4*>(&c_nbr_off[v * NBR_W]);
-                    const uint4 oA1 = *reinterpret_cast<const uint4*>(&c_nbr_off[v * NBR_W + 4]);
-                    const uint4 oB0 = *reinterpret_cast<const uint4*>(&c_nbr_off[vB * NBR_W]);
-                    const uint4 oB1 = *reinterpret_cast<const uint4*>(&c_nbr_off[vB * NBR_W + 4]);
-                    const float4 cA = ld(v * 512), cB = ld(vB * 512);
-                    const float4 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
-                    const float4 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
-                    float4 mA, mB;
-                    mA.x = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x); mA.y = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
-                    mA.z = max6(a0.z, a1.z, a2.z, a3.z, a4.z, a5.z); mA.w = max6(a0.w, a1.w, a2.w, a3.w, a4.w, a5.w);
-                    mB.x = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x); mB.y = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
-                    mB.z = max6(b0.z, b1.z, b2.z, b3.z, b4.z, b5.z); mB.w = max6(b0.w, b1.w, b2.w, b3.w, b4.w, b5.w);
-                    if (p.nbw > 6) {                                    // warp-uniform (meshes with degree 7-8)
-                        const float4 a6 = ld(oA1.z), a7 = ld(oA1.w), b6 = ld(oB1.z), b7 = ld(oB1.w);
-                        mA.x = fmaxf(mA.x, fmaxf(a6.x, a7.x)); mA.y = fmaxf(mA.y, fmaxf(a6.y, a7.y));
-                        mA.z = fmaxf(mA.z, fmaxf(a6.z, a7.z)); mA.w = fmaxf(mA.w, fmaxf(a6.w, a7.w));
-                        mB.x = fmaxf(mB.x, fmaxf(b6.x, b7.x)); mB.y = fmaxf(mB.y, fmaxf(b6.y, b7.y));
-                        mB.z = fmaxf(mB.z, fmaxf(b6.z, b7.z)); mB.w = fmaxf(mB.w, fmaxf(b6.w, b7.w));
+                auto max6 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+                    return umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f));
+                };
+                const bool wide = p.nbw > 6;                            // warp-uniform (meshes with degree 7-8)
+                int v = va;
+                const uint32_t* op = c_nbr_off + v * NBR_W;             // running pointer into the offset table
+                uint4 oA0 = *reinterpret_cast<const uint4*>(op), oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                uint2 oA1 = *reinterpret_cast<const uint2*>(op + 4), oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                uint2 cA = ld(v * KEY_ROW), cB = ld((v + 1) * KEY_ROW);
+                uint2 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
+                uint2 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
+                op += 16;
+                oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                uint32_t crow = (v + 2) * KEY_ROW;
+                for (; v < vb; v += 2) {
+                    // reduce pair i
+                    uint32_t mAx = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x), mAy = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
+                    uint32_t mBx = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x), mBy = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
+                    if (wide) {
+                        const uint2 wA = *reinterpret_cast<const uint2*>(op - 16 + 6), wB = *reinterpret_cast<const uint2*>(op - 16 + 14);
+                        const uint2 a6 = ld(wA.x), a7 = ld(wA.y), b6 = ld(wB.x), b7 = ld(wB.y);
+                        mAx = umax2(mAx, umax2(a6.x, a7.x)); mAy = umax2(mAy, umax2(a6.y, a7.y));
+                        mBx = umax2(mBx, umax2(b6.x, b7.x)); mBy = umax2(mBy, umax2(b6.y, b7.y));
                     }
-                    // candidate <=> value > 0 and value > every neighbour  (value > max(nmax, 0))
-                    const bool pA0 = cA.x > fmaxf(mA.x, 0.f), pA1 = cA.y > fmaxf(mA.y, 0.f), pA2 = cA.z > fmaxf(mA.z, 0.f), pA3 = cA.w > fmaxf(mA.w, 0.f);
-                    const bool pB0 = cB.x > fmaxf(mB.x, 0.f), pB1 = cB.y > fmaxf(mB.y, 0.f), pB2 = cB.z > fmaxf(mB.z, 0.f), pB3 = cB.w > fmaxf(mB.w, 0.f);
-                    if (__any_sync(0xffffffffu, pA0 | pA1 | pA2 | pA3 | pB0 | pB1 | pB2 | pB3)) {   // local maxima are rare
-                        if (pA0) top3_insert(cA.x, v, tv[0], ti[0]);
-                        if (pA1) top3_insert(cA.y, v, tv[1], ti[1]);
-                        if (pA2) top3_insert(cA.z, v, tv[2], ti[2]);
-                        if (pA3) top3_insert(cA.w, v, tv[3], ti[3]);
-                        if (pB0) top3_insert(cB.x, v + 1, tv[0], ti[0]);
-                        if (pB1) top3_insert(cB.y, v + 1, tv[1], ti[1]);
-                        if (pB2) top3_insert(cB.z, v + 1, tv[2], ti[2]);
-                        if (pB3) top3_insert(cB.w, v + 1, tv[3], ti[3]);
+                    const uint2 kA = cA, kB = cB;
+                    // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
+                    cA = ld(crow); cB = ld(crow + KEY_ROW); crow += 2 * KEY_ROW;
+                    a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z); a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y);
+                    b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y);
+                    op += 16;
+                    oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                    oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                    // stored keys have bit 15 set, so per 16-bit half  (k - t + 0x8000) has bit 15 set  <=>  k >= t,
+                    // and the two halves cannot borrow from each other: one 32-bit subtraction tests two voxels.
+                    // threshold t = max(neighbour keys, 1)
+                    const uint32_t hAx = kA.x - umax2(mAx, 0x80018001u) + 0x80008000u, hAy = kA.y - umax2(mAy, 0x80018001u) + 0x80008000u;
+                    const uint32_t hBx = kB.x - umax2(mBx, 0x80018001u) + 0x80008000u, hBy = kB.y - umax2(mBy, 0x80018001u) + 0x80008000u;
+                    const uint32_t hit = (hAx | hAy | hBx | hBy) & 0x80008000u;
+                    if (__any_sync(0xffffffffu, hit != 0u)) {           // local maxima are rare
+                        if (hit != 0u) {
+                            // flag bits: 0-3 = vertex v, voxels 4*lane + 0..3; 4-7 = vertex v + 1
+                            const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
+                                               ((hBx >> 11) & 0x00100010u) | ((hBy >> 9) & 0x00400040u);
+                            uint32_t fl = (w & 0x55u) | ((w >> 15) & 0xAAu);
+                            uint32_t slot = atomicAdd(s_ncand, (uint32_t)__popc(fl));
+                            while (fl) {
+                                const int h = __ffs(fl) - 1;
+                                fl &= fl - 1;
+                                if (slot < (uint32_t)CAND_CAP) s_cand[slot] = ((uint32_t)(v + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
+                                ++slot;
+                            }
+                        }
                     }
                 }
             }
+            named_bar(1, EPI_THREADS);
             if (warp == W_EPI0) TRACE(5);
-            // ---- merge the 8 vertex ranges: three rounds of 64-bit atomicMax on (value, ~index) keys:
-            //      larger value wins, equal values -> smaller index wins (the reference's stable order) ----
-            unsigned long long k0[4], k1[4], k2[4];
+            // ---- phase 3: settle the listed pairs on the exact fp32 values (this CTA wrote them a moment ago: L2 hits).
+            //      Keys that decided strictly need the value only; ties re-run the neighbour test in fp32. ----
+            const uint32_t ncand_raw = *s_ncand;
+            const int ncand = (int)min(ncand_raw, (uint32_t)CAND_CAP);
+            for (int e = et; e < ncand; e += EPI_THREADS) {
+                const uint32_t ent = s_cand[e];
+                const int cv = (int)(ent >> 8), cx = (int)(ent & 0xFFu);
+                const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(p.nbr + cv * NBR_W));     // 8 x uint16 neighbour ids
+                const uint32_t nn[4] = {n0.x, n0.y, n0.z, n0.w};
+                const uint32_t kc = keys[cv * VOX_CTA + cx];
+                uint32_t kn = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                k0[j] = ti[j][0] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][0]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][0]) : 0ull;
-                k1[j] = ti[j][1] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][1]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][1]) : 0ull;
-                k2[j] = ti[j][2] >= 0 ? ((unsigned long long)__float_as_uint(tv[j][2]) << 32) | (0xFFFFFFFFu - (uint32_t)ti[j][2]) : 0ull;
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                    kn = max(kn, (uint32_t)keys[(n != NBR_NONE ? n : (uint32_t)M) * VOX_CTA + cx]);
+                }
+                const float* col = p.odf + vox0 + cx;
+                const float c = __ldcg(col + (int64_t)cv * p.out_pitch);
+                bool ok = c > 0.f;
+                if (kc <= kn) {                                          // keys tie: repeat the neighbour test in fp32
+                    float nv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                        nv[k] = (n != NBR_NONE) ? __ldcg(col + (int64_t)n * p.out_pitch) : -CUDART_INF_F;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ok = ok && (c > nv[k]);
+                }
+                s_ckey[e] = ok ? (((unsigned long long)__float_as_uint(c) << 32) | (0xFFFFFFFFu - (uint32_t)cv)) : 0ull;
             }
+            named_bar(1, EPI_THREADS);
+            // ---- three rounds of 64-bit atomicMax on (value, ~index): larger value wins, equal values -> smaller
+            //      index wins (the reference's stable order); a key joins round r only if it lost every earlier one ----
 #pragma unroll
             for (int rnd = 0; rnd < 3; ++rnd) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (k0[j]) atomicMax(&s_top[rnd * VOX_CTA + 4 * lane + j], k0[j]);
-                named_bar(1, EPI_THREADS);
-                if (rnd < 2) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (k0[j] && s_top[rnd * VOX_CTA + 4 * lane + j] == k0[j]) { k0[j] = k1[j]; k1[j] = k2[j]; k2[j] = 0ull; }
+                for (int e = et; e < ncand; e += EPI_THREADS) {
+                    const unsigned long long k = s_ckey[e];
+                    const int cx = (int)(s_cand[e] & 0xFFu);
+                    if (k != 0ull && (rnd == 0 || k < s_top[(rnd - 1) * VOX_CTA + cx])) atomicMax(&s_top[rnd * VOX_CTA + cx], k);
                 }
+                named_bar(1, EPI_THREADS);
             }
             if (warp == W_EPI0) TRACE(6);
             // ---- outputs: one thread per voxel (epilogue warps 0-3) ----
             if (ew < 4) {
                 const int ov = ew * 32 + lane;                          // voxel within the CTA
-                const int64_t ovox = (int64_t)tile * 256 + rank * VOX_CTA + ov;
+                const int64_t ovox = vox0 + ov;
                 const bool ook = ovox < p.nvox;
                 float omin = s_min[ov], osum = s_sum[ov];
 #pragma unroll
                 for (int cp = 1; cp < N_CPART; ++cp) { omin = fminf(omin, s_min[cp * VOX_CTA + ov]); osum += s_sum[cp * VOX_CTA + ov]; }
                 float mean = osum / (float)M;
-                const bool bad = ook && !(fabsf(osum) < CUDART_INF_F);   // fp16 overflow of the scaled signal (or non-finite input)
+                // fp16 overflow of the scaled signal (or non-finite input), or more listed pairs than the list holds
+                const bool bad = ook && (!(fabsf(osum) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
                 if (ook) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -624,19 +725,18 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     if (mean > -CUDART_INF_F) atomicMax(p.stats, f2ord(mean));
                     if (anybad) {                                       // recompute this 64-voxel tile with the SIMT kernel
                         const int slot = atomicAdd(p.fix_count, 1);
-                        if (slot < p.fix_cap) p.fix_list[slot] = (int)(((int64_t)tile * 256 + rank * VOX_CTA + ew * 32) >> 6);
+                        if (slot < p.fix_cap) p.fix_list[slot] = (int)((vox0 + ew * 32) >> 6);
                     }
                 }
             }
+            if (et == 0) *s_ncand = 0u;
             if (warp == W_EPI0) TRACE(7);
-            if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staged tile fully read
-            named_bar(1, EPI_THREADS);                                  // staging / scratch free for the next tile
+            named_bar(1, EPI_THREADS);                                  // key tile / lists free for the next tile
             if (warp == W_EPI0) TRACE(8);
         }
     }
 
     // ---- teardown --------------------------------------------------------------------------
-    if (p.odf_tma && warp == W_EPI0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -646,8 +746,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 }
 
 size_t tc_smem_bytes(int M, int Nh) {
-    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 1) * VOX_CTA * 4 + 3 * VOX_CTA * 8 + N_CPART * VOX_CTA * 2 * 4 +
-               (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
+    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 12 + 3 * VOX_CTA * 8 +
+               N_CPART * VOX_CTA * 2 * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
 
@@ -679,7 +779,7 @@ static void tc_state_free(TcState* st) {
 int tc_plan_init(Plan* p) {
     if (p->kind != PLAN_GQI && p->kind != PLAN_DSI) { set_error("tensor-core path: GQI / DSI plans only"); return 1; }
     const int M = p->nvert, K = p->nvol;
-    if ((M + 15) / 16 * 16 > 336 || M + 1 > TC_MAX_VERT) { set_error("tensor-core path: more than 336 half-sphere vertices"); return 1; }
+    if ((M + 1 + 15) / 16 * 16 > 336 || M + 8 > TC_MAX_VERT) { set_error("tensor-core path: more than 335 half-sphere vertices"); return 1; }
     if (p->kind == PLAN_DSI && p->cvol < 0) { set_error("tensor-core path: DSI without a q-space origin sample"); return 1; }
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device);
@@ -692,11 +792,11 @@ int tc_plan_init(Plan* p) {
     TcState* st = new TcState();
     st->Kpad = Kpad; st->nbw = p->nbr_width; st->encode = fn;
     st->uid = g_next_uid.fetch_add(1);
-    st->h_nbr_off.assign((size_t)(M + 1) * NBR_W, (uint32_t)M * 512u);          // sentinel row M everywhere ...
+    st->h_nbr_off.assign((size_t)(M + 8) * NBR_W, (uint32_t)M * KEY_ROW);          // sentinel row M everywhere ...
     for (int v = 0; v < M; ++v)
         for (int k = 0; k < NBR_W; ++k) {
             const uint16_t n = p->h_nbr[(size_t)v * NBR_W + k];
-            if (n != NBR_NONE) st->h_nbr_off[(size_t)v * NBR_W + k] = (uint32_t)n * 512u;
+            if (n != NBR_NONE) st->h_nbr_off[(size_t)v * NBR_W + k] = (uint32_t)n * KEY_ROW;
         }
     // passes: ODF rows, then (DSI) the pdf rows in blocks of <= 336
     std::vector<std::pair<int, int>> ranges = {{0, M}};
@@ -705,21 +805,40 @@ int tc_plan_init(Plan* p) {
     for (size_t i = 0; i < ranges.size(); ++i) {
         TcPass ps;
         ps.row0 = ranges[i].first; ps.rows = ranges[i].second; ps.plain = i > 0;
-        split_dims(ps.rows, ps.Npad, ps.N1, ps.N2);
+        const int img_rows_n = ps.rows + (ps.plain ? 0 : 1);          // ODF pass: one extra row = mean of the ODF rows
+        split_dims(img_rows_n, ps.Npad, ps.N1, ps.N2);
         const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
-        smem = std::max(smem, tc_smem_bytes(ps.rows, Nh));
-        // split operand, row order: rank 0 [hi: blk1 rows 0..N1h, blk2 rows 0..N2h][lo: same], then rank 1
-        std::vector<__half> split((size_t)4 * Nh * Kpad, __float2half(0.f));
-        for (int n = 0; n < ps.rows; ++n) {
+        smem = std::max(smem, tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh));
+        // Split operand as a ready-made shared-memory image: [rank][K32 chunk][K16 sub-tile][hi | lo][row][16 halves],
+        // rows in the order (blk1 rows 0..N1h, blk2 rows 0..N2h) of that rank, with the SWIZZLE_32B pattern the
+        // tcgen05 descriptors expect already applied (16-byte chunk ^= bit 2 of the row).  A stage is then ONE
+        // contiguous 128*Nh-byte block: the producer moves it with a single TMA copy of 512-byte rows instead of
+        // 4*Nh separate 32-byte rows.
+        const int nk32 = Kpad / 32;
+        const size_t stage_halves = (size_t)4 * Nh * 16;
+        std::vector<__half> split((size_t)2 * nk32 * stage_halves, __float2half(0.f));
+        std::vector<float> mean_row;
+        if (!ps.plain) {                                   // column means of the ODF rows (fp64 accumulation)
+            mean_row.resize(K);
+            for (int k = 0; k < K; ++k) {
+                double acc = 0.0;
+                for (int n = 0; n < ps.rows; ++n) acc += p->h_matrix[(size_t)(ps.row0 + n) * K + k];
+                mean_row[k] = (float)(acc / ps.rows);
+            }
+        }
+        for (int n = 0; n < img_rows_n; ++n) {
             int rank, local;
             if (n < ps.N1) { rank = n / N1h; local = n % N1h; }
             else { const int m = n - ps.N1; rank = m / N2h; local = N1h + m % N2h; }
-            const float* src = p->h_matrix.data() + (size_t)(ps.row0 + n) * K;
+            const float* src = n < ps.rows ? p->h_matrix.data() + (size_t)(ps.row0 + n) * K : mean_row.data();
             for (int k = 0; k < K; ++k) {
                 const __half h = __float2half_rn(src[k]);
                 const __half l = __float2half_rn(src[k] - __half2float(h));
-                split[((size_t)rank * 2 * Nh + local) * Kpad + k] = h;
-                split[((size_t)rank * 2 * Nh + Nh + local) * Kpad + k] = l;
+                const int c = k / 32, sub = (k % 32) / 16, j = k % 16;
+                const size_t stage = ((size_t)rank * nk32 + c) * stage_halves;
+                const size_t inrow = (size_t)(((j / 8) ^ ((local >> 2) & 1)) * 8 + j % 8);
+                split[stage + ((size_t)(sub * 2 + 0) * Nh + local) * 16 + inrow] = h;
+                split[stage + ((size_t)(sub * 2 + 1) * Nh + local) * 16 + inrow] = l;
             }
         }
         if (cudaMalloc(&ps.d_split, split.size() * sizeof(__half)) != cudaSuccess ||
@@ -727,12 +846,13 @@ int tc_plan_init(Plan* p) {
             set_error("tensor-core path: device allocation failed"); cudaGetLastError(); tc_state_free(st); return 1;
         }
         st->pass.push_back(ps);
-        cuuint64_t gdim[2] = {(cuuint64_t)Kpad, (cuuint64_t)(4 * Nh)};
-        cuuint64_t gstr[1] = {(cuuint64_t)Kpad * 2};
-        cuuint32_t box[2] = {16, (cuuint32_t)Nh};
+        const cuuint64_t img_rows = (cuuint64_t)2 * nk32 * (stage_halves / 256);
+        cuuint64_t gdim[2] = {256, img_rows};
+        cuuint64_t gstr[1] = {512};
+        cuuint32_t box[2] = {256, (cuuint32_t)(stage_halves / 256)};
         cuuint32_t estr[2] = {1, 1};
         if (((EncodeFn)fn)(&st->pass.back().tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ps.d_split, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
             set_error("tensor-core path: cuTensorMapEncodeTiled failed"); tc_state_free(st); return 1;
         }
@@ -810,26 +930,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.nbw = st->nbw;
         tp.plain = ps.plain;
         tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
-        // output tensor map (per call: pointer / pitch belong to the caller).  TMA needs a 16-byte aligned base
-        // and row pitch; otherwise the epilogue falls back to per-thread coalesced stores.
-        CUtensorMap tmapO; memset(&tmapO, 0, sizeof(tmapO));
-        tp.odf_tma = 0;
-        {
-            const int nbox = (ps.rows + 255) / 256, rows = (ps.rows + nbox - 1) / nbox;
-            const bool aligned = ((uintptr_t)out % 16 == 0) && ((a.out_pitch * 4) % 16 == 0) && a.nvox < (1ll << 31);
-            const char* env = getenv("FIBERS_TC_ODF_TMA");
-            if (aligned && nbox * rows <= ps.rows + 1 && !(env && env[0] == '0')) {
-                cuuint64_t gdim[2] = {(cuuint64_t)a.nvox, (cuuint64_t)ps.rows};
-                cuuint64_t gstr[1] = {(cuuint64_t)a.out_pitch * 4};
-                cuuint32_t box[2] = {(cuuint32_t)VOX_CTA, (cuuint32_t)rows};
-                cuuint32_t estr[2] = {1, 1};
-                if (((EncodeFn)st->encode)(&tmapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
-                    tp.odf_tma = 1; tp.odf_box_rows = rows; tp.odf_nbox = nbox;
-                }
-            }
-        }
+        { const char* dbg = getenv("FIBERS_TC_DEBUG"); tp.dbg = dbg ? atoi(dbg) : 0; }
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
         long long* d_trace = nullptr;
         if (trace_path && *trace_path && ip == 0) {
@@ -837,7 +938,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
             FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
             tp.trace = d_trace;
         }
-        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, tmapO);
+        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap);
         count_launch(1);
         FB_CUDA(cudaGetLastError());
         if (d_trace) {

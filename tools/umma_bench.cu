@@ -142,6 +142,56 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int N, int ts, int sw128, i
     if (warp == 0) tmem_dealloc<CG>(tb);
 }
 
+// ---- C: does accumulating into the SAME D back to back serialise?  6 MMAs per elected issue block (as in the
+//         production kernel), destinations cycling over `nacc` accumulators of N columns each.
+template <int NACC, int ORDER>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_alt_kernel(int N, int nblk, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tb;
+    const int warp = threadIdx.x >> 5;
+    uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc<2>(&tb);
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    tc_fence_after();
+    if (rank == 0 && warp == 0) {
+        const uint32_t idesc = make_idesc(256, N);
+        const uint32_t sb = smem_u32(smem);
+        const uint64_t bdesc = make_sdesc(sb, 256, 6);
+        const uint32_t d = tb, a = tb + 480u;
+        long long t0 = clock64();
+        for (int i = 0; i < nblk; ++i) {
+            uint32_t el;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(el));
+            if (el) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    // order 0: d0 d0 d0 d1 d1 d1 (grouped)   order 1: d0 d1 d2 d0 d1 d2 (interleaved)
+                    constexpr int dummy = 0; (void)dummy; const int k = ORDER == 0 ? (j / (6 / NACC)) : (j % NACC);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                 ::"r"(d + (uint32_t)(k * N)), "r"(a), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+        long long t1 = clock64();
+        uint32_t el;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(el));
+        if (el) asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        if (threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    } else mbar_wait(&bar, 0);
+    tc_fence_before();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) tmem_dealloc<2>(tb);
+}
+
 int main() {
     long long* dout; float* sink; CK(cudaMalloc(&dout, 64)); CK(cudaMalloc(&sink, 4));
     long long h[2];
@@ -171,6 +221,19 @@ int main() {
         const double ideal = 128.0 * N / 256.0;      // per-SM 4096 MAC/cycle
         printf("  cta_group=%d A=%s B=%s N=%3d form=%s : issue %.0f, total %.0f cycles/MMA (ideal %.0f)\n", cg, ts ? "TMEM" : "SMEM",
                sw128 ? "SW128" : "SW32 ", N, ndst == 1 ? "plain" : "mask ", h[0] / (double)nmma, h[1] / (double)nmma, ideal);
+    }
+    printf("== C. cta_group::2 TS-mode, 6 MMAs per issue block, destinations over nacc accumulators ==\n");
+    for (int N : {64, 112, 160}) for (int nacc : {1, 2, 3}) for (int order : {0, 1}) {
+        const int nblk = 64;
+        void (*kf)(int, int, long long*) = nacc == 1 ? (order ? mma_alt_kernel<1, 1> : mma_alt_kernel<1, 0>)
+                                         : nacc == 2 ? (order ? mma_alt_kernel<2, 1> : mma_alt_kernel<2, 0>)
+                                                     : (order ? mma_alt_kernel<3, 1> : mma_alt_kernel<3, 0>);
+        CK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kf<<<2, 128, smem>>>(N, nblk, dout);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+        printf("  N=%3d nacc=%d %s : issue %.0f, total %.0f cycles/MMA (ideal %.0f)\n", N, nacc, order ? "interleaved" : "grouped    ",
+               h[0] / (6.0 * nblk), h[1] / (6.0 * nblk), 128.0 * N / 256.0);
     }
     return 0;
 }
