@@ -70,13 +70,14 @@ def make_tables():
     return phantom.shells_table(NB0, list(SHELLS))
 
 
-def synth_dwi_device(torch, nvox, bval, bvec, seed, device, snr=30.0, chunk=1 << 19):
-    """[nvol, nvox] float32 on `device`: two fibres + isotropic compartment, Rician noise, ~0.1 % negatives."""
+def synth_dwi_device(torch, nvox, bval, bvec, seed, device, snr=30.0, chunk=1 << 19, pitch=None):
+    """[nvol, pitch >= nvox] float32 on `device` (columns >= nvox are zero padding): two fibres + isotropic
+    compartment, Rician noise, ~0.1 % negatives."""
     g = torch.Generator(device=device); g.manual_seed(seed)
     b = torch.tensor(bval, device=device, dtype=torch.float32)[:, None]
     G = torch.tensor(bvec, device=device, dtype=torch.float32)
     nvol = b.shape[0]
-    out = torch.empty((nvol, nvox), device=device, dtype=torch.float32)
+    out = torch.zeros((nvol, pitch or nvox), device=device, dtype=torch.float32)
     for c0 in range(0, nvox, chunk):
         n = min(chunk, nvox - c0)
         def dirs():
@@ -245,7 +246,7 @@ def main():
     workload = f"cfg2 GQI recon+peaks {shape[0]}x{shape[1]}x{shape[2]}x{nvol} (18 b0 + 90x b=1000/2000/3000), sphere_642, mask=={1 if args.mask == 'ones' else 'ellipsoid'}"
     config = {"workload": workload, "per_gpu": "one HCP-shaped subject per GPU (weak; cfg4-style batch)",
               "l2_policy": "inputs (4.2 GB/step) larger than L2 (126 MB); no explicit flush", "sigma": 1.25,
-              "layout": "frame-major [frame][voxel]; dwi pitch = nvox, output pitch = nvox rounded up to 64"}
+              "layout": "frame-major [frame][voxel]; dwi and output frame pitch = nvox rounded up to 64"}
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -277,7 +278,8 @@ def main():
     D.set_kernel(args.kernel)
     D.set_devices([local_rank])
 
-    dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000 + rank, dev)
+    pitch = (nvox + 63) // 64 * 64          # frame pitch of the DWI slab and of the outputs: 256-byte aligned rows
+    dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000 + rank, dev, pitch=pitch)
     if args.mask == "ones":
         mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
     else:
@@ -286,7 +288,6 @@ def main():
         m3 = (ax[0][:, None, None] ** 2 + ax[1][None, :, None] ** 2 + ax[2][None, None, :] ** 2) <= r2
         mask = m3.permute(2, 1, 0).contiguous().reshape(-1).to(torch.uint8)          # x fastest (column-major volume)
         config["mask"] = f"ellipsoid, {mask.float().mean().item():.3f} fill; value counts ALL voxels of the volume"
-    pitch = (nvox + 63) // 64 * 64          # output frame pitch: 256-byte aligned rows (lets the ODF tile leave by TMA)
     odf = torch.empty((M_VERT, pitch), dtype=torch.float32, device=dev)
     peak = [torch.empty((3, pitch), dtype=torch.float32, device=dev) for _ in range(3)]
     qa = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
@@ -298,7 +299,7 @@ def main():
     def step(ev=None):
         D.stats_init(stats.data_ptr(), stream)
         if ev: ev[0].record()
-        plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, pitch, odf.data_ptr(), pk, qp, stats.data_ptr(),
+        plan.recon(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, pitch, odf.data_ptr(), pk, qp, stats.data_ptr(),
                    finalize=False, stream=stream)
         if ev: ev[1].record()
         D.qa_scale(qp, nvox, d_stats=stats.data_ptr(), stream=stream)
@@ -333,7 +334,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_dwi = torch.empty((nvol, nvox), dtype=torch.float32, pin_memory=True)
-        h_dwi.copy_(dwi)
+        h_dwi.copy_(dwi[:, :nvox])
         torch.cuda.synchronize()
         del dwi, odf, peak
         torch.cuda.empty_cache()

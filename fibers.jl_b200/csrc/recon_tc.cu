@@ -43,7 +43,7 @@ int launch_recon_simt_list(Plan* p, const ReconArgs& a, const int* d_list, const
 
 namespace {
 
-constexpr int N_EPI = 12;            // epilogue warps (multiple of 4: one per TMEM lane quarter)
+constexpr int N_EPI = 12;            // epilogue warps: 3 groups of 4 (one warp per TMEM lane quarter); group k also writes peak k
 constexpr int N_CONV = 4;            // converter warps (multiple of 4)
 constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = W_CONV0 + N_CONV;
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
@@ -54,6 +54,7 @@ constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns e
 constexpr int TMEM_A_COL = 384;
 constexpr int VOX_CTA = 128;
 constexpr int EPI_THREADS = N_EPI * 32;
+static_assert(N_EPI == 12, "the output stage maps warp group k to peak k");
 constexpr float FP16_TARGET = 8192.f;   // the sampled maximum is scaled to <= 8192 (8x headroom to 65504)
 
 constexpr int KEY_ROW = VOX_CTA * 2;    // bytes per vertex row of the key tile
@@ -79,6 +80,7 @@ struct TcParams {
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
+    int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
     int dbg;                     // experiments only (FIBERS_TC_DEBUG)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
@@ -288,13 +290,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
     uint16_t* keys = (uint16_t*)(sB + NSTAGE * stage_bytes);              // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
     const int Mk = p.plain ? 0 : p.M;                                     // plain passes stage no keys
-    unsigned long long* s_ckey = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [CAND_CAP] exact (value, ~index) keys
-    unsigned long long* s_top = s_ckey + CAND_CAP;                        // [3][128] winners per voxel
+    unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [3][128] best (value, ~index) per voxel
     uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
     float* s_min = (float*)(s_cand + CAND_CAP);                           // [N_CPART][128]
     float* s_sum = s_min + N_CPART * VOX_CTA;                             // [N_CPART][128]
     float* s_dwi = s_sum + N_CPART * VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
-    uint64_t* bars = (uint64_t*)(s_dwi + DSTAGE * 32 * VOX_CTA);
+    uint4* s_nbr = (uint4*)(s_dwi + DSTAGE * 32 * VOX_CTA);               // [M] 8 x uint16 neighbour ids per vertex
+    uint64_t* bars = (uint64_t*)(s_nbr + Mk);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
     uint32_t* s_ncand = (uint32_t*)(d_empty + 1);
@@ -312,6 +314,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     }
     for (int i = threadIdx.x; i < 8 * VOX_CTA; i += TC_THREADS) keys[(size_t)Mk * VOX_CTA + i] = 0x8000;   // key 0
     if (threadIdx.x == 0) *s_ncand = 0u;
+    for (int i = threadIdx.x; i < Mk; i += TC_THREADS) s_nbr[i] = __ldg(reinterpret_cast<const uint4*>(p.nbr) + i);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -399,35 +402,52 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         }
     } else if (warp < W_EPI0) {
         // ===== converters: DWI fp32 -> clamp -> scale -> fp16 hi/lo -> TMEM ring ================
-        // One warp per TMEM lane quarter; thread == voxel.  The raw samples are staged through shared memory with
-        // 4-byte cp.async (any alignment / pitch, zero-fill for masked voxels and K padding): every thread reads back
-        // only what it copied itself, so the ring needs no barrier, holds no registers while the loads are in
-        // flight, and runs DSTAGE - 1 chunks (across tile boundaries) ahead of the conversion.
-        const int q = warp & 3;
+        // One warp per TMEM lane quarter; thread == voxel.  The raw samples are staged through a shared-memory ring
+        // with cp.async, DSTAGE - 1 chunks (across tile boundaries) ahead of the conversion, so no registers are
+        // held while the loads are in flight.  Aligned slabs (16-byte base, pitch % 4 == 0) move 4 voxels per
+        // copy: warp w fetches volumes 8w .. 8w+7 of every chunk for all 128 voxels and a 128-thread barrier
+        // publishes the chunk; otherwise every thread copies its own voxel 4 bytes at a time.
+        const int cw = warp - W_CONV0, q = warp & 3;
         const int vl = q * 32 + lane;                                   // TMEM lane == voxel within the CTA's 128
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t afull0 = mapa(smem_u32(&a_full[0]), 0);
-        const uint32_t sd32 = smem_u32(s_dwi + vl);                     // [DSTAGE][32][128] floats
+        const uint32_t sd0 = smem_u32(s_dwi);                           // [DSTAGE][32][128] floats
         constexpr int PF = DSTAGE - 1;
+        constexpr uint32_t STAGE_B = 32 * VOX_CTA * 4;
+        const bool vec = p.dwi_vec != 0;
         // prefetch cursor
         int p_ti = cluster_id, p_c = 0; uint32_t p_g = 0;
-        const float* p_src = p.dwi; bool p_inside = false;
+        int64_t p_vox0 = 0;
         auto prefetch = [&]() {
             if (p_ti < ntl) {
                 if (p_c == 0) {
                     const int ptile = ident ? p_ti : __ldg(p.tile_list + p_ti);
-                    const int64_t pvox = (int64_t)ptile * 256 + rank * VOX_CTA + vl;
-                    p_inside = pvox < p.nvox && p.mask[pvox] != 0;
-                    p_src = p.dwi + (p_inside ? pvox : 0);
+                    p_vox0 = (int64_t)ptile * 256 + rank * VOX_CTA;
                 }
-                const uint32_t dst = sd32 + (p_g % DSTAGE) * (32 * VOX_CTA * 4);
-                const float* src = p_src + (int64_t)(p_c * 32) * p.dwi_pitch;
+                const uint32_t dst = sd0 + (p_g % DSTAGE) * STAGE_B;
+                if (vec) {
+                    const int64_t v4 = p_vox0 + 4 * lane;
+                    const int64_t left = p.nvox - v4;
+                    const uint32_t full = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
+                    const float* src = p.dwi + (full ? v4 : 0) + (int64_t)(p_c * 32 + cw * 8) * p.dwi_pitch;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int k = p_c * 32 + j;
-                    const uint32_t sz = (p_inside && k < p.K) ? 4u : 0u;                 // 0: zero-fill, nothing is read
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + j * (VOX_CTA * 4)), "l"(k < p.K ? src : p_src), "r"(sz) : "memory");
-                    src += p.dwi_pitch;
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = p_c * 32 + cw * 8 + j;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                                     ::"r"(dst + (uint32_t)(cw * 8 + j) * (VOX_CTA * 4) + lane * 16), "l"(k < p.K ? src : p.dwi), "r"(k < p.K ? full : 0u) : "memory");
+                        src += p.dwi_pitch;
+                    }
+                } else {
+                    const int64_t pvox = p_vox0 + vl;
+                    const bool inb = pvox < p.nvox;
+                    const float* src = p.dwi + (inb ? pvox : 0) + (int64_t)(p_c * 32) * p.dwi_pitch;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = p_c * 32 + j;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;"
+                                     ::"r"(dst + (uint32_t)j * (VOX_CTA * 4) + vl * 4), "l"(k < p.K ? src : p.dwi), "r"((inb && k < p.K) ? 4u : 0u) : "memory");
+                        src += p.dwi_pitch;
+                    }
                 }
                 if (++p_c == nk32) { p_c = 0; p_ti += ncluster; }
             }
@@ -438,19 +458,24 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         for (int i = 0; i < PF; ++i) prefetch();
         uint32_t it = 0, g32 = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
+            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
+            const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
+            const bool inside = vox < p.nvox && p.mask[vox] != 0;
             if (warp == W_CONV0) TRACE(9);
 #pragma unroll 1
             for (int c = 0; c < nk32; ++c, ++g32) {
-                prefetch();
-                asm volatile("cp.async.wait_group %0;" ::"n"(PF) : "memory");
-                const uint32_t sbase = sd32 + (g32 % DSTAGE) * (32 * VOX_CTA * 4);
+                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");   // this thread's copies of chunk g32 have landed
+                named_bar(2, N_CONV * 32);                              // ... everybody's have; chunk g32 - 1 is no longer read
+                prefetch();                                             // refills the stage chunk g32 - 1 used
+                const uint32_t sbase = sd0 + (g32 % DSTAGE) * STAGE_B + vl * 4;
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(sbase + j * (VOX_CTA * 4)));
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float v0 = fmaxf(x[2 * j], 0.f) * scale, v1 = fmaxf(x[2 * j + 1], 0.f) * scale;   // s[s<0] = 0
+                    // s[s<0] = 0; voxels outside the mask contribute zeros
+                    const float v0 = inside ? fmaxf(x[2 * j], 0.f) * scale : 0.f, v1 = inside ? fmaxf(x[2 * j + 1], 0.f) * scale : 0.f;
                     const __half2 h = __floats2half2_rn(v0, v1);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -655,7 +680,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             for (int e = et; e < ncand; e += EPI_THREADS) {
                 const uint32_t ent = s_cand[e];
                 const int cv = (int)(ent >> 8), cx = (int)(ent & 0xFFu);
-                const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(p.nbr + cv * NBR_W));     // 8 x uint16 neighbour ids
+                const float* col = p.odf + vox0 + cx;
+                const float c = __ldcg(col + (int64_t)cv * p.out_pitch);       // in flight while the keys are compared
+                const uint4 n0 = s_nbr[cv];
                 const uint32_t nn[4] = {n0.x, n0.y, n0.z, n0.w};
                 const uint32_t kc = keys[cv * VOX_CTA + cx];
                 uint32_t kn = 0;
@@ -664,8 +691,6 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
                     kn = max(kn, (uint32_t)keys[(n != NBR_NONE ? n : (uint32_t)M) * VOX_CTA + cx]);
                 }
-                const float* col = p.odf + vox0 + cx;
-                const float c = __ldcg(col + (int64_t)cv * p.out_pitch);
                 bool ok = c > 0.f;
                 if (kc <= kn) {                                          // keys tie: repeat the neighbour test in fp32
                     float nv[8];
@@ -677,55 +702,55 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) ok = ok && (c > nv[k]);
                 }
-                s_ckey[e] = ok ? (((unsigned long long)__float_as_uint(c) << 32) | (0xFFFFFFFFu - (uint32_t)cv)) : 0ull;
+                if (ok) {
+                    // Insert (value, ~index) into the voxel's sorted triple: atomicMax returns what it displaced, and the
+                    // smaller of the two moves down one level.  Larger value wins, equal values -> smaller index wins
+                    // (the reference's stable order).  Every level ends up with the right key whatever the interleaving.
+                    unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (0xFFFFFFFFu - (uint32_t)cv);
+#pragma unroll
+                    for (int lvl = 0; lvl < 3; ++lvl) {
+                        const unsigned long long old = atomicMax(&s_top[lvl * VOX_CTA + cx], key);
+                        key = old < key ? old : key;
+                        if (key == 0ull) break;
+                    }
+                }
             }
             named_bar(1, EPI_THREADS);
-            // ---- three rounds of 64-bit atomicMax on (value, ~index): larger value wins, equal values -> smaller
-            //      index wins (the reference's stable order); a key joins round r only if it lost every earlier one ----
-#pragma unroll
-            for (int rnd = 0; rnd < 3; ++rnd) {
-                for (int e = et; e < ncand; e += EPI_THREADS) {
-                    const unsigned long long k = s_ckey[e];
-                    const int cx = (int)(s_cand[e] & 0xFFu);
-                    if (k != 0ull && (rnd == 0 || k < s_top[(rnd - 1) * VOX_CTA + cx])) atomicMax(&s_top[rnd * VOX_CTA + cx], k);
-                }
-                named_bar(1, EPI_THREADS);
-            }
             if (warp == W_EPI0) TRACE(6);
-            // ---- outputs: one thread per voxel (epilogue warps 0-3) ----
-            if (ew < 4) {
-                const int ov = ew * 32 + lane;                          // voxel within the CTA
+            // ---- outputs: warp group k (4 warps = 128 voxels) writes peak k; group 0 also owns the statistics ----
+            {
+                const int k = ew >> 2;                                  // 0..2 (N_EPI == 12)
+                const int ov = (ew & 3) * 32 + lane;                    // voxel within the CTA
                 const int64_t ovox = vox0 + ov;
                 const bool ook = ovox < p.nvox;
                 float omin = s_min[ov], osum = s_sum[ov];
 #pragma unroll
                 for (int cp = 1; cp < N_CPART; ++cp) { omin = fminf(omin, s_min[cp * VOX_CTA + ov]); osum += s_sum[cp * VOX_CTA + ov]; }
-                float mean = osum / (float)M;
-                // fp16 overflow of the scaled signal (or non-finite input), or more listed pairs than the list holds
-                const bool bad = ook && (!(fabsf(osum) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
-                if (ook) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const unsigned long long key = s_top[k * VOX_CTA + ov];
-                        const bool ok = key != 0ull;
-                        const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
-                        const float val = __uint_as_float((uint32_t)(key >> 32));
-                        p.peak[k][ovox]                   = ok ? __ldg(p.vert + id * 3 + 0) : 0.f;
-                        p.peak[k][ovox + p.out_pitch]     = ok ? __ldg(p.vert + id * 3 + 1) : 0.f;
-                        p.peak[k][ovox + 2 * p.out_pitch] = ok ? __ldg(p.vert + id * 3 + 2) : 0.f;
-                        p.qa[k][ovox] = ok ? val - omin : 0.f;
-                        if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
-                    }
+                if (ook && k < 3) {
+                    const unsigned long long key = s_top[k * VOX_CTA + ov];
+                    const bool ok = key != 0ull;
+                    const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
+                    const float val = __uint_as_float((uint32_t)(key >> 32));
+                    p.peak[k][ovox]                   = ok ? __ldg(p.vert + id * 3 + 0) : 0.f;
+                    p.peak[k][ovox + p.out_pitch]     = ok ? __ldg(p.vert + id * 3 + 1) : 0.f;
+                    p.peak[k][ovox + 2 * p.out_pitch] = ok ? __ldg(p.vert + id * 3 + 2) : 0.f;
+                    p.qa[k][ovox] = ok ? val - omin : 0.f;
+                    if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
                 }
-                if (!ook || bad) mean = -CUDART_INF_F;
-                const unsigned anybad = __ballot_sync(0xffffffffu, bad);
+                if (k == 0) {
+                    float mean = osum / (float)M;
+                    // fp16 overflow of the scaled signal (or non-finite input), or more listed pairs than the list holds
+                    const bool bad = ook && (!(fabsf(osum) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
+                    if (!ook || bad) mean = -CUDART_INF_F;
+                    const unsigned anybad = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mean = fmaxf(mean, __shfl_xor_sync(0xffffffffu, mean, o));
-                if (lane == 0) {
-                    if (mean > -CUDART_INF_F) atomicMax(p.stats, f2ord(mean));
-                    if (anybad) {                                       // recompute this 64-voxel tile with the SIMT kernel
-                        const int slot = atomicAdd(p.fix_count, 1);
-                        if (slot < p.fix_cap) p.fix_list[slot] = (int)((vox0 + ew * 32) >> 6);
+                    for (int o = 16; o > 0; o >>= 1) mean = fmaxf(mean, __shfl_xor_sync(0xffffffffu, mean, o));
+                    if (lane == 0) {
+                        if (mean > -CUDART_INF_F) atomicMax(p.stats, f2ord(mean));
+                        if (anybad) {                                   // recompute this 64-voxel tile with the SIMT kernel
+                            const int slot = atomicAdd(p.fix_count, 1);
+                            if (slot < p.fix_cap) p.fix_list[slot] = (int)((vox0 + (ew & 3) * 32) >> 6);
+                        }
                     }
                 }
             }
@@ -746,7 +771,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 }
 
 size_t tc_smem_bytes(int M, int Nh) {
-    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 12 + 3 * VOX_CTA * 8 +
+    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + 3 * VOX_CTA * 8 +
                N_CPART * VOX_CTA * 2 * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
@@ -919,6 +944,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         if (ps.plain && !a.pdf) continue;
         TcParams tp{};
         tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
+        tp.dwi_vec = ((uintptr_t)a.dwi % 16 == 0) && (a.dwi_pitch % 4 == 0);
         tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = ps.rows; tp.Npad = ps.Npad; tp.N1 = ps.N1; tp.N2 = ps.N2;
         tp.odf = out; tp.out_pitch = a.out_pitch;
         for (int k = 0; k < 3; ++k) { tp.peak[k] = a.peak[k]; tp.qa[k] = a.qa[k]; }

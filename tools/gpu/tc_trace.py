@@ -14,9 +14,9 @@ shape = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "145,174,14
 nvox = int(np.prod(shape))
 bval, bvec = bench.make_tables()
 dev = torch.device("cuda", 0)
-dwi = bench.synth_dwi_device(torch, nvox, bval, bvec, 1, dev)
 mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
 pitch = (nvox + 63) // 64 * 64
+dwi = bench.synth_dwi_device(torch, nvox, bval, bvec, 1, dev, pitch=pitch)
 odf = torch.empty((321, pitch), dtype=torch.float32, device=dev)
 peak = [torch.empty((3, pitch), dtype=torch.float32, device=dev) for _ in range(3)]
 qa = [torch.empty(nvox, dtype=torch.float32, device=dev) for _ in range(3)]
@@ -24,7 +24,7 @@ stats = torch.zeros(2, dtype=torch.int32, device=dev)
 D.set_kernel("tc")
 plan = D.Plan("gqi", 0, bval, bvec, F.sphere_642, 1.25)
 for _ in range(2):
-    plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
+    plan.recon(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
                [q.data_ptr() for q in qa], stats.data_ptr(), finalize=True, stream=0)
 torch.cuda.synchronize()
 t = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64).reshape(16, 32)
