@@ -293,8 +293,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [3][128] best (value, ~index) per voxel
     uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
     float* s_min = (float*)(s_cand + CAND_CAP);                           // [N_CPART][128]
-    float* s_sum = s_min + N_CPART * VOX_CTA;                             // [N_CPART][128]
-    float* s_dwi = s_sum + N_CPART * VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
+    float* s_mean = s_min + N_CPART * VOX_CTA;                            // [128] mean ODF per voxel (from the extra matrix row)
+    float* s_dwi = s_mean + VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
     uint4* s_nbr = (uint4*)(s_dwi + DSTAGE * 32 * VOX_CTA);               // [M] 8 x uint16 neighbour ids per vertex
     uint64_t* bars = (uint64_t*)(s_nbr + Mk);
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
@@ -530,22 +530,24 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             tc_fence_after();
             if (warp == W_EPI0) TRACE(2);
             // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + 16-bit key tile ----
-            // key(val) = clamp(ceil(val * ks), 0, 32767), ks = 32768 / (KEY_WINDOW * mean): monotone in val, key >= 1
-            // <=> val > 0.  Stored as 0x8000 | key = the low mantissa bits of fma.rp(val, ks, 2^23 + 2^15) (no
-            // conversion instruction); the always-set bit 15 lets one 32-bit subtraction compare two packed keys.
-            float mn = CUDART_INF_F, sum = 0.f;
+            // key(val) = ceil(32767 * clamp(val * ks, 0, 1)), ks = 1 / (KEY_WINDOW * mean): monotone in val, key >= 1
+            // <=> val > 0.  Stored as 0x8000 | key = the low mantissa bits of fma.rp(sat(val * ks), 32767, 2^23 + 2^15)
+            // (no conversion instruction); the always-set bit 15 lets one 32-bit subtraction compare two packed keys.
+            float mn = CUDART_INF_F, meanv = 0.f;
             {
                 float ks = 0.f;
                 if (!p.plain) {
-                    const float meanv = __uint_as_float(tmem_ld1(lane_addr + M)) * scl;   // extra matrix row M: mean of the ODF rows
+                    meanv = __uint_as_float(tmem_ld1(lane_addr + M)) * scl;   // extra matrix row M: mean of the ODF rows
                     tmem_wait_ld();
-                    ks = (meanv > 0.f && meanv < CUDART_INF_F) ? (32768.f / KEY_WINDOW) / meanv : 1e-30f;
+                    ks = (meanv > 0.f && meanv < CUDART_INF_F) ? (1.f / KEY_WINDOW) / meanv : 1e-30f;
                 }
                 float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
                 uint16_t* kp = keys + c_begin * VOX_CTA + vl;
                 const int64_t pitch = p.out_pitch;
                 const bool plain = p.plain != 0;
                 const bool vst = vok && !(p.dbg & 1);
+                // key = 0x8000 | ceil(32767 * sat(val * ks)): two instructions (FMUL.SAT, FFMA.RP), the low 16 bits of
+                // the second result are the stored key
                 auto process = [&](const uint32_t (&r)[16], int c0) {
                     const int nrow = min(16, M - c0);                   // warp-uniform
                     if (plain) {
@@ -562,24 +564,21 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                             const float val = __uint_as_float(r[j]) * scl;
                             if (vst) *g = val;
                             g += pitch;
-                            float y = __fmaf_ru(val, ks, 8421376.f);
-                            y = fminf(fmaxf(y, 8421376.f), 8421376.f + 32767.f);
+                            const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                             kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                            mn = fminf(mn, val); sum += val;
+                            mn = fminf(mn, val);
                         }
                     } else {
                         float* g = gp;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
+                        for (int j = 0; j < 16; ++j, g += pitch) {
                             if (j < nrow) {
                                 const float val = __uint_as_float(r[j]) * scl;
-                                if (vok) *g = val;
-                                float y = __fmaf_ru(val, ks, 8421376.f);
-                                y = fminf(fmaxf(y, 8421376.f), 8421376.f + 32767.f);
+                                if (vst) *g = val;
+                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                                 kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                                mn = fminf(mn, val); sum += val;
+                                mn = fminf(mn, val);
                             }
-                            g += pitch;
                         }
                     }
                     gp += 16 * pitch; kp += 16 * VOX_CTA;
@@ -602,7 +601,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
             if (warp == W_EPI0) TRACE(3);
             if (p.plain) continue;                                      // rows only (DSI pdf): nothing is staged
-            s_min[cpart * VOX_CTA + vl] = mn; s_sum[cpart * VOX_CTA + vl] = sum;
+            s_min[cpart * VOX_CTA + vl] = mn;
+            if (cpart == 0) s_mean[vl] = meanv;
             named_bar(1, EPI_THREADS);                                  // key tile + this tile's ODF stores visible to the group
             if (warp == W_EPI0) TRACE(4);
             // ---- phase 2: scan.  A vertex can only be a local maximum (value > 0, > every mesh neighbour) if its
@@ -723,9 +723,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 const int ov = (ew & 3) * 32 + lane;                    // voxel within the CTA
                 const int64_t ovox = vox0 + ov;
                 const bool ook = ovox < p.nvox;
-                float omin = s_min[ov], osum = s_sum[ov];
+                float omin = s_min[ov];
 #pragma unroll
-                for (int cp = 1; cp < N_CPART; ++cp) { omin = fminf(omin, s_min[cp * VOX_CTA + ov]); osum += s_sum[cp * VOX_CTA + ov]; }
+                for (int cp = 1; cp < N_CPART; ++cp) omin = fminf(omin, s_min[cp * VOX_CTA + ov]);
                 if (ook && k < 3) {
                     const unsigned long long key = s_top[k * VOX_CTA + ov];
                     const bool ok = key != 0ull;
@@ -738,9 +738,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
                 }
                 if (k == 0) {
-                    float mean = osum / (float)M;
-                    // fp16 overflow of the scaled signal (or non-finite input), or more listed pairs than the list holds
-                    const bool bad = ook && (!(fabsf(osum) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
+                    float mean = s_mean[ov];
+                    // fp16 overflow of the scaled signal (every accumulator column of the voxel, the mean row included, is
+                    // then non-finite), or more listed pairs than the list holds
+                    const bool bad = ook && (!(fabsf(mean) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
                     if (!ook || bad) mean = -CUDART_INF_F;
                     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
@@ -772,7 +773,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 
 size_t tc_smem_bytes(int M, int Nh) {
     size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + 3 * VOX_CTA * 8 +
-               N_CPART * VOX_CTA * 2 * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
+               (N_CPART + 1) * VOX_CTA * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
 
@@ -902,7 +903,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     TcState* st = reinterpret_cast<TcState*>(p->tc);
     if (!st) return fail(FIBERS_ERR_ARG, "plan has no tensor-core state");
     if (a.nvox <= 0) return 0;
-    if (a.nvox > 0x7FFFFFFFLL * 32) return fail(FIBERS_ERR_ARG, "slab too large");
+    if (a.nvox > 0x7FFFFFFFLL * 32 || a.out_pitch >= (1ll << 30)) return fail(FIBERS_ERR_ARG, "slab too large");
     const int64_t ntile64 = (a.nvox + 63) / 64, ntile256 = (a.nvox + 255) / 256;
     const int64_t need = 4 + 2 * ntile64 + 2 * ntile256 + 8;   // [0] maxbits [1] fix_count [2] tile_count | fix list | tile list | tile flags
     if (st->scratch_cap < need) {
