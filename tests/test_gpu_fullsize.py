@@ -149,3 +149,49 @@ def test_full_volume_dti_invariants(env):
     assert torch.all((v1 * v2).sum(dim=0)[ok].abs() < 1e-3)
     f = fa[0][ok]
     assert torch.isfinite(f).all() and f.min() >= 0 and f.median() > 0.1
+
+
+def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
+    """The tensor-core kernel stages the DWI slab with 16-byte copies when the rows are 16-byte aligned and with
+    4-byte copies otherwise; both must give the same bits.  Odd voxel count, partial last tile, ragged mask."""
+    import torch
+    import bench
+    import fibers_jl_b200 as F
+    from fibers_jl_b200 import device as D
+    dev = torch.device("cuda", 0)
+    bval, bvec = bench.make_tables()
+    nvox = 50003                                              # not a multiple of 4; last 256-voxel tile is partial
+    pitch_al, pitch_un = (nvox + 63) // 64 * 64, nvox + 1     # 50004 * 4 bytes: rows not 16-byte aligned
+    dwi_al = bench.synth_dwi_device(torch, nvox, bval, bvec, 5, dev, pitch=pitch_al)
+    dwi_un = torch.zeros((bval.shape[0], pitch_un), dtype=torch.float32, device=dev)
+    dwi_un[:, :nvox] = dwi_al[:, :nvox]
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    mask = (torch.rand(nvox, generator=g, device=dev) < 0.7).to(torch.uint8)
+    mask[1024:2048] = 0                                       # whole tiles without a mask voxel
+    res = []
+    D.set_kernel("tc")
+    try:
+        plan = D.Plan("gqi", 0, bval, bvec, F.sphere_642, 1.25)
+        assert plan.kernel == "tc"
+        for dwi, dp in ((dwi_al, pitch_al), (dwi_un, pitch_un)):
+            opitch = pitch_al
+            odf = torch.full((321, opitch), 7.0, dtype=torch.float32, device=dev)
+            peak = [torch.full((3, opitch), 7.0, dtype=torch.float32, device=dev) for _ in range(3)]
+            qa = [torch.full((opitch,), 7.0, dtype=torch.float32, device=dev) for _ in range(3)]
+            idx = torch.full((3, opitch), 7, dtype=torch.int16, device=dev)
+            stats = torch.zeros(2, dtype=torch.int32, device=dev)
+            plan.recon(dwi.data_ptr(), dp, mask.data_ptr(), nvox, opitch, odf.data_ptr(), [p.data_ptr() for p in peak],
+                       [q.data_ptr() for q in qa], stats.data_ptr(), d_peak_idx=idx.data_ptr(), finalize=True)
+            torch.cuda.synchronize()
+            res.append((odf[:, :nvox].clone(), [p[:, :nvox].clone() for p in peak], [q[:nvox].clone() for q in qa],
+                        idx[:, :nvox].clone(), int(stats[0].item())))
+    finally:
+        D.set_kernel("auto")
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and a[4] == b[4]
+    for k in range(3):
+        assert torch.equal(a[1][k], b[1][k]) and torch.equal(a[2][k], b[2][k])
+    # voxels outside the mask are zero-filled, inside they are reconstructed
+    out = mask == 0
+    assert (a[0][:, out] == 0).all() and (a[3][:, out] == -1).all()
+    assert (a[0][:, ~out].abs().amax(dim=0) > 0).all()

@@ -31,8 +31,8 @@ def timeit(fn, steps=10, warm=3):
     return e0.elapsed_time(e1) / steps
 
 
-def synth(nvox, bval, bvec, seed):
-    return bench.synth_dwi_device(torch, nvox, bval, bvec, seed, dev)
+def synth(nvox, bval, bvec, seed, pitch=None):
+    return bench.synth_dwi_device(torch, nvox, bval, bvec, seed, dev, pitch=pitch)
 
 
 def report(name, nvox, ms, bytes_per_voxel, flops_per_voxel=0, note=""):
@@ -56,10 +56,11 @@ def run_dti(shape, bval, bvec, tag):
     report(f"adc_fit {tag}", nvox, ms, 4 * N + 9, 5 * N)
 
 
-def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642):
+def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642, aligned=True):
     nvox = int(np.prod(shape)); N = bval.shape[0]; M = odf_dirs.nvert
     pitch = (nvox + 63) // 64 * 64
-    dwi = synth(nvox, bval, bvec, 5)
+    dpitch = pitch if aligned else nvox                      # frame pitch of the DWI slab (16-byte aligned rows or not)
+    dwi = synth(nvox, bval, bvec, 5, dpitch)
     mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
     odf = torch.empty((M, pitch), dtype=torch.float32, device=dev)
     pdf = torch.empty((N, pitch), dtype=torch.float32, device=dev) if kind == "dsi" else None
@@ -69,7 +70,7 @@ def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642):
     D.set_kernel(kernel)
     plan = D.Plan(kind, 0, bval, bvec, odf_dirs)
     D.set_kernel("auto")
-    fn = lambda: plan.recon(dwi.data_ptr(), nvox, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
+    fn = lambda: plan.recon(dwi.data_ptr(), dpitch, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
                             [q.data_ptr() for q in qa], stats.data_ptr(), d_pdf=pdf.data_ptr() if pdf is not None else 0, finalize=True)
     ms = timeit(fn, steps=5 if kind == "dsi" else 10)
     if kind == "gqi":
@@ -83,6 +84,7 @@ run_dti((64, 64, 40), b1, g1, "cfg1 64x64x40x31")
 b2, g2 = bench.make_tables()
 run_dti((145, 174, 145), b2, g2, "cfg4 145x174x145x288")
 run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288")
+run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288, DWI pitch = nvox (rows not 16-byte aligned)", aligned=False)
 run_recon("gqi", (145, 174, 145), b2, g2, "simt", "cfg2 145x174x145x288")
 b5, g5 = phantom.shells_table(8, [(4000.0, 120)])
 run_recon("gqi", (400, 400, 38), b5, g5, "tc", "cfg5 slab 400x400x38x128 (1/8 of 400x400x300)")
