@@ -81,7 +81,6 @@ struct TcParams {
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
-    int dbg;                     // experiments only (FIBERS_TC_DEBUG)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
@@ -129,19 +128,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-// kBackoff: non-critical waiters let the hardware suspend them (try_wait with a time hint) instead of polling,
-// so that they do not steal issue slots from the working warps
-template <bool kBackoff = false>
+// kBackoff: non-critical waiters sleep between polls so that they do not steal issue slots from the working warps
+// (measured: a polling loop without the sleep issues ~10 k instructions per tile and role)
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; ++spin) {
-        if (kBackoff)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
-        else
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (kSleepNs > 0 && !ok) __nanosleep(kSleepNs);
         if (spin > (1u << 26)) __trap();        // never hang the GPU: a lost signal becomes a launch error
     }
 }
@@ -208,32 +204,40 @@ __global__ void sample_max_kernel(const float* __restrict__ dwi, int64_t pitch, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile scan: one CTA per 256-voxel tile.  Tiles without a single mask voxel are zero-filled here (the
+// tile scan: one warp per 256-voxel tile.  Tiles without a single mask voxel are zero-filled here (the
 // reference leaves them at the zero of its MRI constructor) and never reach the reconstruction kernel;
-// the others are appended to the work list.  On a brain-masked volume this removes most of the tiles.
+// the others are counted and, if any tile is empty, compacted into the work list.  On a brain-masked
+// volume this removes most of the tiles.
 // ---------------------------------------------------------------------------------------------
 struct ScanOut { float* ptr[9]; int rows[9]; int n; int16_t* idx; };
 
+// one WARP per 256-voxel tile (8 mask bytes per lane), 8 tiles per CTA
 __global__ void __launch_bounds__(256) tile_scan_kernel(const uint8_t* __restrict__ mask, int64_t nvox, int64_t out_pitch, ScanOut o,
-                                                         int32_t* stats, int* tile_flag) {
-    const int64_t vox = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int inside = vox < nvox && mask[vox] != 0;
-    if (__syncthreads_or(inside)) {
-        if (threadIdx.x == 0) tile_flag[blockIdx.x] = 1;
-        return;
-    }
-    if (threadIdx.x == 0) tile_flag[blockIdx.x] = 0;
-    if (vox < nvox) {
-        for (int a = 0; a < o.n; ++a)
-            for (int r = 0; r < o.rows[a]; ++r) o.ptr[a][(int64_t)r * out_pitch + vox] = 0.f;
-        if (o.idx) for (int r = 0; r < 3; ++r) o.idx[(int64_t)r * out_pitch + vox] = (int16_t)-1;
-    }
-    if (threadIdx.x == 0 && stats) atomicMax(stats, f2ord(0.f));      // skipped voxels count as mean(odf) = 0 in odfmax
+                                                         int32_t* stats, int* tile_flag, int ntiles, int* tile_count) {
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tile >= ntiles) return;
+    const int64_t v0 = (int64_t)tile * 256 + lane * 8;
+    unsigned long long m = 0;
+    if (v0 + 8 <= nvox && (reinterpret_cast<uintptr_t>(mask) & 7) == 0) m = *reinterpret_cast<const unsigned long long*>(mask + v0);
+    else for (int j = 0; j < 8; ++j) if (v0 + j < nvox && mask[v0 + j]) m |= 1ull << (8 * j);
+    const bool any = __any_sync(0xffffffffu, m != 0ull);
+    if (lane == 0) { tile_flag[tile] = any ? 1 : 0; if (any) atomicAdd(tile_count, 1); }
+    if (any) return;
+    for (int a = 0; a < o.n; ++a)
+        for (int r = 0; r < o.rows[a]; ++r)
+            for (int j = lane; j < 256; j += 32) { const int64_t v = (int64_t)tile * 256 + j; if (v < nvox) o.ptr[a][(int64_t)r * out_pitch + v] = 0.f; }
+    if (o.idx)
+        for (int r = 0; r < 3; ++r)
+            for (int j = lane; j < 256; j += 32) { const int64_t v = (int64_t)tile * 256 + j; if (v < nvox) o.idx[(int64_t)r * out_pitch + v] = (int16_t)-1; }
+    if (lane == 0 && stats) atomicMax(stats, f2ord(0.f));      // skipped voxels count as mean(odf) = 0 in odfmax
 }
 
 // ordered compaction of the non-empty tiles (one block; ascending tile order keeps the DWI / ODF streams of
-// neighbouring clusters adjacent in memory)
-__global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restrict__ flag, int ntiles, int* list, int* count) {
+// neighbouring clusters adjacent in memory).  Nothing to do when no tile is empty: the kernel then walks the
+// identity.
+__global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restrict__ flag, int ntiles, int* list, const int* count) {
+    if (*count >= ntiles) return;
     __shared__ int s_part[1024];
     const int per = (ntiles + 1023) / 1024;
     const int t0 = threadIdx.x * per, t1 = min(ntiles, t0 + per);
@@ -249,7 +253,6 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restric
     }
     int pos = s_part[threadIdx.x] - c;
     for (int t = t0; t < t1; ++t) if (flag[t]) list[pos++] = t;
-    if (threadIdx.x == 1023) *count = s_part[1023];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,7 +344,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             TRACE(13);
             for (int c = 0; c < nk32; ++c, ++g) {
                 const int s = g % NSTAGE; const uint32_t use = g / NSTAGE;
-                mbar_wait<true>(&b_empty[s], (use & 1) ^ 1);
+                mbar_wait<200>(&b_empty[s], (use & 1) ^ 1);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * stage_bytes);       // both CTAs' bytes land on the leader's barrier
                     // one bulk tensor copy per stage: the global image is already in shared-memory order
@@ -360,7 +363,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             const uint32_t idesc2 = p.N2 ? make_idesc_f16(256, p.N2) : 0u;
             uint32_t g32 = 0, it = 0;
             for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {             // (this role only needs the tile count)
-                mbar_wait(d_empty, (it & 1) ^ 1);                    // epilogue of the previous tile has drained TMEM
+                mbar_wait<100>(d_empty, (it & 1) ^ 1);              // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 TRACE(0);
                 for (int c = 0; c < nk32; ++c, ++g32) {
@@ -484,7 +487,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 }
                 const int slot = g32 % ASLOT;
                 if (warp == W_CONV0 && c == 0) TRACE(10);
-                mbar_wait<true>(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
+                mbar_wait<100>(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
                 if (warp == W_CONV0 && c == 0) TRACE(11);
                 tc_fence_after();
                 const uint32_t col = lane_addr + TMEM_A_COL + slot * 32;
@@ -509,8 +512,6 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         const int M = p.M;
         const int cper = ((p.Npad + N_CPART - 1) / N_CPART + 15) & ~15;
         const int c_begin = cpart * cper, c_end = min(min(c_begin + cper, p.Npad), (M + 15) & ~15);
-        const int vper = ((M + N_EPI - 1) / N_EPI + 1) & ~1;           // even: a vertex pair never straddles two warps
-        const int va = min(M, ew * vper), vb = min(M, va + vper);
         uint32_t it = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
@@ -526,7 +527,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 scl = sc > 0.f ? inv_scale * (1.f / (p.dscale * sc)) : 0.f;     // inv_scale is a power of two: exact
             }
             for (int i = et; i < 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
-            mbar_wait<true>(d_full, it & 1);
+            mbar_wait<50>(d_full, it & 1);
             tc_fence_after();
             if (warp == W_EPI0) TRACE(2);
             // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + 16-bit key tile ----
@@ -545,7 +546,6 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 uint16_t* kp = keys + c_begin * VOX_CTA + vl;
                 const int64_t pitch = p.out_pitch;
                 const bool plain = p.plain != 0;
-                const bool vst = vok && !(p.dbg & 1);
                 // key = 0x8000 | ceil(32767 * sat(val * ks)): two instructions (FMUL.SAT, FFMA.RP), the low 16 bits of
                 // the second result are the stored key
                 auto process = [&](const uint32_t (&r)[16], int c0) {
@@ -562,7 +562,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float val = __uint_as_float(r[j]) * scl;
-                            if (vst) *g = val;
+                            if (vok) *g = val;
                             g += pitch;
                             const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                             kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
@@ -574,7 +574,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                         for (int j = 0; j < 16; ++j, g += pitch) {
                             if (j < nrow) {
                                 const float val = __uint_as_float(r[j]) * scl;
-                                if (vst) *g = val;
+                                if (vok) *g = val;
                                 const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                                 kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
                                 mn = fminf(mn, val);
@@ -612,6 +612,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
             {
                 const uint32_t kb = smem_u32(keys) + lane * 8;
+                const uint32_t ncand32 = smem_u32(s_ncand);
                 auto ld = [&](uint32_t off) {
                     uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
                 };
@@ -619,33 +620,39 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     return umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f));
                 };
                 const bool wide = p.nbw > 6;                            // warp-uniform (meshes with degree 7-8)
-                int v = va;
-                const uint32_t* op = c_nbr_off + v * NBR_W;             // running pointer into the offset table
+                // Vertex pairs are dealt round-robin to the warps (pair ew, ew + N_EPI, ...): ODF peaks are spatially
+                // compact, so contiguous ranges would give all the listing work of a tile to one or two warps.
+                const int npair = (M + 1) >> 1;
+                auto pair_vertex = [&](int pi) { return 2 * min(pi, npair); };      // past the end -> sentinel rows
+                int pi = ew;
+                int v = pair_vertex(pi), vn = pair_vertex(pi + N_EPI);
+                const uint32_t* op = c_nbr_off + v * NBR_W;
                 uint4 oA0 = *reinterpret_cast<const uint4*>(op), oB0 = *reinterpret_cast<const uint4*>(op + 8);
                 uint2 oA1 = *reinterpret_cast<const uint2*>(op + 4), oB1 = *reinterpret_cast<const uint2*>(op + 12);
                 uint2 cA = ld(v * KEY_ROW), cB = ld((v + 1) * KEY_ROW);
                 uint2 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
                 uint2 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
-                op += 16;
+                op = c_nbr_off + vn * NBR_W;
                 oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
                 oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
-                uint32_t crow = (v + 2) * KEY_ROW;
-                for (; v < vb; v += 2) {
+                for (; pi < npair; pi += N_EPI) {
                     // reduce pair i
                     uint32_t mAx = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x), mAy = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
                     uint32_t mBx = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x), mBy = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
                     if (wide) {
-                        const uint2 wA = *reinterpret_cast<const uint2*>(op - 16 + 6), wB = *reinterpret_cast<const uint2*>(op - 16 + 14);
+                        const uint2 wA = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 6), wB = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 14);
                         const uint2 a6 = ld(wA.x), a7 = ld(wA.y), b6 = ld(wB.x), b7 = ld(wB.y);
                         mAx = umax2(mAx, umax2(a6.x, a7.x)); mAy = umax2(mAy, umax2(a6.y, a7.y));
                         mBx = umax2(mBx, umax2(b6.x, b7.x)); mBy = umax2(mBy, umax2(b6.y, b7.y));
                     }
                     const uint2 kA = cA, kB = cB;
                     // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
-                    cA = ld(crow); cB = ld(crow + KEY_ROW); crow += 2 * KEY_ROW;
+                    const int vcur = v;
+                    v = vn; vn = pair_vertex(pi + 2 * N_EPI);
+                    cA = ld(v * KEY_ROW); cB = ld((v + 1) * KEY_ROW);
                     a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z); a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y);
                     b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y);
-                    op += 16;
+                    op = c_nbr_off + vn * NBR_W;
                     oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
                     oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
                     // stored keys have bit 15 set, so per 16-bit half  (k - t + 0x8000) has bit 15 set  <=>  k >= t,
@@ -660,11 +667,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                             const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
                                                ((hBx >> 11) & 0x00100010u) | ((hBy >> 9) & 0x00400040u);
                             uint32_t fl = (w & 0x55u) | ((w >> 15) & 0xAAu);
-                            uint32_t slot = atomicAdd(s_ncand, (uint32_t)__popc(fl));
+                            uint32_t slot;                              // (inline PTX: one ATOMS per warp instead of the compiler's
+                            //  vote + prefix-scan aggregation -- only one to three lanes get here)
+                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(ncand32), "r"((uint32_t)__popc(fl)) : "memory");
                             while (fl) {
                                 const int h = __ffs(fl) - 1;
                                 fl &= fl - 1;
-                                if (slot < (uint32_t)CAND_CAP) s_cand[slot] = ((uint32_t)(v + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
+                                if (slot < (uint32_t)CAND_CAP) s_cand[slot] = ((uint32_t)(vcur + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
                                 ++slot;
                             }
                         }
@@ -934,7 +943,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         for (int k = 0; k < 3; ++k) { so.ptr[n] = a.qa[k]; so.rows[n++] = 1; }
         so.n = n; so.idx = a.peak_idx;
         int* d_tile_flag = d_tile_list + ntile256;
-        tile_scan_kernel<<<(unsigned)ntile256, 256, 0, stream>>>(a.mask, a.nvox, a.out_pitch, so, a.stats, d_tile_flag);
+        tile_scan_kernel<<<(unsigned)((ntile256 + 7) / 8), 256, 0, stream>>>(a.mask, a.nvox, a.out_pitch, so, a.stats, d_tile_flag, (int)ntile256, st->d_scratch + 2);
         tile_compact_kernel<<<1, 1024, 0, stream>>>(d_tile_flag, (int)ntile256, d_tile_list, st->d_scratch + 2);
     }
     count_launch(3);
@@ -957,7 +966,6 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.nbw = st->nbw;
         tp.plain = ps.plain;
         tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
-        { const char* dbg = getenv("FIBERS_TC_DEBUG"); tp.dbg = dbg ? atoi(dbg) : 0; }
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
         long long* d_trace = nullptr;
         if (trace_path && *trace_path && ip == 0) {
