@@ -81,6 +81,7 @@ struct TcParams {
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
+    int cand_cap;                // capacity of the candidate list (<= CAND_CAP; tests shrink it to force the fall-back)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
@@ -673,7 +674,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                             while (fl) {
                                 const int h = __ffs(fl) - 1;
                                 fl &= fl - 1;
-                                if (slot < (uint32_t)CAND_CAP) s_cand[slot] = ((uint32_t)(vcur + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
+                                if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)(vcur + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
                                 ++slot;
                             }
                         }
@@ -685,7 +686,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             // ---- phase 3: settle the listed pairs on the exact fp32 values (this CTA wrote them a moment ago: L2 hits).
             //      Keys that decided strictly need the value only; ties re-run the neighbour test in fp32. ----
             const uint32_t ncand_raw = *s_ncand;
-            const int ncand = (int)min(ncand_raw, (uint32_t)CAND_CAP);
+            const int ncand = (int)min(ncand_raw, (uint32_t)p.cand_cap);
             for (int e = et; e < ncand; e += EPI_THREADS) {
                 const uint32_t ent = s_cand[e];
                 const int cv = (int)(ent >> 8), cx = (int)(ent & 0xFFu);
@@ -750,7 +751,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     float mean = s_mean[ov];
                     // fp16 overflow of the scaled signal (every accumulator column of the voxel, the mean row included, is
                     // then non-finite), or more listed pairs than the list holds
-                    const bool bad = ook && (!(fabsf(mean) < CUDART_INF_F) || ncand_raw > (uint32_t)CAND_CAP);
+                    const bool bad = ook && (!(fabsf(mean) < CUDART_INF_F) || ncand_raw > (uint32_t)p.cand_cap);
                     if (!ook || bad) mean = -CUDART_INF_F;
                     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
 #pragma unroll
@@ -955,6 +956,8 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         TcParams tp{};
         tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
         tp.dwi_vec = ((uintptr_t)a.dwi % 16 == 0) && (a.dwi_pitch % 4 == 0);
+        tp.cand_cap = CAND_CAP;
+        if (const char* cap = getenv("FIBERS_TC_CAND_CAP")) tp.cand_cap = std::max(0, std::min(CAND_CAP, atoi(cap)));
         tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = ps.rows; tp.Npad = ps.Npad; tp.N1 = ps.N1; tp.N2 = ps.N2;
         tp.odf = out; tp.out_pitch = a.out_pitch;
         for (int k = 0; k < 3; ++k) { tp.peak[k] = a.peak[k]; tp.qa[k] = a.qa[k]; }

@@ -286,3 +286,19 @@ def test_dsi_tc_overflow_fixup_and_uint16(F, sphere642):
     assert np.isfinite(got.odf.vol).all() and np.isfinite(got.pdf.vol).all()
     _check_recon(got, None, r64, v, f, 321, "dsi tc overflow fix-up")
     assert P.odf_rel_err(got.pdf.vol, r64["pdf"]) < P.ODF_TOL
+
+
+def test_gqi_tc_candidate_list_overflow_falls_back(F, sphere642, monkeypatch):
+    """A 128-voxel tile that lists more (voxel, vertex) pairs than the shared-memory list holds is handed to the
+    fp32 fix-up kernel.  The capacity is shrunk to 8 entries so that every tile takes that route."""
+    from fibers_jl_b200 import phantom
+    v, f = sphere642
+    ph = phantom.gqi_phantom((20, 16, 9), seed=23)
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    monkeypatch.setenv("FIBERS_TC_CAND_CAP", "8")
+    F.device.set_kernel("tc")
+    try:
+        got = F.gqi_rec(*_mri(F, ph))
+    finally:
+        F.device.set_kernel("auto")
+    _check_recon(got, None, r64, v, f, 321, "gqi tc candidate-list overflow")
