@@ -49,6 +49,7 @@ SIGNATURES = {
     "fibers_adc_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _i]),
     "fibers_gqi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _f] + [_p] * 8 + [_i]),
     "fibers_dsi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i] + [_p] * 9 + [_i]),
+    "fibers_dti_gqi_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 10 + [_p, _i, _p, _i, _f] + [_p] * 7 + [_i]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),
     "fibers_adc_plan_create": (_i, [_p, _i, _i, _p]),
     "fibers_gqi_plan_create": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _i, _f]),

@@ -358,6 +358,10 @@ struct HostJob {
     std::vector<std::pair<void*, int>> out_f32;     // (ptr, nframes) float outputs in kernel order
     float* qa[3] = {nullptr, nullptr, nullptr};
     int16_t* peak_idx = nullptr; uint8_t* valid = nullptr;
+    // optional companion DTI fit on the same resident slab (fibers_dti_gqi_fit): one H2D of the DWI feeds both
+    std::function<int(Plan**, int)> make_plan2;
+    uint64_t plan2_key = 0;
+    std::vector<std::pair<void*, int>> out2_f32;    // the 10 DTI outputs in kernel order
 };
 
 struct Rendezvous {       // cross-shard reduction of odfmax (host side; no device collective)
@@ -382,6 +386,7 @@ struct DeviceCache {
     char* slab[3] = {nullptr, nullptr, nullptr}; size_t slab_bytes = 0;
     float* qa = nullptr; size_t qa_bytes = 0; int32_t* stats = nullptr;
     Plan* plan = nullptr; uint64_t plan_key = 0;
+    Plan* plan2 = nullptr; uint64_t plan2_key = 0;     // companion DTI plan of the fused entry point
 };
 static DeviceCache g_cache[64];
 
@@ -398,7 +403,8 @@ static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
 
 static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* rv, int* out_code, std::string* out_err) {
     int code = 0; std::string err;
-    Plan* plan = nullptr;
+    Plan* plan = nullptr; Plan* plan2 = nullptr;
+    const bool fused = (bool)job.make_plan2;
     constexpr int NSLOT = 3;
     cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
     char* slab[NSLOT] = {nullptr, nullptr, nullptr};
@@ -423,9 +429,19 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
                 if (code) { err = g_err; goto done; }
                 if (dc) { dc->plan = plan; dc->plan_key = job.plan_key; }
             }
+            if (fused) {
+                if (dc && dc->plan2 && dc->plan2_key == job.plan2_key && job.plan2_key != 0) plan2 = dc->plan2;
+                else {
+                    if (dc && dc->plan2) { plan_free(dc->plan2); dc->plan2 = nullptr; }
+                    code = job.make_plan2(&plan2, device);
+                    if (code) { err = g_err; goto done; }
+                    if (dc) { dc->plan2 = plan2; dc->plan2_key = job.plan2_key; }
+                }
+            }
             // per-voxel device bytes of one pipeline slot
             int out_frames = 0;
             for (auto& o : job.out_f32) out_frames += o.second;
+            for (auto& o : job.out2_f32) out_frames += o.second;
             const int64_t per_vox = (int64_t)job.nvol * 4 + (job.dtype != FIBERS_F32 ? (int64_t)job.nvol * esz : 0)
                                   + 1 + (int64_t)out_frames * 4 + 6 + 1;
             size_t free_b = 0, total_b = 0;
@@ -479,6 +495,8 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
                 if (job.dtype != FIBERS_F32) { d_raw = base; base += (size_t)esz * job.nvol * cp; base = (char*)(((uintptr_t)base + 255) & ~(uintptr_t)255); }
                 std::vector<float*> d_out;
                 for (auto& o : job.out_f32) { d_out.push_back((float*)base); base += sizeof(float) * o.second * cp; }
+                std::vector<float*> d_out2;
+                for (auto& o : job.out2_f32) { d_out2.push_back((float*)base); base += sizeof(float) * o.second * cp; }
                 int16_t* d_idx = (int16_t*)base; base += 6 * cp;
                 uint8_t* d_mask = (uint8_t*)base; base += cp;
                 uint8_t* d_valid = (uint8_t*)base;
@@ -509,6 +527,13 @@ static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* r
                     code = plan->kernel == FIBERS_KERNEL_TC ? launch_recon_tc(plan, a, st[s]) : launch_recon_simt(plan, a, st[s]);
                 }
                 if (code) { err = g_err; goto done; }
+                if (fused) {                              // companion DTI fit on the slab that is already resident
+                    code = launch_dti(plan2, d_dwi, cp, d_mask, cn, cp, d_out2.data(), nullptr, st[s]);
+                    if (code) { err = g_err; goto done; }
+                    for (size_t i = 0; i < job.out2_f32.size(); ++i)
+                        W_CUDA(cudaMemcpy2DAsync((char*)job.out2_f32[i].first + g0 * 4, job.nvox * 4, d_out2[i], cp * 4, cn * 4,
+                                                 job.out2_f32[i].second, cudaMemcpyDeviceToHost, st[s]));
+                }
                 // D2H gathers into the caller's arrays at the slab offset
                 for (size_t i = 0; i < job.out_f32.size(); ++i)
                     W_CUDA(cudaMemcpy2DAsync((char*)job.out_f32[i].first + g0 * 4, job.nvox * 4, d_out[i], cp * 4, cn * 4,
@@ -552,6 +577,7 @@ done:
         if (d_qa_all) cudaFree(d_qa_all);
         if (d_stats) cudaFree(d_stats);
         if (plan) plan_free(plan);
+        if (plan2) plan_free(plan2);
     }
     *out_code = code; *out_err = err;
 }
@@ -587,13 +613,14 @@ void fibers_cuda_release_cache(void) {
         DeviceCache& c = g_cache[d];
         std::lock_guard<std::mutex> lk(c.mu);
         if (c.busy) continue;
-        bool any = c.plan || c.qa || c.stats || c.slab[0] || c.st[0];
+        bool any = c.plan || c.plan2 || c.qa || c.stats || c.slab[0] || c.st[0];
         if (!any) continue;
         int cur = 0; cudaGetDevice(&cur); cudaSetDevice(d);
         for (int s = 0; s < 3; ++s) { if (c.slab[s]) cudaFree(c.slab[s]); if (c.st[s]) cudaStreamDestroy(c.st[s]); c.slab[s] = nullptr; c.st[s] = nullptr; }
         if (c.qa) cudaFree(c.qa); if (c.stats) cudaFree(c.stats);
         if (c.plan) plan_free(c.plan);
-        c.qa = nullptr; c.stats = nullptr; c.plan = nullptr; c.slab_bytes = c.qa_bytes = 0; c.plan_key = 0;
+        if (c.plan2) plan_free(c.plan2);
+        c.qa = nullptr; c.stats = nullptr; c.plan = nullptr; c.plan2 = nullptr; c.slab_bytes = c.qa_bytes = 0; c.plan_key = c.plan2_key = 0;
         cudaSetDevice(cur);
     }
 }
@@ -678,7 +705,8 @@ int fibers_adc_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
 static int recon_host(int kind, const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,
                       const float* bval, const float* bvec, const float* vertices, int nvert2, const int32_t* faces,
                       int nface, float sigma, int hann_width, float* pdf, float* odf, float* peak1, float* peak2,
-                      float* peak3, float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu) {
+                      float* peak3, float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu,
+                      float* const* dti_out = nullptr) {
     if (!bval || nvol <= 0) return fail(FIBERS_ERR_TABLE, "Missing b-value table from input DWI structure");
     if (!bvec) return fail(FIBERS_ERR_TABLE, "Missing gradient table from input DWI structure");
     if (nx <= 0 || ny <= 0 || nz <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions must be positive");
@@ -706,6 +734,17 @@ static int recon_host(int kind, const void* dwi, int dwi_dtype, const uint8_t* m
         const int kc = kernel_choice(); h = fnv1a(h, &kc, sizeof(kc));
         job.plan_key = h;
     }
+    if (dti_out) {
+        const int nfr[10] = {1, 1, 1, 1, 3, 3, 3, 1, 1, 1};
+        for (int i = 0; i < 10; ++i) {
+            if (!dti_out[i]) return fail(FIBERS_ERR_ARG, "NULL output pointer");
+            job.out2_f32.push_back({dti_out[i], nfr[i]});
+        }
+        job.make_plan2 = [=](Plan** p, int dev) {
+            return fibers_dti_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval, bvec);
+        };
+        job.plan2_key = fnv1a(fnv1a(fnv1a(1469598103934665603ull, "dti", 3), bval, sizeof(float) * nvol), bvec, sizeof(float) * 3 * nvol);
+    }
     return run_host_job(job, ngpu);
 }
 
@@ -715,6 +754,16 @@ int fibers_gqi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, 
                    float* qa2, float* qa3, int16_t* peak_idx, int ngpu) {
     return recon_host(PLAN_GQI, dwi, dwi_dtype, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
                       sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, peak_idx, ngpu);
+}
+
+int fibers_dti_gqi_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol, const float* bval,
+                       const float* bvec, float* s0, float* eval1, float* eval2, float* eval3, float* evec1,
+                       float* evec2, float* evec3, float* rd, float* md, float* fa, const float* vertices,
+                       int nvert2, const int32_t* faces, int nface, float sigma, float* odf, float* peak1,
+                       float* peak2, float* peak3, float* qa1, float* qa2, float* qa3, int ngpu) {
+    float* const dti_out[10] = {s0, eval1, eval2, eval3, evec1, evec2, evec3, rd, md, fa};
+    return recon_host(PLAN_GQI, dwi, FIBERS_F32, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
+                      sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, nullptr, ngpu, dti_out);
 }
 
 int fibers_dsi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,

@@ -134,6 +134,31 @@ def gqi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25
     return _recon("gqi", dwi, mask, odf_dirs, sigma, ngpu)
 
 
+def dti_gqi_fit(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1):
+    """`dti_fit(dwi, mask)` and `gqi_rec(dwi, mask, odf_dirs, sigma)` in one pass over the DWI volume (each z-slab
+    chunk crosses PCIe once and feeds both kernels); returns `(DTI, GQI)`, bit-identical to the two separate calls
+    (src/dti.jl:221, src/gqi.jl:109)."""
+    _check_tables(dwi, True)
+    if dwi.vol.dtype != np.float32:
+        raise TypeError("dti_fit requires a Float32 DWI volume (reference method signature, src/dti.jl:286)")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwi.vol.shape
+    m = _mask_u8(mask, (nx, ny, nz))
+    vol = np.asfortranarray(dwi.vol)
+    bvec = np.asfortranarray(dwi.bvec, np.float32)
+    V = np.asfortranarray(odf_dirs.vertices, np.float32)
+    F = np.asfortranarray(odf_dirs.faces, np.int32)
+    douts = [MRI.like(mask, n) for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)]
+    odf = MRI.like(mask, odf_dirs.nvert)
+    peak = [MRI.like(mask, 3) for _ in range(3)]
+    qa = [MRI.like(mask, 1) for _ in range(3)]
+    _lib.check(L.fibers_dti_gqi_fit(_lib.ptr(vol), _lib.ptr(m), nx, ny, nz, nvol, _lib.ptr(dwi.bval), _lib.ptr(bvec),
+                                    *[_lib.ptr(o.vol) for o in douts], _lib.ptr(V), V.shape[0], _lib.ptr(F), F.shape[0],
+                                    float(np.float32(sigma)), _lib.ptr(odf.vol), *[_lib.ptr(p.vol) for p in peak],
+                                    *[_lib.ptr(q.vol) for q in qa], ngpu))
+    return DTI(*douts), GQI(odf, peak, qa, None)
+
+
 def dsi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, hann_width: int = 32, ngpu: int = 1) -> DSI:
     """Diffusion spectrum imaging reconstruction; returns a `DSI` structure."""
     return _recon("dsi", dwi, mask, odf_dirs, hann_width, ngpu)

@@ -106,6 +106,19 @@ int fibers_dsi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask,
                    float* pdf, float* odf, float* peak1, float* peak2, float* peak3,
                    float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu);
 
+/* dti_fit + gqi_rec on the SAME dwi volume in one pass: the result of
+ * calling fibers_dti_fit (src/dti.jl:221-316) and fibers_gqi_rec (src/gqi.jl:109-171) one after the other,
+ * bit for bit, but every z-slab chunk of the DWI crosses PCIe once and feeds both kernels while it is
+ * resident.  dwi must be Float32 (the reference's dti_fit accepts nothing else, src/dti.jl:286). */
+int fibers_dti_gqi_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol,
+                       const float* bval, const float* bvec,
+                       float* s0, float* eval1, float* eval2, float* eval3,
+                       float* evec1, float* evec2, float* evec3,
+                       float* rd, float* md, float* fa,
+                       const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma,
+                       float* odf, float* peak1, float* peak2, float* peak3,
+                       float* qa1, float* qa2, float* qa3, int ngpu);
+
 /* ---- device-resident entry points (kernel-only timing, slab pipelines, batch drivers) ---
  * A plan holds the per-protocol constants on ONE device (reconstruction matrix, neighbour
  * table, vertex table, pinv of the design matrix): the GPU analogue of GQIwork / DSIwork /

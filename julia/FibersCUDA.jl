@@ -19,7 +19,7 @@ module FibersCUDA
 
 using ..Fibers: MRI, ODF, DTI, GQI, DSI, sphere_642
 
-export adc_fit, dti_fit, gqi_rec, dsi_rec, device_count
+export adc_fit, dti_fit, gqi_rec, dsi_rec, dti_gqi_fit, device_count
 
 const libfibers = get(ENV, "FIBERS_CUDA_LIB", "libfibers_cuda.so")
 const NGPU = Ref{Cint}(parse(Cint, get(ENV, "FIBERS_CUDA_NGPU", "1")))
@@ -113,6 +113,41 @@ function gqi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Floa
               odf.vol, peak[1].vol, peak[2].vol, peak[3].vol, qa[1].vol, qa[2].vol, qa[3].vol,
               C_NULL, NGPU[]))
   return GQI(odf, peak, qa)
+end
+
+"""
+    dti_gqi_fit(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
+
+`dti_fit(dwi, mask)` and `gqi_rec(dwi, mask, odf_dirs, σ)` in ONE pass over `dwi.vol` (every z-slab chunk is
+copied to the GPU once and feeds both kernels); returns `(DTI, GQI)`, bit-identical to the two separate calls.
+"""
+function dti_gqi_fit(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
+  isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
+  isempty(dwi.bvec) && error("Missing gradient table from input DWI structure")
+  S0    = MRI(mask, 1, Float32); Eval1 = MRI(mask, 1, Float32)
+  Eval2 = MRI(mask, 1, Float32); Eval3 = MRI(mask, 1, Float32)
+  Evec1 = MRI(mask, 3, Float32); Evec2 = MRI(mask, 3, Float32); Evec3 = MRI(mask, 3, Float32)
+  RD    = MRI(mask, 1, Float32); MD    = MRI(mask, 1, Float32); FA    = MRI(mask, 1, Float32)
+  nvert = div(size(odf_dirs.vertices, 1), 2)
+  odf  = MRI(mask, nvert, Float32)
+  peak = [MRI(mask, 3, Float32) for _ in 1:3]
+  qa   = [MRI(mask, 1, Float32) for _ in 1:3]
+  vol = dwi.vol::Array{Float32,4}                      # dti_fit's method signature is Float32-only
+  nx, ny, nz, nvol = size(vol)
+  m = mask_u8(mask)
+  bvec  = Matrix{Float32}(dwi.bvec)
+  faces = Matrix{Int32}(odf_dirs.faces)
+  check(ccall((:fibers_dti_gqi_fit, libfibers), Cint,
+              (Ptr{Float32}, Ptr{UInt8}, Cint, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32},
+               Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+               Ptr{Float32}, Ptr{Float32}, Ptr{Float32},
+               Ptr{Float32}, Cint, Ptr{Int32}, Cint, Cfloat,
+               Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Cint),
+              vol, m, nx, ny, nz, nvol, dwi.bval, bvec,
+              S0.vol, Eval1.vol, Eval2.vol, Eval3.vol, Evec1.vol, Evec2.vol, Evec3.vol, RD.vol, MD.vol, FA.vol,
+              odf_dirs.vertices, size(odf_dirs.vertices, 1), faces, size(faces, 1), σ,
+              odf.vol, peak[1].vol, peak[2].vol, peak[3].vol, qa[1].vol, qa[2].vol, qa[3].vol, NGPU[]))
+  return DTI(S0, Eval1, Eval2, Eval3, Evec1, Evec2, Evec3, RD, MD, FA), GQI(odf, peak, qa)
 end
 
 """

@@ -302,3 +302,27 @@ def test_gqi_tc_candidate_list_overflow_falls_back(F, sphere642, monkeypatch):
     finally:
         F.device.set_kernel("auto")
     _check_recon(got, None, r64, v, f, 321, "gqi tc candidate-list overflow")
+
+
+def test_fused_dti_gqi_equals_the_two_calls(F, sphere642):
+    """fibers_dti_gqi_fit: one pass over the DWI volume, results bit-identical to dti_fit
+    followed by gqi_rec.  Several chunks (FIBERS_CUDA_CHUNK_VOXELS), ragged mask, non-positive samples."""
+    import os
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((26, 22, 14), seed=31, mask_fill=0.6)     # 8008 voxels, 288 volumes
+    os.environ["FIBERS_CUDA_CHUNK_VOXELS"] = "4096"
+    try:
+        F._lib.lib().fibers_cuda_release_cache()
+        d1 = F.dti_fit(*_mri(F, ph))
+        g1 = F.gqi_rec(*_mri(F, ph))
+        d2, g2 = F.dti_gqi_fit(*_mri(F, ph))
+    finally:
+        del os.environ["FIBERS_CUDA_CHUNK_VOXELS"]
+        F._lib.lib().fibers_cuda_release_cache()
+    for name in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "eigvec2", "eigvec3", "rd", "md", "fa"):
+        a, b = getattr(d1, name).vol, getattr(d2, name).vol
+        assert np.array_equal(a, b, equal_nan=True), name
+    assert np.array_equal(g1.odf.vol, g2.odf.vol)
+    for k in range(3):
+        assert np.array_equal(g1.peak[k].vol, g2.peak[k].vol) and np.array_equal(g1.qa[k].vol, g2.qa[k].vol)
+    assert np.count_nonzero(d2.fa.vol) > 1000 and np.count_nonzero(g2.qa[0].vol) > 1000
