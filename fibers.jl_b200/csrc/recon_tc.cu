@@ -612,7 +612,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             //      pair i+2 are in flight while pair i is tested.  (Prefetches past the warp's range touch rows
             //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
             {
-                const uint32_t kb = smem_u32(keys) + lane * 8;
+                uint32_t kb = smem_u32(keys) + lane * 8;
+                asm volatile("mov.u32 %0, %0;" : "+r"(kb));             // pin: keeps the compiler from re-deriving the base in every iteration
                 const uint32_t ncand32 = smem_u32(s_ncand);
                 auto ld = [&](uint32_t off) {
                     uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
