@@ -10,20 +10,23 @@
 //   kernel -- see launch_recon_tc.)
 //
 // One persistent CTA PAIR (cta_group::2, M = 256) per two SMs; every CTA owns 128 voxels of a tile:
-//   warp 0      TMA producer: streams K32 chunks of the split matrix (this CTA's half of the rows)
-//               from L2 into a 2-stage SWIZZLE_32B shared-memory ring (two K16 sub-tiles per stage)
+//   warp 0      TMA producer: the split matrix lives in HBM as a ready-made shared-memory image (K32 stage
+//               after K32 stage, SWIZZLE_32B pattern applied on the host), so a stage of this CTA's half of the
+//               rows is ONE bulk tensor copy into a 3-stage ring
 //   warp 1      MMA issuer (leader CTA): tcgen05.mma.cta_group::2, A operand from TENSOR MEMORY,
 //               B from shared memory; accumulators D[128 x Npad] fp32 in TMEM columns [0, Npad)
-//   warps 2-9   converters: coalesced fp32 loads of the DWI slab (voxel-contiguous), clamp, scale,
-//               hi/lo fp16 split, tcgen05.st into a 4-slot TMEM ring (columns 384..511)
-//   warps 10-17 epilogue: tcgen05.ld, un-scale, coalesced ODF store; every value is also quantised to a
-//               16-bit ORDER-PRESERVING key (fixed point relative to the voxel's mean ODF, which the MMA
-//               delivers as one extra matrix row) and staged as a 128 x M key tile in shared memory.
-//               The local-maximum scan of the folded mesh runs on the keys (4 voxels per thread, packed
-//               u16x2 max/min, neighbour offsets from constant memory) and only LISTS possible maxima;
-//               the few listed (voxel, vertex) pairs are then settled EXACTLY on the fp32 values just
-//               written (L2 hits), ranked by three rounds of 64-bit shared atomicMax on (value, ~index),
-//               QA, per-voxel mean -> atomicMax
+//   warps 2-5   converters (one per TMEM lane quarter): the raw DWI slab is staged through a 3-stage
+//               shared-memory ring with cp.async (16-byte copies when the rows are 16-byte aligned), two chunks
+//               ahead of the conversion; clamp, scale, hi/lo fp16 split, tcgen05.st into a 4-slot TMEM ring
+//               (columns 384..511)
+//   warps 6-17  epilogue (three groups of four): tcgen05.ld, un-scale, coalesced ODF store; every value is also
+//               quantised to a 15-bit ORDER-PRESERVING key (fixed point relative to the voxel's mean ODF, which
+//               the MMA delivers as one extra matrix row) and staged as a 128 x M key tile in shared memory.
+//               The local-maximum scan of the folded mesh runs on the keys (4 voxels per thread, packed u16x2
+//               max, one 32-bit subtraction tests two voxels, neighbour offsets from constant memory) and only
+//               LISTS possible maxima; the few listed (voxel, vertex) pairs are then settled EXACTLY on the
+//               fp32 values just written (L2 hits) and inserted into the voxel's sorted triple by chained
+//               64-bit shared atomicMax on (value, ~index); QA, per-voxel mean -> atomicMax
 // The full ODF never round-trips HBM: it is written once; the scan reads 2 bytes per value from shared memory.
 #include <cuda.h>
 #include <cuda_fp16.h>
