@@ -13,8 +13,8 @@ namespace fibers {
 
 namespace {
 
-constexpr int DTI_THREADS = 128;
-constexpr int UNROLL = 8;
+constexpr int DTI_THREADS = 256;
+constexpr int UNROLL = 16;
 
 struct Cross { float x, y, z; };
 __device__ __forceinline__ Cross cross3(float a0, float a1, float a2, float b0, float b1, float b2) {
@@ -199,14 +199,11 @@ __device__ __forceinline__ float fast_ln(float s) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2m) : "f"(m));
     return fmaf(ef, 0.693145752f, fmaf(ef, 1.42860677e-6f, l2m * 0.693147182f));
 }
-// (bits - min_normal) as unsigned is >= 0x7F000000 exactly for denormals, zero, negatives, inf and NaN
-__device__ __forceinline__ uint32_t fast_ln_range(float s) { return __float_as_uint(s) - 0x00800000u; }
-
 constexpr int RMAX = 6;
 constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] = pinv(A)' padded (2 x LDS.128 per sample)
 
 template <int NC>
-__global__ void __launch_bounds__(DTI_THREADS, 8)      // <= 64 registers: the rare float64 downdate may spill, the stream must not
+__global__ void __launch_bounds__(DTI_THREADS, 3)      // <= 80 registers: the rare float64 downdate may spill, the stream must not
 fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __restrict__ mask, int64_t nvox,
                 int nvol, const float* __restrict__ pinv, const float* __restrict__ design, const uint8_t* __restrict__ ib0,
                 DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
@@ -224,100 +221,106 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
     float d[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) d[k] = 0.f;
-    int npos = 0, nrem = 0;
+    float nposf = 0.f;                                  // number of positive samples (<= 2^24: exact in fp32, one FADD per sample)
+    int nrem = 0;
     int rem[RMAX];
     float b0acc = 0.f;                                  // > 0 iff some minimum-b volume is positive (flag rides in the padded coefficient row)
-    uint32_t odd = 0u;                                  // max over POSITIVE samples of fast_ln_range: flags denormal / inf input
     auto sample = [&](float s, int j) {
         const bool pos = s > 0.f;
-        npos += pos;
-        odd = max(odd, pos ? fast_ln_range(s) : 0u);
-        const float lg = pos ? fast_ln(s) : 0.f;        // select, not a branch: garbage for s <= 0 is discarded
+        const float posf = pos ? 1.f : 0.f;
+        nposf += posf;
+        // MUFU.LG2 (<= 2 ulp of log2 outside [0.5, 2], 2^-22 absolute inside) times ln 2.  A denormal sample is
+        // flushed to zero (-inf) and an infinite one gives +inf: both leave a non-finite fit, which is detected
+        // after the loop and sent to the exact-log path -- no per-sample range test.
+        float l2;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s));
+        const float lg = pos ? l2 * 0.693147182f : 0.f;  // select, not a branch: garbage for s <= 0 is discarded
         const float4 c0 = *reinterpret_cast<const float4*>(spa + j * CW);
         d[0] = fmaf(c0.x, lg, d[0]); d[1] = fmaf(c0.y, lg, d[1]);
         if (NC > 2) {
             const float4 c1 = *reinterpret_cast<const float4*>(spa + j * CW + 4);
             d[2 % NC] = fmaf(c0.z, lg, d[2 % NC]); d[3 % NC] = fmaf(c0.w, lg, d[3 % NC]);
             d[4 % NC] = fmaf(c1.x, lg, d[4 % NC]); d[5 % NC] = fmaf(c1.y, lg, d[5 % NC]); d[6 % NC] = fmaf(c1.z, lg, d[6 % NC]);
-            b0acc = fmaf(c1.w, pos ? 1.f : 0.f, b0acc);
+            b0acc = fmaf(c1.w, posf, b0acc);
         } else {
-            b0acc = fmaf(c0.z, pos ? 1.f : 0.f, b0acc);
+            b0acc = fmaf(c0.z, posf, b0acc);
         }
     };
     if (inside) {
-        // UNROLL running pointers, one per sample of the group (64-bit add per load instead of a 64-bit multiply-add)
-        const float* ptr[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) ptr[u] = dwi + vox + (int64_t)u * pitch;
-        const int64_t step = (int64_t)UNROLL * pitch;
+        // the row base (volume j) is warp-uniform and the voxel offset fits 32 bits: the address is formed as
+        // uniform base + 32-bit thread offset, without per-thread 64-bit arithmetic
+        const uint32_t vox32 = (uint32_t)vox;
+        const float* rb = dwi;
         int j = 0;
         for (; j + UNROLL <= nvol; j += UNROLL) {
             float s[UNROLL];
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) { s[u] = __ldg(ptr[u]); ptr[u] += step; }
-            const int before = npos;
+            for (int u = 0; u < UNROLL; ++u) s[u] = __ldg(rb + (int64_t)u * pitch + vox32);
+            rb += (int64_t)UNROLL * pitch;
+            const float before = nposf;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) sample(s[u], j + u);
-            if (npos - before != UNROLL) {                          // rare: remember which samples were dropped
+            if (nposf - before != (float)UNROLL) {                          // rare: remember which samples were dropped
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) { if (nrem < RMAX) rem[nrem] = j + u; ++nrem; }
             }
         }
         for (int u = 0; j < nvol; ++j, ++u) {
-            const float sv = __ldg(ptr[0] + (int64_t)u * pitch);
+            const float sv = __ldg(rb + (int64_t)u * pitch + vox32);
             sample(sv, j);
             if (!(sv > 0.f)) { if (nrem < RMAX) rem[nrem] = j; ++nrem; }
         }
     }
     const bool b0pos = b0acc > 0.f;
+    const int npos = (int)nposf;
     const bool full = inside && npos == nvol;                       // src/dti.jl:294
     bool part = inside && !full && npos > 6 && b0pos;               // :297 (ADC keeps the same rule, :206)
     bool solved = full;
-    if (odd >= 0x7F000000u && (full || part)) { solved = false; part = true; nrem = RMAX + 1; }   // denormal / inf sample: exact-log path
+    {
+        bool finite = true;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) finite = finite && (fabsf(d[k]) < CUDART_INF_F);
+        if (!finite && (full || part)) { solved = false; part = true; nrem = RMAX + 1; }   // denormal / inf sample: exact-log path
+    }
     if (part && nrem <= RMAX) {
-        // rank-nrem downdate in float64
-        double S[RMAX][RMAX], z[RMAX];
+        // rank-nrem downdate (fp32: the correction is a small, well-conditioned update; fp64 runs at 1/64 rate here)
+        float S[RMAX][RMAX], z[RMAX];
         for (int i = 0; i < nrem; ++i) {
             const float* ai = design + (size_t)rem[i] * NC;
-            double r = 0;
-            for (int k = 0; k < NC; ++k) r += (double)ai[k] * (double)d[k];
+            float r = 0.f;
+            for (int k = 0; k < NC; ++k) r = fmaf(ai[k], d[k], r);
             z[i] = r;                                                // U' x0
             for (int jj = 0; jj < nrem; ++jj) {
                 const float* pj = spa + rem[jj] * CW;
-                double t = 0;
-                for (int k = 0; k < NC; ++k) t += (double)ai[k] * (double)pj[k];
-                S[i][jj] = (i == jj ? 1.0 : 0.0) - t;                // I - U' P_r
+                float t = 0.f;
+                for (int k = 0; k < NC; ++k) t = fmaf(ai[k], pj[k], t);
+                S[i][jj] = (i == jj ? 1.f : 0.f) - t;                // I - U' P_r
             }
         }
         bool ok = true;
         for (int c = 0; c < nrem && ok; ++c) {                       // Gaussian elimination, partial pivoting
-            int piv = c; double best = fabs(S[c][c]);
-            for (int i = c + 1; i < nrem; ++i) if (fabs(S[i][c]) > best) { best = fabs(S[i][c]); piv = i; }
-            if (!(best > 1e-9)) { ok = false; break; }               // (near-)singular downdate: general path decides
-            if (piv != c) { for (int k = 0; k < nrem; ++k) { double t = S[c][k]; S[c][k] = S[piv][k]; S[piv][k] = t; } double t = z[c]; z[c] = z[piv]; z[piv] = t; }
-            const double inv = 1.0 / S[c][c];
+            int piv = c; float best = fabsf(S[c][c]);
+            for (int i = c + 1; i < nrem; ++i) if (fabsf(S[i][c]) > best) { best = fabsf(S[i][c]); piv = i; }
+            if (!(best > 1e-5f)) { ok = false; break; }               // (near-)singular downdate: general path decides
+            if (piv != c) { for (int k = 0; k < nrem; ++k) { float t = S[c][k]; S[c][k] = S[piv][k]; S[piv][k] = t; } float t = z[c]; z[c] = z[piv]; z[piv] = t; }
+            const float inv = 1.f / S[c][c];
             for (int i = c + 1; i < nrem; ++i) {
-                const double f = S[i][c] * inv;
+                const float f = S[i][c] * inv;
                 for (int k = c; k < nrem; ++k) S[i][k] -= f * S[c][k];
                 z[i] -= f * z[c];
             }
         }
         if (ok) {
             for (int c = nrem - 1; c >= 0; --c) {
-                double t = z[c];
+                float t = z[c];
                 for (int k = c + 1; k < nrem; ++k) t -= S[c][k] * z[k];
                 z[c] = t / S[c][c];
             }
-            double acc[NC];
-#pragma unroll
-            for (int k = 0; k < NC; ++k) acc[k] = (double)d[k];
             for (int i = 0; i < nrem; ++i) {
                 const float* pj = spa + rem[i] * CW;
 #pragma unroll
-                for (int k = 0; k < NC; ++k) acc[k] += (double)pj[k] * z[i];
+                for (int k = 0; k < NC; ++k) d[k] = fmaf(pj[k], z[i], d[k]);
             }
-#pragma unroll
-            for (int k = 0; k < NC; ++k) d[k] = (float)acc[k];
             solved = true; part = false;
         }
     }
