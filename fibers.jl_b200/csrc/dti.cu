@@ -184,21 +184,8 @@ __device__ void dti_zero(int64_t vox, const DtiOut& o) {
 // rows U = A[removed,:]' the normal matrix is a rank-r downdate, G_pos = G - U U', so by Woodbury
 //     d = x0 + P_r (I - U' P_r)^-1 U' x0,   x0 = pinv(A) * (ln s with zeros at removed rows),
 // where P_r = pinv(A)[:, removed] (= G^-1 U for a full-column-rank design).  x0 falls out of the main
-// loop for free; the r x r system (r <= RMAX) is solved per thread in float64.  Voxels with more
+// loop for free; the r x r system (r <= RMAX) is solved per thread in fp32.  Voxels with more
 // removed samples, or a singular downdate, go to the general per-voxel pinv kernel via a device list.
-// ln(s) for normal positive s in ~8 branch-free instructions: s = m * 2^e with m in [0.75, 1.5); MUFU.LG2
-// on the mantissa only (absolute error ~1e-7 because |log2 m| <= 0.585), exponent added with a two-term
-// ln 2.  About 0.5 ulp at typical DWI magnitudes, i.e. as accurate as logf at a third of the instructions.
-// Denormal / inf inputs are detected by the caller (fast_ln_range) and sent to the library-logf path.
-__device__ __forceinline__ float fast_ln(float s) {
-    const uint32_t b = __float_as_uint(s);
-    const uint32_t eb = (b - 0x3F400000u) & 0xFF800000u;              // exponent part to strip: floor(log2(s / 0.75)) << 23
-    const float m = __uint_as_float(b - eb);                          // in [0.75, 1.5)
-    const float ef = (float)((int)eb >> 23);
-    float l2m;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2m) : "f"(m));
-    return fmaf(ef, 0.693145752f, fmaf(ef, 1.42860677e-6f, l2m * 0.693147182f));
-}
 constexpr int RMAX = 6;
 constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] = pinv(A)' padded (2 x LDS.128 per sample)
 
