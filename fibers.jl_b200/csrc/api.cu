@@ -83,6 +83,7 @@ static void plan_free(Plan* p) {
     tc_plan_free(p);
     cudaFree(p->d_mt); cudaFree(p->d_pinv); cudaFree(p->d_design); cudaFree(p->d_ib0);
     cudaFree(p->d_nbr); cudaFree(p->d_vert); cudaFree(p->d_list); cudaFree(p->d_count);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
     cudaSetDevice(cur);
     delete p;
 }

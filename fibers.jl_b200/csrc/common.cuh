@@ -57,7 +57,20 @@ struct Plan {
     int64_t   list_cap = 0;
     int*      d_count = nullptr;   // DTI partial-path counter
     void*     tc = nullptr;        // tensor-core path state (recon_tc.cu), or null
+    cudaEvent_t ev_done = nullptr; // end of the plan's most recent launch (see plan_enter / plan_leave)
 };
+
+// Launches of ONE plan share its device scratch (work lists, counters, scale): their kernel sections are
+// serialised across streams with an event chain, while the copies queued on those streams still overlap.
+inline int plan_enter(Plan* p, cudaStream_t st) {
+    if (p->ev_done) FB_CUDA(cudaStreamWaitEvent(st, p->ev_done, 0));
+    return 0;
+}
+inline int plan_leave(Plan* p, cudaStream_t st) {
+    if (!p->ev_done) FB_CUDA(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    FB_CUDA(cudaEventRecord(p->ev_done, st));
+    return 0;
+}
 
 // ---- host-side set-up (setup.cpp) -------------------------------------------------------
 // All return "" on success or an error message.

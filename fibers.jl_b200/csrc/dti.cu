@@ -413,6 +413,7 @@ int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_
     if (nvox > 0x7FFFFFFFLL) return fail(FIBERS_ERR_ARG, "slab too large (nvox must fit in int32)");
     int rc = ensure_list(p, nvox);
     if (rc) return rc;
+    if (int rc2 = plan_enter(p, st)) return rc2;                    // the partial-path list / counter belong to the plan
     FB_CUDA(cudaMemsetAsync(p->d_count, 0, sizeof(int), st));
     size_t smem = sizeof(float) * CW * p->nvol + p->nvol + 16;
     if (smem > 48 * 1024)
@@ -427,7 +428,7 @@ int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_
                                                    p->d_list, p->d_count);
     count_launch(2);
     FB_CUDA(cudaGetLastError());
-    return 0;
+    return plan_leave(p, st);
 }
 
 }  // namespace

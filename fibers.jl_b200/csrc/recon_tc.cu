@@ -926,6 +926,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         FB_CUDA(cudaMalloc(&st->d_scratch, sizeof(int) * (size_t)need));
         st->scratch_cap = need;
     }
+    if (int rc = plan_enter(p, stream)) return rc;                  // the scratch below belongs to the plan
     FB_CUDA(cudaMemsetAsync(st->d_scratch, 0, 4 * sizeof(int), stream));
     int* d_fix_list = st->d_scratch + 4; int* d_tile_list = st->d_scratch + 4 + 2 * ntile64;
     {   // neighbour offsets -> constant memory of this device (skipped when this plan's table is already resident;
@@ -992,7 +993,8 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         }
     }
     // voxels whose scaled signal overflowed fp16 (rare): recompute their 64-voxel tiles in fp32
-    return launch_recon_simt_list(p, a, d_fix_list, st->d_scratch + 1, stream);
+    if (int rc = launch_recon_simt_list(p, a, d_fix_list, st->d_scratch + 1, stream)) return rc;
+    return plan_leave(p, stream);
 }
 
 }  // namespace fibers
