@@ -51,7 +51,7 @@ constexpr int N_CONV = 4;            // converter warps (multiple of 4)
 constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = W_CONV0 + N_CONV;
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
 constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
-constexpr int NSTAGE = 3;            // B ring: K32 chunks (two K16 sub-tiles each)
+constexpr int NSTAGE = 3;            // B ring: K32 chunks (two K16 sub-tiles each); 2 when shared memory is short (M > 335)
 constexpr int DSTAGE = 3;            // raw DWI ring of the converters: K32 chunks of 128 voxels (16 KB each)
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
@@ -67,7 +67,7 @@ constexpr float KEY_WINDOW = 8.f;       // keys cover [0, 8 x mean(ODF of the vo
 // Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * KEY_ROW) into the key tile,
 // 8 per vertex (missing neighbours -> the all-zero sentinel row M).  The vertex index is warp-uniform,
 // so the offsets arrive through the uniform datapath and each neighbour costs one LDS.64.
-constexpr int TC_MAX_VERT = 344;        // rows of the offset table: M + 1 sentinel rows up to M + 8 (prefetch overrun)
+constexpr int TC_MAX_VERT = 392;        // rows of the offset table: M + 1 sentinel rows up to M + 8 (prefetch overrun)
 __constant__ uint32_t c_nbr_off[TC_MAX_VERT * NBR_W];
 
 struct TcParams {
@@ -81,6 +81,7 @@ struct TcParams {
     int ntiles;                  // 256-voxel tiles of the slab
     const int* tile_list; const int* tile_count;   // tiles that contain at least one mask voxel (built by tile_scan_kernel)
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
+    int nstage;                  // depth of the B ring (<= NSTAGE)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
@@ -88,7 +89,7 @@ struct TcParams {
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
 };
 
-// One launch of the kernel covers at most 336 matrix rows (TMEM columns).  GQI: a single pass (the ODF
+// One launch of the kernel covers at most 384 matrix rows (TMEM columns 0..383; the A ring sits above).  GQI: a single pass (the ODF
 // rows).  DSI: the ODF rows, then the pdf rows in passes of <= 336 (plain mode).
 struct TcPass {
     __half* d_split = nullptr;   // [2 ranks][K32 chunks][shared-memory image of one stage]
@@ -96,6 +97,7 @@ struct TcPass {
     int rows = 0, row0 = 0;      // matrix rows [row0, row0 + rows) of the plan's matrix
     int Npad = 0, N1 = 0, N2 = 0;
     int plain = 0;               // 1: pdf rows
+    int nstage = NSTAGE;         // B ring depth that fits in shared memory for this pass
 };
 
 struct TcState {
@@ -295,7 +297,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     uint8_t* base = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
     uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
-    uint16_t* keys = (uint16_t*)(sB + NSTAGE * stage_bytes);              // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
+    uint16_t* keys = (uint16_t*)(sB + p.nstage * stage_bytes);              // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
     const int Mk = p.plain ? 0 : p.M;                                     // plain passes stage no keys
     unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [3][128] best (value, ~index) per voxel
     uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
@@ -347,7 +349,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             TRACE(13);
             for (int c = 0; c < nk32; ++c, ++g) {
-                const int s = g % NSTAGE; const uint32_t use = g / NSTAGE;
+                const int s = g % p.nstage; const uint32_t use = g / p.nstage;
                 mbar_wait<200>(&b_empty[s], (use & 1) ^ 1);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * stage_bytes);       // both CTAs' bytes land on the leader's barrier
@@ -371,10 +373,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 tc_fence_after();
                 TRACE(0);
                 for (int c = 0; c < nk32; ++c, ++g32) {
-                    const int s = g32 % NSTAGE;
+                    const int s = g32 % p.nstage;
                     const int slot = g32 % ASLOT;
                     long long t0 = p.trace ? clock64() : 0;
-                    mbar_wait(&b_full[s], (g32 / NSTAGE) & 1);
+                    mbar_wait(&b_full[s], (g32 / p.nstage) & 1);
                     long long t1 = p.trace ? clock64() : 0;
                     mbar_wait(&a_full[slot], (g32 / ASLOT) & 1);
                     if (p.trace) { long long t2 = clock64(); TRACE_ADD(15, t1 - t0); TRACE_ADD(16, t2 - t1); }
@@ -785,8 +787,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-size_t tc_smem_bytes(int M, int Nh) {
-    size_t b = (size_t)NSTAGE * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + 3 * VOX_CTA * 8 +
+size_t tc_smem_bytes(int M, int Nh, int nstage) {
+    size_t b = (size_t)nstage * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + 3 * VOX_CTA * 8 +
                (N_CPART + 1) * VOX_CTA * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
@@ -819,7 +821,7 @@ static void tc_state_free(TcState* st) {
 int tc_plan_init(Plan* p) {
     if (p->kind != PLAN_GQI && p->kind != PLAN_DSI) { set_error("tensor-core path: GQI / DSI plans only"); return 1; }
     const int M = p->nvert, K = p->nvol;
-    if ((M + 1 + 15) / 16 * 16 > 336 || M + 8 > TC_MAX_VERT) { set_error("tensor-core path: more than 335 half-sphere vertices"); return 1; }
+    if ((M + 1 + 15) / 16 * 16 > 384 || M + 8 > TC_MAX_VERT) { set_error("tensor-core path: more than 383 half-sphere vertices"); return 1; }
     if (p->kind == PLAN_DSI && p->cvol < 0) { set_error("tensor-core path: DSI without a q-space origin sample"); return 1; }
     int cc_major = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device);
@@ -842,13 +844,17 @@ int tc_plan_init(Plan* p) {
     std::vector<std::pair<int, int>> ranges = {{0, M}};
     if (p->kind == PLAN_DSI) for (int r0 = 0; r0 < K; r0 += 336) ranges.push_back({M + r0, std::min(336, K - r0)});
     size_t smem = 0;
+    int dev_smem = 0;
+    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess) dev_smem = 0;
     for (size_t i = 0; i < ranges.size(); ++i) {
         TcPass ps;
         ps.row0 = ranges[i].first; ps.rows = ranges[i].second; ps.plain = i > 0;
         const int img_rows_n = ps.rows + (ps.plain ? 0 : 1);          // ODF pass: one extra row = mean of the ODF rows
         split_dims(img_rows_n, ps.Npad, ps.N1, ps.N2);
         const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
-        smem = std::max(smem, tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh));
+        ps.nstage = NSTAGE;                                            // the deepest B ring that fits beside the key tile
+        while (ps.nstage > 2 && tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh, ps.nstage) > (size_t)dev_smem) --ps.nstage;
+        smem = std::max(smem, tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh, ps.nstage));
         // Split operand as a ready-made shared-memory image: [rank][K32 chunk][K16 sub-tile][hi | lo][row][16 halves],
         // rows in the order (blk1 rows 0..N1h, blk2 rows 0..N2h) of that rank, with the SWIZZLE_32B pattern the
         // tcgen05 descriptors expect already applied (16-byte chunk ^= bit 2 of the row).  A stage is then ONE
@@ -897,9 +903,7 @@ int tc_plan_init(Plan* p) {
             set_error("tensor-core path: cuTensorMapEncodeTiled failed"); tc_state_free(st); return 1;
         }
     }
-    int dev_smem = 0;
-    if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess ||
-        smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
+    if (smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
     st->smem = smem;
     if (cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); tc_state_free(st); return 1;
@@ -972,6 +976,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.fix_cap = (int)(2 * ntile64);
         tp.ntiles = (int)((a.nvox + 255) / 256);
         tp.nbw = st->nbw;
+        tp.nstage = ps.nstage;
         tp.plain = ps.plain;
         tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));

@@ -126,7 +126,7 @@ def test_auto_selects_tensor_core_kernel(F):
     F.device.set_kernel("auto")
     assert F.device.Plan("gqi", 0, bval, bvec).kernel == "tc"
     assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_362).kernel == "tc"
-    assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_724).kernel == "simt"     # 362 half-sphere vertices: tile too big
+    assert F.device.Plan("gqi", 0, bval, bvec, F.sphere_724).kernel == "tc"       # 362 half-sphere vertices: 2-stage B ring
     bq, gq = phantom.dsi_grid_table()
     assert F.device.Plan("dsi", 0, bq, gq).kernel == "tc"
 
@@ -134,8 +134,6 @@ def test_auto_selects_tensor_core_kernel(F):
 @pytest.mark.parametrize("nsphere", [642, 362, 724])
 def test_gqi_parity(F, nsphere, kernel):
     from fibers_jl_b200 import phantom
-    if kernel == "tc" and nsphere == 724:
-        pytest.skip("sphere_724 (M = 362) is served by the SIMT kernel")
     v, f = O.load_sphere(nsphere)
     odf_dirs = F.ODF(v, f)
     ph = phantom.gqi_phantom((24, 20, 12) if nsphere == 642 else (12, 10, 6), seed=2, mask_fill=0.6)

@@ -89,6 +89,7 @@ run_recon("gqi", (145, 174, 145), b2, g2, "simt", "cfg2 145x174x145x288")
 b5, g5 = phantom.shells_table(8, [(4000.0, 120)])
 run_recon("gqi", (400, 400, 38), b5, g5, "tc", "cfg5 slab 400x400x38x128 (1/8 of 400x400x300)")
 run_recon("gqi", (145, 174, 73), b2, g2, "tc", "cfg2 half volume, sphere_362", F.sphere_362)
+run_recon("gqi", (145, 174, 73), b2, g2, "tc", "cfg2 half volume, sphere_724", F.sphere_724)
 b3, g3 = phantom.dsi_grid_table()
 run_recon("dsi", (96, 96, 60), b3, g3, "tc", "cfg3 96x96x60x515")
 run_recon("dsi", (96, 96, 60), b3, g3, "simt", "cfg3 96x96x60x515")
