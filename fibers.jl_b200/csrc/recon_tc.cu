@@ -642,6 +642,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                 op = c_nbr_off + vn * NBR_W;
                 oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
                 oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                uint32_t fw0 = 0u, fw1 = 0u, fw2 = 0u, fw3 = 0u;       // result bits: one byte per iteration (<= 16 iterations: M <= 383)
+                int iter = 0;
                 for (; pi < npair; pi += N_EPI) {
                     // reduce pair i
                     uint32_t mAx = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x), mAy = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
@@ -654,7 +656,6 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     }
                     const uint2 kA = cA, kB = cB;
                     // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
-                    const int vcur = v;
                     v = vn; vn = pair_vertex(pi + 2 * N_EPI);
                     cA = ld(v * KEY_ROW); cB = ld((v + 1) * KEY_ROW);
                     a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z); a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y);
@@ -667,22 +668,36 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     // threshold t = max(neighbour keys, 1)
                     const uint32_t hAx = kA.x - umax2(mAx, 0x80018001u) + 0x80008000u, hAy = kA.y - umax2(mAy, 0x80018001u) + 0x80008000u;
                     const uint32_t hBx = kB.x - umax2(mBx, 0x80018001u) + 0x80008000u, hBy = kB.y - umax2(mBy, 0x80018001u) + 0x80008000u;
-                    const uint32_t hit = (hAx | hAy | hBx | hBy) & 0x80008000u;
-                    if (__any_sync(0xffffffffu, hit != 0u)) {           // local maxima are rare
-                        if (hit != 0u) {
-                            // flag bits: 0-3 = vertex v, voxels 4*lane + 0..3; 4-7 = vertex v + 1
-                            const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
-                                               ((hBx >> 11) & 0x00100010u) | ((hBy >> 9) & 0x00400040u);
-                            uint32_t fl = (w & 0x55u) | ((w >> 15) & 0xAAu);
-                            uint32_t slot;                              // (inline PTX: one ATOMS per warp instead of the compiler's
-                            //  vote + prefix-scan aggregation -- only one to three lanes get here)
-                            asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(ncand32), "r"((uint32_t)__popc(fl)) : "memory");
-                            while (fl) {
-                                const int h = __ffs(fl) - 1;
-                                fl &= fl - 1;
-                                if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)(vcur + (h >> 2)) << 8) | (uint32_t)(4 * lane + (h & 3));
-                                ++slot;
-                            }
+                    // No branch in the loop: the 8 result bits of the pair (0-3 = vertex v, voxels 4*lane + 0..3; 4-7 =
+                    // vertex v + 1) go into a per-lane bit field, one byte per iteration, and are listed after the loop.
+                    const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
+                                       ((hBx >> 11) & 0x00100010u) | ((hBy >> 9) & 0x00400040u);
+                    const uint32_t fl = (w & 0x55u) | ((w >> 15) & 0xAAu);
+                    const uint32_t sh = (uint32_t)(iter & 3) * 8u;
+                    switch (iter >> 2) {                                // (warp-uniform)
+                        case 0: fw0 |= fl << sh; break;
+                        case 1: fw1 |= fl << sh; break;
+                        case 2: fw2 |= fl << sh; break;
+                        default: fw3 |= fl << sh; break;
+                    }
+                    ++iter;
+                }
+                // list the hits: one shared-memory atomic per lane that has any (typically a dozen lanes per warp and tile)
+                const uint32_t nhit = __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);
+                if (nhit) {
+                    uint32_t slot;
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(ncand32), "r"(nhit) : "memory");
+                    const uint32_t fws[4] = {fw0, fw1, fw2, fw3};
+#pragma unroll
+                    for (int wi = 0; wi < 4; ++wi) {
+                        uint32_t bits = fws[wi];
+                        while (bits) {
+                            const int h = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int it_ = wi * 4 + (h >> 3), bit = h & 7;
+                            const int vv = pair_vertex(ew + it_ * N_EPI) + (bit >> 2);
+                            if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)vv << 8) | (uint32_t)(4 * lane + (bit & 3));
+                            ++slot;
                         }
                     }
                 }

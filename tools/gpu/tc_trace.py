@@ -13,6 +13,9 @@ from fibers_jl_b200 import device as D
 shape = tuple(int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "145,174,145").split(","))
 nvox = int(np.prod(shape))
 bval, bvec = bench.make_tables()
+if os.environ.get("TC_TRACE_CFG5"):                      # 8 b0 + 120 directions at b = 4000 (128 volumes)
+    from fibers_jl_b200 import phantom
+    bval, bvec = phantom.shells_table(8, [(4000.0, 120)])
 dev = torch.device("cuda", 0)
 mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
 pitch = (nvox + 63) // 64 * 64
