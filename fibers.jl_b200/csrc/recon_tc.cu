@@ -305,7 +305,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     float* s_mean = s_min + N_CPART * VOX_CTA;                            // [128] mean ODF per voxel (from the extra matrix row)
     float* s_dwi = s_mean + VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
     uint4* s_nbr = (uint4*)(s_dwi + DSTAGE * 32 * VOX_CTA);               // [M] 8 x uint16 neighbour ids per vertex
-    uint64_t* bars = (uint64_t*)(s_nbr + Mk);
+    float* s_vert = (float*)(s_nbr + Mk);                                 // [M][3] first-half vertices (peak vectors); padded to 4 floats
+    uint64_t* bars = (uint64_t*)(s_vert + ((3 * Mk + 3) & ~3));
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
     uint32_t* s_ncand = (uint32_t*)(d_empty + 1);
@@ -324,6 +325,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     for (int i = threadIdx.x; i < 8 * VOX_CTA; i += TC_THREADS) keys[(size_t)Mk * VOX_CTA + i] = 0x8000;   // key 0
     if (threadIdx.x == 0) *s_ncand = 0u;
     for (int i = threadIdx.x; i < Mk; i += TC_THREADS) s_nbr[i] = __ldg(reinterpret_cast<const uint4*>(p.nbr) + i);
+    for (int i = threadIdx.x; i < 3 * Mk; i += TC_THREADS) s_vert[i] = __ldg(p.vert + i);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -762,9 +764,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     const bool ok = key != 0ull;
                     const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
                     const float val = __uint_as_float((uint32_t)(key >> 32));
-                    p.peak[k][ovox]                   = ok ? __ldg(p.vert + id * 3 + 0) : 0.f;
-                    p.peak[k][ovox + p.out_pitch]     = ok ? __ldg(p.vert + id * 3 + 1) : 0.f;
-                    p.peak[k][ovox + 2 * p.out_pitch] = ok ? __ldg(p.vert + id * 3 + 2) : 0.f;
+                    p.peak[k][ovox]                   = ok ? s_vert[id * 3 + 0] : 0.f;
+                    p.peak[k][ovox + p.out_pitch]     = ok ? s_vert[id * 3 + 1] : 0.f;
+                    p.peak[k][ovox + 2 * p.out_pitch] = ok ? s_vert[id * 3 + 2] : 0.f;
                     p.qa[k][ovox] = ok ? val - omin : 0.f;
                     if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
                 }
@@ -803,7 +805,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
 }
 
 size_t tc_smem_bytes(int M, int Nh, int nstage) {
-    size_t b = (size_t)nstage * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + 3 * VOX_CTA * 8 +
+    size_t b = (size_t)nstage * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + (size_t)M * 12 + 16 + 3 * VOX_CTA * 8 +
                (N_CPART + 1) * VOX_CTA * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
     return b + 1024 + 64;
 }
