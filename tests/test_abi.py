@@ -41,6 +41,9 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == 3 and "no CPU fallback" in str(e.value)
     with pytest.raises(F.FibersCudaError):
         F.gqi_rec(F.MRI(ph["dwi"], ph["bval"], ph["bvec"]), F.MRI(ph["mask"]))
+    with pytest.raises(F.FibersCudaError) as e2:                     # the fused DTI + GQI entry point refuses as well
+        F.dti_gqi_fit(F.MRI(ph["dwi"], ph["bval"], ph["bvec"]), F.MRI(ph["mask"]))
+    assert e2.value.code == 3
     # plan creation (device API) also refuses
     from fibers_jl_b200 import _lib
     plan = C.c_void_p()
@@ -57,6 +60,10 @@ def test_reference_error_behaviour():
         F.dsi_rec(F.MRI(np.zeros((2, 2, 2, 4), np.float32), bval=np.ones(4, np.float32)), m)
     with pytest.raises(TypeError):      # reference: MethodError for non-Float32 DWI in dti_fit
         F.dti_fit(F.MRI(np.zeros((2, 2, 2, 4), np.int16), np.ones(4, np.float32), np.ones((4, 3), np.float32)), m)
+    with pytest.raises(TypeError):      # ... which the fused call inherits
+        F.dti_gqi_fit(F.MRI(np.zeros((2, 2, 2, 4), np.int16), np.ones(4, np.float32), np.ones((4, 3), np.float32)), m)
+    with pytest.raises(RuntimeError, match="Missing b-value table from input DWI structure"):
+        F.dti_gqi_fit(F.MRI(np.zeros((2, 2, 2, 4), np.float32)), m)
 
 
 def test_mri_container_layout():
