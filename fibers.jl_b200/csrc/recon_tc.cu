@@ -87,6 +87,7 @@ struct TcParams {
     int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
     int cand_cap;                // capacity of the candidate list (<= CAND_CAP; tests shrink it to force the fall-back)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
+    uint32_t trace_skip;         // first traced tile iteration
 };
 
 // One launch of the kernel covers at most 384 matrix rows (TMEM columns 0..383; the A ring sits above).  GQI: a single pass (the ODF
@@ -184,8 +185,9 @@ __device__ __forceinline__ uint64_t make_sdesc_sw32(uint32_t saddr) {          /
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
 }
 
-#define TRACE(slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] = clock64(); } while (0)
-#define TRACE_ADD(slot, dt) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it < 16) p.trace[it * 32 + (slot)] += (dt); } while (0)
+// (16 consecutive tiles of CTA 0, starting at tile iteration p.trace_skip: FIBERS_TC_TRACE_SKIP, default 0)
+#define TRACE(slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] = clock64(); } while (0)
+#define TRACE_ADD(slot, dt) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] += (dt); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // strided sample of the slab: max over 32-voxel runs every 2048 voxels of every volume
@@ -331,6 +333,11 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
+    if (p.trace && threadIdx.x == 0 && rank == 0) {           // per-cluster wall-clock span (debug trace only)
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[16 * 32 + 2 * cluster_id] = (long long)t;
+        if (cluster_id == 0) p.trace[16 * 32 + 2 * 127] = clock64();            // SM cycles over the same span -> effective clock
+    }
 
     float scale = 1.f, inv_scale = 1.f;
     {
@@ -796,6 +803,11 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
     }
 
     // ---- teardown --------------------------------------------------------------------------
+    if (p.trace && warp == W_EPI0 && lane == 0 && rank == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[16 * 32 + 2 * cluster_id + 1] = (long long)t;
+        if (cluster_id == 0) p.trace[16 * 32 + 2 * 127 + 1] = clock64();
+    }
     __syncwarp();
     tc_fence_before();
     __syncthreads();
@@ -999,15 +1011,16 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
         long long* d_trace = nullptr;
         if (trace_path && *trace_path && ip == 0) {
-            FB_CUDA(cudaMalloc(&d_trace, 16 * 32 * sizeof(long long)));
-            FB_CUDA(cudaMemsetAsync(d_trace, 0, 16 * 32 * sizeof(long long), stream));
+            FB_CUDA(cudaMalloc(&d_trace, (16 * 32 + 2 * 128) * sizeof(long long)));
+            FB_CUDA(cudaMemsetAsync(d_trace, 0, (16 * 32 + 2 * 128) * sizeof(long long), stream));
             tp.trace = d_trace;
+            if (const char* sk = getenv("FIBERS_TC_TRACE_SKIP")) tp.trace_skip = (uint32_t)atoi(sk);
         }
         recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap);
         count_launch(1);
         FB_CUDA(cudaGetLastError());
         if (d_trace) {
-            std::vector<long long> h(16 * 32);
+            std::vector<long long> h(16 * 32 + 2 * 128);               // tile trace + per-cluster (start, end) in ns
             FB_CUDA(cudaStreamSynchronize(stream));
             FB_CUDA(cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
             cudaFree(d_trace);

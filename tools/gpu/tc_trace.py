@@ -30,7 +30,18 @@ for _ in range(2):
     plan.recon(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
                [q.data_ptr() for q in qa], stats.data_ptr(), finalize=True, stream=0)
 torch.cuda.synchronize()
-t = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64).reshape(16, 32)
+raw = np.fromfile("/tmp/tc_trace.bin", dtype=np.int64)
+t = raw[:512].reshape(16, 32)
+span = raw[512:].reshape(-1, 2)
+cyc = span[127]
+span = span[:127]
+span = span[span[:, 1] > 0]
+if len(span):
+    dur = (span[:, 1] - span[:, 0]) / 1e3
+    print(f"per-cluster kernel span (us): n={len(dur)} min {dur.min():.0f} median {np.median(dur):.0f} max {dur.max():.0f}; "
+          f"start spread {(span[:, 0].max() - span[:, 0].min()) / 1e3:.0f} us, end spread {(span[:, 1].max() - span[:, 1].min()) / 1e3:.0f} us")
+    print(f"cluster 0: {cyc[1] - cyc[0]} SM cycles in {(span[0, 1] - span[0, 0]) / 1e3:.0f} us -> effective SM clock {(cyc[1] - cyc[0]) / (span[0, 1] - span[0, 0]) * 1e3:.0f} MHz")
+    print("slowest clusters:", np.argsort(-dur)[:8].tolist(), " fastest:", np.argsort(dur)[:8].tolist())
 t0 = t[0, 0]
 names = {0: "mma:start", 1: "mma:done", 2: "epi:d_full", 3: "epi:tmem_read_done", 4: "epi:bar1", 5: "epi:peaks_done", 6: "epi:bar2",
          7: "epi:merge_done", 8: "epi:bar3", 9: "conv:tile_start", 10: "conv:first_loads_issued", 11: "conv:a_empty_ok", 12: "conv:tile_end",
