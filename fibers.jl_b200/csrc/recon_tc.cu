@@ -84,7 +84,7 @@ struct TcParams {
     int nstage;                  // depth of the B ring (<= NSTAGE)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
-    int dwi_vec;                 // 1: dwi base 16-byte aligned and pitch % 4 == 0 (16-byte cp.async)
+    int dwi_vec;                 // DWI staging copies: 2 = 16 bytes (base 16-byte aligned, pitch % 4 == 0), 1 = 8 bytes, 0 = 4 bytes
     int cand_cap;                // capacity of the candidate list (<= CAND_CAP; tests shrink it to force the fall-back)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
     uint32_t trace_skip;         // first traced tile iteration
@@ -432,7 +432,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
         const uint32_t sd0 = smem_u32(s_dwi);                           // [DSTAGE][32][128] floats
         constexpr int PF = DSTAGE - 1;
         constexpr uint32_t STAGE_B = 32 * VOX_CTA * 4;
-        const bool vec = p.dwi_vec != 0;
+        const int vec = p.dwi_vec;
         // prefetch cursor
         int p_ti = cluster_id, p_c = 0; uint32_t p_g = 0;
         int64_t p_vox0 = 0;
@@ -443,7 +443,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                     p_vox0 = (int64_t)ptile * 256 + rank * VOX_CTA;
                 }
                 const uint32_t dst = sd0 + (p_g % DSTAGE) * STAGE_B;
-                if (vec) {
+                if (vec == 2) {
                     const int64_t v4 = p_vox0 + 4 * lane;
                     const int64_t left = p.nvox - v4;
                     const uint32_t full = left >= 4 ? 16u : (left > 0 ? (uint32_t)left * 4u : 0u);
@@ -454,6 +454,21 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
                                      ::"r"(dst + (uint32_t)(cw * 8 + j) * (VOX_CTA * 4) + lane * 16), "l"(k < p.K ? src : p.dwi), "r"(k < p.K ? full : 0u) : "memory");
                         src += p.dwi_pitch;
+                    }
+                } else if (vec == 1) {                                  // rows 8-byte aligned: two voxels per copy, two copies per volume
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int64_t v2 = p_vox0 + 64 * half + 2 * lane;
+                        const int64_t left = p.nvox - v2;
+                        const uint32_t full = left >= 2 ? 8u : (left > 0 ? 4u : 0u);
+                        const float* src = p.dwi + (full ? v2 : 0) + (int64_t)(p_c * 32 + cw * 8) * p.dwi_pitch;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = p_c * 32 + cw * 8 + j;
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+                                         ::"r"(dst + (uint32_t)(cw * 8 + j) * (VOX_CTA * 4) + half * 256 + lane * 8), "l"(k < p.K ? src : p.dwi), "r"(k < p.K ? full : 0u) : "memory");
+                            src += p.dwi_pitch;
+                        }
                     }
                 } else {
                     const int64_t pvox = p_vox0 + vl;
@@ -993,7 +1008,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         if (ps.plain && !a.pdf) continue;
         TcParams tp{};
         tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
-        tp.dwi_vec = ((uintptr_t)a.dwi % 16 == 0) && (a.dwi_pitch % 4 == 0);
+        tp.dwi_vec = ((uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0) ? 2 : ((uintptr_t)a.dwi % 8 == 0 && a.dwi_pitch % 2 == 0) ? 1 : 0;
         tp.cand_cap = CAND_CAP;
         if (const char* cap = getenv("FIBERS_TC_CAND_CAP")) tp.cand_cap = std::max(0, std::min(CAND_CAP, atoi(cap)));
         tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = ps.rows; tp.Npad = ps.Npad; tp.N1 = ps.N1; tp.N2 = ps.N2;

@@ -153,7 +153,7 @@ def test_full_volume_dti_invariants(env):
 
 def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
     """The tensor-core kernel stages the DWI slab with 16-byte copies when the rows are 16-byte aligned and with
-    4-byte copies otherwise; both must give the same bits.  Odd voxel count, partial last tile, ragged mask."""
+    8- or 4-byte copies otherwise; all three must give the same bits.  Odd voxel count, partial last tile, ragged mask."""
     import torch
     import bench
     import fibers_jl_b200 as F
@@ -161,10 +161,15 @@ def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
     dev = torch.device("cuda", 0)
     bval, bvec = bench.make_tables()
     nvox = 50003                                              # not a multiple of 4; last 256-voxel tile is partial
-    pitch_al, pitch_un = (nvox + 63) // 64 * 64, nvox + 1     # 50004 * 4 bytes: rows not 16-byte aligned
+    pitch_al, pitch_un = (nvox + 63) // 64 * 64, nvox + 2     # 50005 elements: rows are only 4-byte aligned
+    assert pitch_al % 4 == 0 and pitch_un % 2 == 1
     dwi_al = bench.synth_dwi_device(torch, nvox, bval, bvec, 5, dev, pitch=pitch_al)
     dwi_un = torch.zeros((bval.shape[0], pitch_un), dtype=torch.float32, device=dev)
     dwi_un[:, :nvox] = dwi_al[:, :nvox]
+    pitch_8 = nvox + 3                                        # 50006 elements: rows 8-byte aligned (8-byte copies)
+    assert pitch_8 % 4 == 2
+    dwi_8 = torch.zeros((bval.shape[0], pitch_8), dtype=torch.float32, device=dev)
+    dwi_8[:, :nvox] = dwi_al[:, :nvox]
     g = torch.Generator(device=dev); g.manual_seed(3)
     mask = (torch.rand(nvox, generator=g, device=dev) < 0.7).to(torch.uint8)
     mask[1024:2048] = 0                                       # whole tiles without a mask voxel
@@ -173,7 +178,7 @@ def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
     try:
         plan = D.Plan("gqi", 0, bval, bvec, F.sphere_642, 1.25)
         assert plan.kernel == "tc"
-        for dwi, dp in ((dwi_al, pitch_al), (dwi_un, pitch_un)):
+        for dwi, dp in ((dwi_al, pitch_al), (dwi_un, pitch_un), (dwi_8, pitch_8)):
             opitch = pitch_al
             odf = torch.full((321, opitch), 7.0, dtype=torch.float32, device=dev)
             peak = [torch.full((3, opitch), 7.0, dtype=torch.float32, device=dev) for _ in range(3)]
@@ -187,10 +192,11 @@ def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
                         idx[:, :nvox].clone(), int(stats[0].item())))
     finally:
         D.set_kernel("auto")
-    a, b = res
-    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and a[4] == b[4]
-    for k in range(3):
-        assert torch.equal(a[1][k], b[1][k]) and torch.equal(a[2][k], b[2][k])
+    a = res[0]
+    for b in res[1:]:
+        assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3]) and a[4] == b[4]
+        for k in range(3):
+            assert torch.equal(a[1][k], b[1][k]) and torch.equal(a[2][k], b[2][k])
     # voxels outside the mask are zero-filled, inside they are reconstructed
     out = mask == 0
     assert (a[0][:, out] == 0).all() and (a[3][:, out] == -1).all()
