@@ -210,6 +210,13 @@ def test_multi_gpu_zslab_sharding(F, sphere642):
         pt = phantom.dti_phantom((16, 14, 9), seed=18)
         d1 = F.dti_fit(*_mri(F, pt), ngpu=1); d2 = F.dti_fit(*_mri(F, pt), ngpu=2)
         assert np.array_equal(d1.fa.vol, d2.fa.vol, equal_nan=True) and np.array_equal(d1.valid, d2.valid)
+        # the fused DTI + GQI call shards the same way
+        fd, fg = F.dti_gqi_fit(*_mri(F, ph), ngpu=2)
+        assert np.array_equal(fg.odf.vol, g1.odf.vol)
+        for k in range(3):
+            assert np.array_equal(fg.qa[k].vol, g1.qa[k].vol, equal_nan=True) and np.array_equal(fg.peak[k].vol, g1.peak[k].vol)
+        dref = F.dti_fit(*_mri(F, ph), ngpu=1)
+        assert np.array_equal(fd.fa.vol, dref.fa.vol, equal_nan=True) and np.array_equal(fd.eigvec1.vol, dref.eigvec1.vol, equal_nan=True)
     finally:
         F.device.set_devices([0])
 
