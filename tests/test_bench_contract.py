@@ -24,3 +24,26 @@ def test_reference_arm_prints_one_contract_line():
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_our_arm_prints_one_contract_line_on_the_gpu():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--shape", "64,64,32", "--steps", "3", "--warmup", "3",
+                          "--e2e-steps", "2", "--no-cpu"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert "impl" not in d and d["metric"] == "voxels/sec (GQI recon+peaks)" and d["unit"] == "voxels/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["value"] > 0
+    assert d["kernel"] == "tc" and d["gpu_launches"] >= 3 * 5          # the native kernels ran (no fallback exists)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1 and abs(r["achieved"] / r["peak"] - r["frac"]) < 1e-9
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 64 * 32 * 288 * 4 + 64 * 64 * 32
+    assert e["d2h_bytes_per_step"] == 64 * 64 * 32 * 4 * (321 + 9 + 3)
+    c = d["clocks"]
+    assert c["sm_max_mhz"] > 0 and isinstance(c["reasons"], list)
