@@ -353,39 +353,52 @@ def main():
 
     # ---- end to end through the host-pointer C ABI (what the Julia wrapper ccalls) ----------
     e2e = None
+    e2e_error = None
     if not args.no_e2e:
-        h_dwi = torch.empty((nvol, nvox), dtype=torch.float32, pin_memory=True)
-        h_dwi.copy_(dwi[:, :nvox])
-        torch.cuda.synchronize()
-        del dwi, odf, peak
-        torch.cuda.empty_cache()
-        h_mask = torch.empty(nvox, dtype=torch.uint8, pin_memory=True); h_mask.copy_(mask)
-        h_odf = torch.empty((M_VERT, nvox), dtype=torch.float32, pin_memory=True)
-        h_peak = [torch.empty((3, nvox), dtype=torch.float32, pin_memory=True) for _ in range(3)]
-        h_qa = [torch.empty(nvox, dtype=torch.float32, pin_memory=True) for _ in range(3)]
-        L = F._lib.lib()
-        V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces)
-        bv = np.asfortranarray(bvec)
+        # Set-up can fail on a box that cannot pin 9 GB of host memory per rank: every rank then agrees (one reduction)
+        # to report "e2e": null instead of hanging in a barrier or losing the whole line.
+        e2e_step = None
+        try:
+            h_dwi = torch.empty((nvol, nvox), dtype=torch.float32, pin_memory=True)
+            h_dwi.copy_(dwi[:, :nvox])
+            torch.cuda.synchronize()
+            del dwi, odf, peak
+            torch.cuda.empty_cache()
+            h_mask = torch.empty(nvox, dtype=torch.uint8, pin_memory=True); h_mask.copy_(mask)
+            h_odf = torch.empty((M_VERT, nvox), dtype=torch.float32, pin_memory=True)
+            h_peak = [torch.empty((3, nvox), dtype=torch.float32, pin_memory=True) for _ in range(3)]
+            h_qa = [torch.empty(nvox, dtype=torch.float32, pin_memory=True) for _ in range(3)]
+            L = F._lib.lib()
+            V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces)
+            bv = np.asfortranarray(bvec)
 
-        def e2e_step():
-            F._lib.check(L.fibers_gqi_rec(h_dwi.data_ptr(), 0, h_mask.data_ptr(), shape[0], shape[1], shape[2], nvol,
-                                          F._lib.ptr(bval), F._lib.ptr(bv), F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc),
-                                          Fc.shape[0], 1.25, h_odf.data_ptr(), *[p.data_ptr() for p in h_peak],
-                                          *[q.data_ptr() for q in h_qa], None, 1))
-        e2e_step(); e2e_step()                      # warm-up: first-touch of the pinned pages, context cache
-        barrier()
-        per_step = []
-        for _ in range(args.e2e_steps):
-            t0 = time.perf_counter()
-            e2e_step()                              # blocking call: returns when the host buffers hold the results
-            per_step.append(time.perf_counter() - t0)
-        # host / PCIe side of a shared box is noisy: the median step is reported, the mean is kept beside it
-        dt = float(np.median(per_step)); dt_mean = float(np.mean(per_step))
-        dt = F.batch.reduce_max(dt, dist if world > 1 else None, dev)
-        e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox * (4 * nvol + 1),
-               "d2h_bytes_per_step": nvox * 4 * (M_VERT + 9 + 3), "ms_per_step": dt * 1e3, "ms_per_step_mean": dt_mean * 1e3,
-               "statistic": "median of per-step wall times", "steps": args.e2e_steps,
-               "api": "fibers_gqi_rec (host pointers, pinned buffers)"}
+            def e2e_step():
+                F._lib.check(L.fibers_gqi_rec(h_dwi.data_ptr(), 0, h_mask.data_ptr(), shape[0], shape[1], shape[2], nvol,
+                                              F._lib.ptr(bval), F._lib.ptr(bv), F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc),
+                                              Fc.shape[0], 1.25, h_odf.data_ptr(), *[p.data_ptr() for p in h_peak],
+                                              *[q.data_ptr() for q in h_qa], None, 1))
+            e2e_step(); e2e_step()                  # warm-up: first-touch of the pinned pages, context cache
+            ok = 1.0
+        except Exception as ex:                     # noqa: BLE001 - reported in the JSON line
+            ok = 0.0
+            e2e_error = f"{type(ex).__name__}: {ex}"[:200]
+        ok_all = -F.batch.reduce_max(-ok, dist if world > 1 else None, dev)      # min over ranks
+        if ok_all > 0.5:
+            barrier()
+            per_step = []
+            for _ in range(args.e2e_steps):
+                t0 = time.perf_counter()
+                e2e_step()                          # blocking call: returns when the host buffers hold the results
+                per_step.append(time.perf_counter() - t0)
+            # host / PCIe side of a shared box is noisy: the median step is reported, the mean is kept beside it
+            dt = float(np.median(per_step)); dt_mean = float(np.mean(per_step))
+            dt = F.batch.reduce_max(dt, dist if world > 1 else None, dev)
+            e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox * (4 * nvol + 1),
+                   "d2h_bytes_per_step": nvox * 4 * (M_VERT + 9 + 3), "ms_per_step": dt * 1e3, "ms_per_step_mean": dt_mean * 1e3,
+                   "statistic": "median of per-step wall times", "steps": args.e2e_steps,
+                   "api": "fibers_gqi_rec (host pointers, pinned buffers)"}
+        elif e2e_error is None:
+            e2e_error = "end-to-end set-up failed on another rank"
 
     if rank == 0:
         peak_gbs, peak_src = measured_peaks()
@@ -405,6 +418,9 @@ def main():
                              "algorithmic_tflops": 2.0 * nvol * M_VERT * fill * nvox / (kern_ms * 1e-3) / 1e12}}
         if e2e:
             line["e2e"] = e2e
+        elif e2e_error:
+            line["e2e"] = None
+            line["e2e_error"] = e2e_error
         if not args.no_cpu and world == 1:              # reported baseline: rank 0 at N = 1 only
             vps, ms, cores, sample = run_cpu_reference(shape, 2, 1, budget_s=12.0)
             line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
