@@ -47,3 +47,17 @@ def test_our_arm_prints_one_contract_line_on_the_gpu():
     assert e["d2h_bytes_per_step"] == 64 * 64 * 32 * 4 * (321 + 9 + 3)
     c = d["clocks"]
     assert c["sm_max_mhz"] > 0 and isinstance(c["reasons"], list)
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """N > 1: the driver launches the reference arm through torchrun as well; rank 0 alone runs and prints."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--shape", "16,16,8", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
