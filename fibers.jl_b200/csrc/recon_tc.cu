@@ -64,11 +64,13 @@ constexpr int KEY_ROW = VOX_CTA * 2;    // bytes per vertex row of the key tile
 constexpr int CAND_CAP = 2048;          // listed (voxel, vertex) pairs per 128-voxel tile; overflow -> SIMT fix-up
 constexpr float KEY_WINDOW = 8.f;       // keys cover [0, 8 x mean(ODF of the voxel)) in 32767 steps (bit 15 is always set)
 
-// Folded-mesh neighbour table in CONSTANT memory: byte offsets (vertex * KEY_ROW) into the key tile,
-// 8 per vertex (missing neighbours -> the all-zero sentinel row M).  The vertex index is warp-uniform,
-// so the offsets arrive through the uniform datapath and each neighbour costs one LDS.64.
+// Folded-mesh neighbour table as a KERNEL PARAMETER (constant bank 0, private to the launch): byte offsets
+// (vertex * KEY_ROW) into the key tile, 8 per vertex (missing neighbours -> the all-zero sentinel row M).  The
+// vertex index is warp-uniform, so the offsets arrive through the uniform datapath and each neighbour costs one
+// LDS.64.  (A device-global __constant__ symbol here would be shared by every plan and stream of the device:
+// two plans with different meshes running concurrently would read each other's table.)
 constexpr int TC_MAX_VERT = 392;        // rows of the offset table: M + 1 sentinel rows up to M + 8 (prefetch overrun)
-__constant__ uint32_t c_nbr_off[TC_MAX_VERT * NBR_W];
+struct NbrOffTable { uint32_t off[TC_MAX_VERT * NBR_W]; };   // 12.5 KB of the 32 KB parameter space
 
 struct TcParams {
     const float* dwi; int64_t dwi_pitch; const uint8_t* mask; int64_t nvox;
@@ -105,8 +107,7 @@ struct TcState {
     std::vector<TcPass> pass;
     void* encode = nullptr;      // cuTensorMapEncodeTiled
     int Kpad = 0, nbw = 8;
-    unsigned long long uid = 0;              // identifies the neighbour table in the per-device constant-memory cache
-    std::vector<uint32_t> h_nbr_off;         // [M + 8][NBR_W] byte offsets (rows >= M: sentinel)
+    NbrOffTable nbr_off;                     // [M + 8][NBR_W] byte offsets (rows >= M: sentinel); passed by value with every launch
     size_t smem = 0;
     int* d_scratch = nullptr;    // [0] maxbits, [1] fix_count, [2..] fix list
     int64_t scratch_cap = 0;
@@ -273,7 +274,8 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB) {
+recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ NbrOffTable nbt) {
+    const uint32_t* const c_nbr_off = nbt.off;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the warp index is rebuilt from warp votes so that the compiler can prove it warp-uniform (uniform registers,
     // uniform branches, constant-bank loads and [R + UR] addressing in the role loops)
@@ -837,10 +839,11 @@ size_t tc_smem_bytes(int M, int Nh, int nstage) {
     return b + 1024 + 64;
 }
 
-struct ConstCache { unsigned long long uid[64]; };
-ConstCache g_const_cache{};
-std::mutex g_const_mu;
-std::atomic<unsigned long long> g_next_uid{1};
+// The dynamic shared-memory limit is an attribute of (function, device), shared by all plans: it is only ever
+// raised (a plan with a smaller tile must not lower it under a live plan with a larger one).
+std::mutex g_smem_mu;
+size_t g_smem_limit[64] = {};
+int raise_smem_limit(int device, size_t smem);
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -877,12 +880,11 @@ int tc_plan_init(Plan* p) {
     const int Kpad = (K + 31) / 32 * 32;
     TcState* st = new TcState();
     st->Kpad = Kpad; st->nbw = p->nbr_width; st->encode = fn;
-    st->uid = g_next_uid.fetch_add(1);
-    st->h_nbr_off.assign((size_t)(M + 8) * NBR_W, (uint32_t)M * KEY_ROW);          // sentinel row M everywhere ...
+    for (int i = 0; i < TC_MAX_VERT * NBR_W; ++i) st->nbr_off.off[i] = (uint32_t)M * KEY_ROW;      // sentinel row M everywhere ...
     for (int v = 0; v < M; ++v)
         for (int k = 0; k < NBR_W; ++k) {
             const uint16_t n = p->h_nbr[(size_t)v * NBR_W + k];
-            if (n != NBR_NONE) st->h_nbr_off[(size_t)v * NBR_W + k] = (uint32_t)n * KEY_ROW;
+            if (n != NBR_NONE) st->nbr_off.off[(size_t)v * NBR_W + k] = (uint32_t)n * KEY_ROW;
         }
     // passes: ODF rows, then (DSI) the pdf rows in blocks of <= 336
     std::vector<std::pair<int, int>> ranges = {{0, M}};
@@ -949,12 +951,23 @@ int tc_plan_init(Plan* p) {
     }
     if (smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
     st->smem = smem;
-    if (cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); tc_state_free(st); return 1;
-    }
+    if (raise_smem_limit(p->device, smem)) { tc_state_free(st); return 1; }
     p->tc = st;
     return 0;
 }
+
+namespace {
+int raise_smem_limit(int device, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    size_t& cur = g_smem_limit[device & 63];
+    if (smem <= cur) return 0;
+    if (cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); return 1;
+    }
+    cur = smem;
+    return 0;
+}
+}  // namespace
 
 void tc_plan_free(Plan* p) {
     tc_state_free(reinterpret_cast<TcState*>(p->tc));
@@ -977,15 +990,6 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
     if (int rc = plan_enter(p, stream)) return rc;                  // the scratch below belongs to the plan
     FB_CUDA(cudaMemsetAsync(st->d_scratch, 0, 4 * sizeof(int), stream));
     int* d_fix_list = st->d_scratch + 4; int* d_tile_list = st->d_scratch + 4 + 2 * ntile64;
-    {   // neighbour offsets -> constant memory of this device (skipped when this plan's table is already resident;
-        // launches of DIFFERENT plans on one device must not overlap in time)
-        std::lock_guard<std::mutex> lk(g_const_mu);
-        if (p->device < 64 && g_const_cache.uid[p->device] != st->uid) {
-            FB_CUDA(cudaMemcpyToSymbolAsync(c_nbr_off, st->h_nbr_off.data(), st->h_nbr_off.size() * sizeof(uint32_t), 0,
-                                            cudaMemcpyHostToDevice, stream));
-            g_const_cache.uid[p->device] = st->uid;
-        }
-    }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p->device);
     sample_max_kernel<<<nsm * 8, 256, 0, stream>>>(a.dwi, a.dwi_pitch, a.nvox, p->nvol, st->d_scratch);
@@ -1031,7 +1035,7 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
             tp.trace = d_trace;
             if (const char* sk = getenv("FIBERS_TC_TRACE_SKIP")) tp.trace_skip = (uint32_t)atoi(sk);
         }
-        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap);
+        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, st->nbr_off);
         count_launch(1);
         FB_CUDA(cudaGetLastError());
         if (d_trace) {

@@ -1,0 +1,212 @@
+"""GPU parity on the BASELINE.json configurations themselves (shapes and protocols, z-sub-slabs where the
+full volume would take the CPU oracle minutes): the CUDA path, called through the C ABI, against the
+CPU oracle (numpy fp64 truth, fp32 reference-order restatement, C port) on the same seeded inputs.
+
+  cfg1  64x64x40x31   DTI and ADC, full volume                       src/dti.jl:164-316
+  cfg2  145x174x8x288 GQI, DTI (multi-shell, Woodbury branch), fused src/gqi.jl:132-168, src/dti.jl:286-316
+  cfg3  96x96x4x515   DSI (odf, pdf, peaks)                           src/dsi.jl:197-267
+  cfg5  400x400x2x128 GQI with the 8 b0 + 120 x b=4000 protocol       src/gqi.jl:132-168
+
+Every test prints the measured errors (pytest -s / the log kept under profiles/) and asserts the
+north_star tolerances written in tests/parity.py.
+"""
+import numpy as np
+import pytest
+
+import fibers_oracle as O
+import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def F():
+    import fibers_jl_b200 as F
+    assert F.device_count() > 0, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return F
+
+
+def _mri(F, ph):
+    return F.MRI(ph["dwi"], ph["bval"], ph["bvec"]), F.MRI(ph["mask"])
+
+
+def _report(name, **kw):
+    print(f"[parity] {name}: " + ", ".join(f"{k}={v:.3g}" if isinstance(v, float) else f"{k}={v}" for k, v in kw.items()))
+
+
+# --------------------------------------------------------------------------------------------
+# DTI comparison shared by cfg1 / cfg2 / fused.  Tolerances: north_star 1e-4 relative for FA / MD /
+# eigenvalues (lambda2/3 and RD relative to lambda1: conditioning-aware), |V1.V1ref| >= 0.9999
+# where lambda1 is separated.  The PARTIAL branch (per-voxel pinv of the positive samples,
+# src/dti.jl:297-298) is held to the same 1e-4; a voxel is exempt only when the reference-order fp32
+# oracle ITSELF is further than 0.5e-4 from the fp64 truth (ill-conditioned sub-system), and the
+# exempted fraction is reported and bounded.
+# --------------------------------------------------------------------------------------------
+def _check_dti(got, ph, what, min_partial_frac=0.0, valid=None):
+    r64 = O.dti_fit(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], np.float64)
+    r32 = O.dti_fit(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], np.float32)
+    kind = P.flat(r64["kind"])
+    if valid is not None:
+        assert np.array_equal(valid, r32["valid"]), f"{what}: valid-voxel set must be bit exact"
+    v = P.flat(r32["valid"])
+    for name in ("s0", "eigval1", "eigval2", "eigval3", "rd", "md", "fa"):
+        assert np.all(P.flat(getattr(got, name).vol)[~v] == 0), f"{what}: {name} must stay zero outside the valid set"
+    full, part = kind == 1, kind == 2
+    assert full.sum() > 0
+    frac_part = part.sum() / max(1, (full | part).sum())
+    assert frac_part >= min_partial_frac, f"{what}: partial-branch fraction {frac_part:.3f} < {min_partial_frac}"
+    out = {"partial_frac": float(frac_part)}
+    l1 = np.abs(P.flat(r64["eigval1"]))
+    for branch, sel in (("full", full), ("partial", part)):
+        if sel.sum() == 0:
+            continue
+        exempt = np.zeros(sel.sum(), bool)
+        worst = 0.0
+        for name in ("s0", "eigval1", "md", "fa", "eigval2", "eigval3", "rd"):
+            ref = P.flat(r64[name])[sel]
+            scale = l1[sel] if name in ("eigval2", "eigval3", "rd") else np.maximum(np.abs(ref), 1e-30)
+            e_gpu = np.abs(P.flat(getattr(got, name).vol)[sel].astype(np.float64) - ref) / scale
+            e_ref = np.abs(P.flat(r32[name])[sel].astype(np.float64) - ref) / scale
+            ill = e_ref > 0.5 * P.SCALAR_TOL
+            if branch == "full":
+                assert not ill.any(), f"{what}: fp32 reference arithmetic off by > 0.5e-4 on the full branch ({name})"
+            exempt |= ill
+            bad = (e_gpu >= P.SCALAR_TOL) & ~ill
+            assert not bad.any(), f"{what} {branch} {name}: {bad.sum()} voxels off by up to {e_gpu[bad].max():.2e}"
+            worst = max(worst, float(e_gpu[~ill].max()) if (~ill).any() else 0.0)
+        out[f"{branch}_max_rel_err"] = worst
+        out[f"{branch}_exempt_frac"] = float(exempt.mean())
+        assert exempt.mean() < 0.02, f"{what}: {exempt.mean():.3f} of the {branch} voxels are ill-conditioned"
+    # V1 where lambda1 is separated from lambda2
+    both = full | part
+    gap = ((P.flat(r64["eigval1"]) - P.flat(r64["eigval2"])) / np.maximum(l1, 1e-30))[both]
+    dots = np.abs((P.flat(got.eigvec1.vol, 3)[both].astype(np.float64) * P.flat(r64["eigvec1"], 3)[both]).sum(axis=1))
+    sep = gap > 2e-2
+    assert dots[sep].min() >= P.V1_DOT, f"{what}: V1 dot {dots[sep].min()}"
+    out["v1_min_dot"] = float(dots[sep].min()); out["v1_checked_frac"] = float(sep.mean())
+    _report(what, **out)
+    return out
+
+
+def _check_recon(got, r64, v, f, M, what, idx=None):
+    nbr = O.neighbour_table(O.fold_faces(f, M), M)
+    err = P.odf_rel_err(got.odf.vol, r64["odf"])
+    assert err < P.ODF_TOL, (what, err)
+    idx = got.peak_idx if idx is None else idx
+    nbad, nun = P.peak_mismatch_report(idx, r64, nbr)
+    nvox = r64["computed"].size
+    assert nun == 0, f"{what}: {nun} unexplained peak mismatches ({nbad} total of {nvox})"
+    assert nbad <= max(2, 2e-3 * nvox), f"{what}: too many tie-explained mismatches: {nbad}"
+    fi = P.flat(idx, 3)
+    same = (fi == P.flat(r64["peak_idx"], 3)).all(axis=1)
+    scale = np.abs(P.flat(r64["odf"], M)).max(axis=1) / float(r64["odfmax"])
+    qerr = 0.0
+    for k in range(3):
+        pk = P.flat(got.peak[k].vol, 3)
+        ok = fi[:, k] >= 0
+        assert np.array_equal(pk[ok], v[fi[ok, k]]) and np.all(pk[~ok] == 0)
+        d = np.abs(P.flat(got.qa[k].vol).astype(np.float64) - P.flat(r64["qa"][k]))[same]
+        assert np.all(d <= 2 * P.ODF_TOL * scale[same] + 1e-12), what
+        qerr = max(qerr, float((d / np.maximum(scale[same], 1e-30)).max()))
+    _report(what, odf_max_rel_err=err, peak_mismatch=nbad, unexplained=nun, voxels=nvox, qa_err_rel_voxel_max=qerr,
+            computed_frac=float(r64["computed"].mean()))
+    return err, nbad
+
+
+def _peak_indices_from_vectors(peaks, vertices_half):
+    """The reference never outputs indices: recover them by exact row match against the vertex table."""
+    out = []
+    for pk in peaks:
+        p = P.flat(pk.vol, 3)
+        i = np.argmax(p.astype(np.float64) @ vertices_half.T.astype(np.float64), axis=1)
+        hit = (vertices_half[i] == p).all(axis=1)
+        zero = (p == 0).all(axis=1)
+        assert np.all(hit | zero), "peak vectors must be verbatim vertex rows"
+        out.append(np.where(hit, i, -1))
+    return np.stack(out, axis=1).reshape(peaks[0].vol.shape[:3] + (3,), order="F")
+
+
+# ---------------------------------------------------------------- cfg1
+def test_cfg1_dti_and_adc_full_volume(F):
+    from fibers_jl_b200 import phantom
+    ph = phantom.dti_phantom((64, 64, 40), nb0=1, ndir=30, b=1000.0, seed=1)
+    assert ph["dwi"].shape == (64, 64, 40, 31)
+    got = F.dti_fit(*_mri(F, ph))
+    # single shell, up to 3 of 31 samples dropped: the partial sub-system is markedly worse conditioned
+    _check_dti(got, ph, "cfg1 dti 64x64x40x31", valid=got.valid)
+    adc, s0 = F.adc_fit(*_mri(F, ph))
+    a64, s64 = O.adc_fit(ph["dwi"], ph["mask"], ph["bval"], np.float64)
+    a32, s32 = O.adc_fit(ph["dwi"], ph["mask"], ph["bval"], np.float32)
+    nz = P.flat(a64) != 0
+    assert np.array_equal(P.flat(adc.vol) != 0, nz)
+    ea, es = P.rel_err(adc.vol, a64, nz), P.rel_err(s0.vol, s64, nz)
+    assert ea < P.SCALAR_TOL and es < P.SCALAR_TOL, (ea, es)
+    _report("cfg1 adc 64x64x40x31", adc_max_rel_err=ea, s0_max_rel_err=es, voxels=int(nz.sum()),
+            fp32_oracle_adc_err=P.rel_err(a32, a64, nz))
+
+
+# ---------------------------------------------------------------- cfg2 / cfg4 protocol
+@pytest.fixture(scope="module")
+def cfg2_slab():
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((145, 174, 8), seed=202)           # 201 840 voxels x 288 volumes, mask == 1
+    v, f = O.load_sphere(642)
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    return ph, v, f, r64
+
+
+def test_cfg2_gqi_subslab(F, cfg2_slab):
+    ph, v, f, r64 = cfg2_slab
+    assert ph["dwi"].shape == (145, 174, 8, 288)
+    got = F.gqi_rec(*_mri(F, ph))
+    assert F.device.Plan("gqi", 0, ph["bval"], ph["bvec"]).kernel == "tc"
+    _check_recon(got, r64, v, f, 321, "cfg2 gqi 145x174x8x288 (tensor-core kernel)")
+    # the C port (what bench.py times as the CPU baseline) agrees with the numpy oracle on the same slab
+    import c_oracle as CO
+    rc = CO.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25)
+    assert P.odf_rel_err(rc["odf"], r64["odf"]) < P.ODF_TOL
+    nbr = O.neighbour_table(O.fold_faces(f, 321), 321)
+    assert P.peak_mismatch_report(rc["peak_idx"], r64, nbr)[1] == 0
+
+
+def test_cfg2_dti_multishell_woodbury(F, cfg2_slab):
+    """N = 288 multi-shell (the cfg4 protocol): ~25 % of the voxels hold a non-positive sample and take the
+    partial branch, which the kernel solves inline as a rank-r downdate (Woodbury) of the full normal matrix."""
+    ph = cfg2_slab[0]
+    got = F.dti_fit(*_mri(F, ph))
+    _check_dti(got, ph, "cfg2 dti 145x174x8x288", min_partial_frac=0.10, valid=got.valid)
+
+
+def test_cfg2_fused_dti_gqi_vs_oracle(F, cfg2_slab):
+    """fibers_dti_gqi_fit against the ORACLE (not against the two separate CUDA calls)."""
+    ph, v, f, r64 = cfg2_slab
+    d, g = F.dti_gqi_fit(*_mri(F, ph))
+    idx = _peak_indices_from_vectors(g.peak, v[:321])
+    _check_recon(g, r64, v, f, 321, "cfg2 fused: gqi part", idx=idx)
+    _check_dti(d, ph, "cfg2 fused: dti part", min_partial_frac=0.10)
+
+
+# ---------------------------------------------------------------- cfg3
+def test_cfg3_dsi_subslab(F):
+    from fibers_jl_b200 import phantom
+    ph = phantom.dsi_phantom((96, 96, 4), seed=303)              # 36 864 voxels x 515 q-space points
+    assert ph["dwi"].shape == (96, 96, 4, 515)
+    v, f = O.load_sphere(642)
+    got = F.dsi_rec(*_mri(F, ph))
+    assert F.device.Plan("dsi", 0, ph["bval"], ph["bvec"]).kernel == "tc"
+    r64 = O.dsi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 32, np.float64)
+    _check_recon(got, r64, v, f, 321, "cfg3 dsi 96x96x4x515 (tensor-core kernel)")
+    perr = P.odf_rel_err(got.pdf.vol, r64["pdf"])
+    assert perr < P.ODF_TOL, perr
+    _report("cfg3 dsi pdf", pdf_max_rel_err=perr)
+
+
+# ---------------------------------------------------------------- cfg5 protocol
+def test_cfg5_protocol_gqi_slab(F):
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((400, 400, 2), nb0=8, shells=((4000.0, 120),), seed=505)
+    assert ph["dwi"].shape == (400, 400, 2, 128)
+    v, f = O.load_sphere(642)
+    got = F.gqi_rec(*_mri(F, ph))
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    _check_recon(got, r64, v, f, 321, "cfg5 protocol gqi 400x400x2x128 (8 b0 + 120 x b=4000)")

@@ -331,3 +331,44 @@ def test_fused_dti_gqi_equals_the_two_calls(F, sphere642):
     for k in range(3):
         assert np.array_equal(g1.peak[k].vol, g2.peak[k].vol) and np.array_equal(g1.qa[k].vol, g2.qa[k].vol)
     assert np.count_nonzero(d2.fa.vol) > 1000 and np.count_nonzero(g2.qa[0].vol) > 1000
+
+
+def test_two_live_plans_with_different_spheres_interleaved_and_concurrent(F):
+    """Two tensor-core plans with different meshes live on ONE device: the neighbour table travels with every
+    launch (kernel parameter) and the shared-memory limit of the kernel is never lowered, so alternating launches
+    and two host threads reconstructing at the same time (the library is re-entrant, include/fibers_cuda.h) give
+    the same bits as each call alone."""
+    import threading
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((24, 20, 12), seed=52, mask_fill=0.7)
+    spheres = {n: F.ODF(*O.load_sphere(n)) for n in (642, 362, 724)}
+    F.device.set_kernel("tc")
+    try:
+        alone = {n: F.gqi_rec(*_mri(F, ph), s) for n, s in spheres.items()}
+        # creating the plan with the smallest tile LAST must not break the larger ones (642 needs ~215 KB, 362 ~145 KB)
+        for n in (642, 362, 642, 724, 362, 724, 642):
+            g = F.gqi_rec(*_mri(F, ph), spheres[n])
+            assert np.array_equal(g.odf.vol, alone[n].odf.vol) and np.array_equal(g.peak_idx, alone[n].peak_idx)
+        # device-resident plans kept alive side by side
+        plans = [F.device.Plan("gqi", 0, ph["bval"], ph["bvec"], spheres[n]) for n in (642, 362, 724)]
+        assert all(p.kernel == "tc" for p in plans)
+        out, errs = {}, []
+
+        def work(n, reps):
+            try:
+                for _ in range(reps):
+                    out[n] = F.gqi_rec(*_mri(F, ph), spheres[n])
+            except Exception as e:          # noqa: BLE001
+                errs.append(e)
+        for _ in range(3):
+            th = [threading.Thread(target=work, args=(n, 4)) for n in (642, 724)]
+            [t.start() for t in th]; [t.join() for t in th]
+            assert not errs, errs
+            for n in (642, 724):
+                assert np.array_equal(out[n].odf.vol, alone[n].odf.vol)
+                assert np.array_equal(out[n].peak_idx, alone[n].peak_idx), f"sphere_{n}: peaks differ under concurrency"
+                for k in range(3):
+                    assert np.array_equal(out[n].qa[k].vol, alone[n].qa[k].vol, equal_nan=True)
+        del plans
+    finally:
+        F.device.set_kernel("auto")
