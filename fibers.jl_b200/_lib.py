@@ -50,6 +50,9 @@ SIGNATURES = {
     "fibers_gqi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _f] + [_p] * 8 + [_i]),
     "fibers_dsi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i] + [_p] * 9 + [_i]),
     "fibers_dti_gqi_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 10 + [_p, _i, _p, _i, _f] + [_p] * 7 + [_i]),
+    "fibers_dti_gqi_fit_batch": (_i, [_i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i, _f, _p, _i]),
+    "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
+    "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),
     "fibers_adc_plan_create": (_i, [_p, _i, _i, _p]),
     "fibers_gqi_plan_create": (_i, [_p, _i, _i, _p, _p, _p, _i, _p, _i, _f]),

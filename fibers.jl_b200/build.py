@@ -22,7 +22,7 @@ EXTRA = {
     "setup.cpp": ["-Xcompiler", "-ffp-contract=off"],
     "recon_simt.cu": ["-diag-suppress", "128"],   # "loop is not reachable" in the plain-rows instantiation (early return)
 }
-SOURCES = ["api.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu"]
+SOURCES = ["api.cu", "host_pipeline.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu"]
 
 
 def _nvcc() -> str:

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include "common.cuh"
+#include "host_pipeline.h"
 
 namespace fibers {
 
@@ -22,6 +23,7 @@ static bool g_devices_init = false;
 static int g_kernel = FIBERS_KERNEL_AUTO;
 
 void set_error(const std::string& msg) { g_err = msg; }
+const std::string& last_error() { return g_err; }
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -32,7 +34,7 @@ static int device_count_raw() {
     return n;
 }
 
-static std::vector<int> device_list() {
+std::vector<int> device_list() {
     std::lock_guard<std::mutex> lk(g_cfg_mu);
     if (!g_devices_init) {
         g_devices_init = true;
@@ -75,7 +77,7 @@ static int upload(T** dptr, const std::vector<T>& h) {
     return 0;
 }
 
-static void plan_free(Plan* p) {
+void plan_free(Plan* p) {
     if (!p) return;
     int cur = 0;
     cudaGetDevice(&cur);
@@ -140,6 +142,12 @@ static int plan_upload_recon(Plan* p, const std::vector<float>& mat, const float
         else if (want == FIBERS_KERNEL_TC) return fail(FIBERS_ERR_ARG, "tensor-core kernel requested but not usable for this shape: " + g_err);
     }
     return 0;
+}
+
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = (const unsigned char*)data;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
 }
 
 static int to_rc(const std::string& e) {
@@ -312,319 +320,9 @@ int fibers_recon_device(fibers_plan* plan, const float* d_dwi, int64_t dwi_pitch
 
 }  // extern "C"
 
-// ============================================================================================
-// Host-pointer entry points: z-slab partitioner + per-GPU pipelines
-// ============================================================================================
-namespace fibers {
-
-struct Shard { int64_t v0, v1; };   // voxel range [v0, v1), aligned to z-slab boundaries
-
-// Split nz slices into ngpu contiguous z-slabs balanced by masked-voxel count.
-static std::vector<Shard> partition_slabs(const uint8_t* mask, int64_t nxny, int nz, int ngpu) {
-    std::vector<int64_t> cnt(nz);
-    int64_t total = 0;
-    for (int z = 0; z < nz; ++z) {
-        int64_t c = 0;
-        const uint8_t* m = mask + (int64_t)z * nxny;
-        for (int64_t i = 0; i < nxny; ++i) c += m[i] != 0;
-        cnt[z] = c + 1;           // +1: empty slices still cost a little
-        total += cnt[z];
-    }
-    std::vector<Shard> out;
-    int z0 = 0; int64_t acc = 0;
-    for (int g = 0; g < ngpu; ++g) {
-        int64_t target = total * (g + 1) / ngpu;
-        int z1 = z0;
-        while (z1 < nz && (acc + cnt[z1] <= target || z1 == z0) && (nz - z1) > (ngpu - 1 - g)) { acc += cnt[z1]; ++z1; }
-        if (g == ngpu - 1) z1 = nz;
-        out.push_back({(int64_t)z0 * nxny, (int64_t)z1 * nxny});
-        z0 = z1;
-    }
-    return out;
-}
-
-struct Frames {            // one host array with `nframes` frames of nvox elements each
-    void* host; int nframes; int elem; bool input;
-    char* dev[3];          // per pipeline slot
-};
-
-struct HostJob {
-    int kind;
-    int nvol, dtype;
-    int64_t nvox, nxny; int nz;
-    const void* dwi; const uint8_t* mask;
-    std::function<int(Plan**, int)> make_plan;
-    uint64_t plan_key = 0;                          // hash of everything the plan depends on (context cache)
-    // outputs (host)
-    std::vector<std::pair<void*, int>> out_f32;     // (ptr, nframes) float outputs in kernel order
-    float* qa[3] = {nullptr, nullptr, nullptr};
-    int16_t* peak_idx = nullptr; uint8_t* valid = nullptr;
-    // optional companion DTI fit on the same resident slab (fibers_dti_gqi_fit): one H2D of the DWI feeds both
-    std::function<int(Plan**, int)> make_plan2;
-    uint64_t plan2_key = 0;
-    std::vector<std::pair<void*, int>> out2_f32;    // the 10 DTI outputs in kernel order
-};
-
-struct Rendezvous {       // cross-shard reduction of odfmax (host side; no device collective)
-    std::mutex mu; std::condition_variable cv;
-    int arrived = 0, n = 0; float maxv = -INFINITY; bool failed = false;
-    float wait_max(float mine, bool ok) {
-        std::unique_lock<std::mutex> lk(mu);
-        if (!ok) failed = true;
-        maxv = std::max(maxv, mine);
-        if (++arrived == n) cv.notify_all();
-        else cv.wait(lk, [&] { return arrived == n; });
-        return maxv;
-    }
-};
-
-// Per-device context cache: streams, slab ring, QA scratch and the last plan survive between host
-// calls (a batch of subjects with one protocol pays for set-up once).  One call at a time may own a
-// device's cache; concurrent calls on the same device fall back to private allocations.
-struct DeviceCache {
-    std::mutex mu; bool busy = false;
-    cudaStream_t st[3] = {nullptr, nullptr, nullptr};
-    char* slab[3] = {nullptr, nullptr, nullptr}; size_t slab_bytes = 0;
-    float* qa = nullptr; size_t qa_bytes = 0; int32_t* stats = nullptr;
-    Plan* plan = nullptr; uint64_t plan_key = 0;
-    Plan* plan2 = nullptr; uint64_t plan2_key = 0;     // companion DTI plan of the fused entry point
-};
-static DeviceCache g_cache[64];
-
-static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
-    const unsigned char* p = (const unsigned char*)data;
-    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
-    return h;
-}
-
-#define W_CUDA(expr)                                                                          \
-    do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                    \
-        err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
-        code = _e == cudaErrorMemoryAllocation ? FIBERS_ERR_NOMEM : FIBERS_ERR_CUDA; goto done; } } while (0)
-
-static void shard_worker(const HostJob& job, int device, Shard sh, Rendezvous* rv, int* out_code, std::string* out_err) {
-    int code = 0; std::string err;
-    Plan* plan = nullptr; Plan* plan2 = nullptr;
-    const bool fused = (bool)job.make_plan2;
-    constexpr int NSLOT = 3;
-    cudaStream_t st[NSLOT] = {nullptr, nullptr, nullptr};
-    char* slab[NSLOT] = {nullptr, nullptr, nullptr};
-    float* d_qa_all = nullptr; int32_t* d_stats = nullptr;
-    DeviceCache* dc = nullptr;
-    if (device >= 0 && device < 64) {
-        std::lock_guard<std::mutex> lk(g_cache[device].mu);
-        if (!g_cache[device].busy) { g_cache[device].busy = true; dc = &g_cache[device]; }
-    }
-    const int64_t n = sh.v1 - sh.v0;
-    const bool recon = job.kind == PLAN_GQI || job.kind == PLAN_DSI;
-    bool reached_rv = false;
-    const int esz = job.dtype == FIBERS_F32 ? 4 : job.dtype == FIBERS_F64 ? 8 : job.dtype == FIBERS_I32 ? 4
-                  : job.dtype == FIBERS_U8 ? 1 : 2;
-    {
-        W_CUDA(cudaSetDevice(device));
-        if (n > 0) {
-            if (dc && dc->plan && dc->plan_key == job.plan_key && job.plan_key != 0) plan = dc->plan;
-            else {
-                if (dc && dc->plan) { plan_free(dc->plan); dc->plan = nullptr; }
-                code = job.make_plan(&plan, device);
-                if (code) { err = g_err; goto done; }
-                if (dc) { dc->plan = plan; dc->plan_key = job.plan_key; }
-            }
-            if (fused) {
-                if (dc && dc->plan2 && dc->plan2_key == job.plan2_key && job.plan2_key != 0) plan2 = dc->plan2;
-                else {
-                    if (dc && dc->plan2) { plan_free(dc->plan2); dc->plan2 = nullptr; }
-                    code = job.make_plan2(&plan2, device);
-                    if (code) { err = g_err; goto done; }
-                    if (dc) { dc->plan2 = plan2; dc->plan2_key = job.plan2_key; }
-                }
-            }
-            // per-voxel device bytes of one pipeline slot
-            int out_frames = 0;
-            for (auto& o : job.out_f32) out_frames += o.second;
-            for (auto& o : job.out2_f32) out_frames += o.second;
-            const int64_t per_vox = (int64_t)job.nvol * 4 + (job.dtype != FIBERS_F32 ? (int64_t)job.nvol * esz : 0)
-                                  + 1 + (int64_t)out_frames * 4 + 6 + 1;
-            size_t free_b = 0, total_b = 0;
-            W_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            int64_t chunk_max = 1 << 18;
-            if (const char* cv = getenv("FIBERS_CUDA_CHUNK_VOXELS")) { long v = atol(cv); if (v >= 4096) chunk_max = v; }
-            int64_t chunk = std::min<int64_t>(n, chunk_max);
-            while (chunk > 4096 && (double)chunk * per_vox * NSLOT > 0.6 * (double)free_b) chunk /= 2;
-            chunk = (chunk + 63) / 64 * 64;
-            const int64_t cp = chunk;                  // device pitch (elements) inside a slot
-            const size_t slab_need = (size_t)(per_vox * cp + 1024);
-            if (dc) {
-                for (int s = 0; s < NSLOT; ++s) if (!dc->st[s]) W_CUDA(cudaStreamCreateWithFlags(&dc->st[s], cudaStreamNonBlocking));
-                if (dc->slab_bytes < slab_need) {
-                    for (int s = 0; s < NSLOT; ++s) { if (dc->slab[s]) cudaFree(dc->slab[s]); dc->slab[s] = nullptr; }
-                    dc->slab_bytes = 0;
-                    for (int s = 0; s < NSLOT; ++s) W_CUDA(cudaMalloc(&dc->slab[s], slab_need));
-                    dc->slab_bytes = slab_need;
-                }
-                for (int s = 0; s < NSLOT; ++s) { st[s] = dc->st[s]; slab[s] = dc->slab[s]; }
-            } else {
-                for (int s = 0; s < NSLOT; ++s) {
-                    W_CUDA(cudaStreamCreateWithFlags(&st[s], cudaStreamNonBlocking));
-                    W_CUDA(cudaMalloc(&slab[s], slab_need));
-                }
-            }
-            if (recon) {
-                const size_t qa_need = sizeof(float) * 3 * (size_t)n;
-                if (dc) {
-                    if (dc->qa_bytes < qa_need) { if (dc->qa) cudaFree(dc->qa); dc->qa = nullptr; dc->qa_bytes = 0;
-                                                   W_CUDA(cudaMalloc(&dc->qa, qa_need)); dc->qa_bytes = qa_need; }
-                    if (!dc->stats) W_CUDA(cudaMalloc(&dc->stats, 2 * sizeof(int32_t)));
-                    d_qa_all = dc->qa; d_stats = dc->stats;
-                } else {
-                    W_CUDA(cudaMalloc(&d_qa_all, qa_need));
-                    W_CUDA(cudaMalloc(&d_stats, 2 * sizeof(int32_t)));
-                }
-                code = launch_stats_init(d_stats, st[0]);
-                if (code) { err = g_err; goto done; }
-                W_CUDA(cudaStreamSynchronize(st[0]));
-            }
-            int ci = 0;
-            for (int64_t c0 = 0; c0 < n; c0 += chunk, ++ci) {
-                const int s = ci % NSLOT;
-                const int64_t cn = std::min(chunk, n - c0);
-                const int64_t g0 = sh.v0 + c0;          // global voxel offset
-                char* base = slab[s];
-                // slot layout: [dwi f32 nvol*cp][raw (non-f32 input) nvol*cp*esz][outputs...][idx i16 3cp][mask cp][valid cp]
-                float* d_dwi = (float*)base; base += sizeof(float) * job.nvol * cp;
-                char* d_raw = nullptr;
-                if (job.dtype != FIBERS_F32) { d_raw = base; base += (size_t)esz * job.nvol * cp; base = (char*)(((uintptr_t)base + 255) & ~(uintptr_t)255); }
-                std::vector<float*> d_out;
-                for (auto& o : job.out_f32) { d_out.push_back((float*)base); base += sizeof(float) * o.second * cp; }
-                std::vector<float*> d_out2;
-                for (auto& o : job.out2_f32) { d_out2.push_back((float*)base); base += sizeof(float) * o.second * cp; }
-                int16_t* d_idx = (int16_t*)base; base += 6 * cp;
-                uint8_t* d_mask = (uint8_t*)base; base += cp;
-                uint8_t* d_valid = (uint8_t*)base;
-                // H2D: every volume contributes one contiguous run of cn voxels (pitch = full volume)
-                if (job.dtype == FIBERS_F32)
-                    W_CUDA(cudaMemcpy2DAsync(d_dwi, cp * 4, (const char*)job.dwi + g0 * 4, job.nvox * 4, cn * 4, job.nvol,
-                                             cudaMemcpyHostToDevice, st[s]));
-                else {
-                    W_CUDA(cudaMemcpy2DAsync(d_raw, cp * esz, (const char*)job.dwi + g0 * esz, job.nvox * esz, cn * esz,
-                                             job.nvol, cudaMemcpyHostToDevice, st[s]));
-                    code = launch_convert(d_raw, job.dtype, d_dwi, (int64_t)job.nvol * cp, st[s]);
-                    if (code) { err = g_err; goto done; }
-                }
-                W_CUDA(cudaMemcpyAsync(d_mask, job.mask + g0, cn, cudaMemcpyHostToDevice, st[s]));
-                if (job.kind == PLAN_DTI) {
-                    code = launch_dti(plan, d_dwi, cp, d_mask, cn, cp, d_out.data(), job.valid ? d_valid : nullptr, st[s]);
-                } else if (job.kind == PLAN_ADC) {
-                    code = launch_adc(plan, d_dwi, cp, d_mask, cn, d_out[0], d_out[1], st[s]);
-                } else {
-                    ReconArgs a{};
-                    a.dwi = d_dwi; a.dwi_pitch = cp; a.mask = d_mask; a.nvox = cn; a.out_pitch = cp;
-                    int oi = 0;
-                    if (job.kind == PLAN_DSI) a.pdf = d_out[oi++];
-                    a.odf = d_out[oi++];
-                    for (int k = 0; k < 3; ++k) a.peak[k] = d_out[oi++];
-                    for (int k = 0; k < 3; ++k) a.qa[k] = d_qa_all + (size_t)k * n + c0;   // QA stays on device until odfmax is known
-                    a.peak_idx = job.peak_idx ? d_idx : nullptr; a.stats = d_stats;
-                    code = plan->kernel == FIBERS_KERNEL_TC ? launch_recon_tc(plan, a, st[s]) : launch_recon_simt(plan, a, st[s]);
-                }
-                if (code) { err = g_err; goto done; }
-                if (fused) {                              // companion DTI fit on the slab that is already resident
-                    code = launch_dti(plan2, d_dwi, cp, d_mask, cn, cp, d_out2.data(), nullptr, st[s]);
-                    if (code) { err = g_err; goto done; }
-                    for (size_t i = 0; i < job.out2_f32.size(); ++i)
-                        W_CUDA(cudaMemcpy2DAsync((char*)job.out2_f32[i].first + g0 * 4, job.nvox * 4, d_out2[i], cp * 4, cn * 4,
-                                                 job.out2_f32[i].second, cudaMemcpyDeviceToHost, st[s]));
-                }
-                // D2H gathers into the caller's arrays at the slab offset
-                for (size_t i = 0; i < job.out_f32.size(); ++i)
-                    W_CUDA(cudaMemcpy2DAsync((char*)job.out_f32[i].first + g0 * 4, job.nvox * 4, d_out[i], cp * 4, cn * 4,
-                                             job.out_f32[i].second, cudaMemcpyDeviceToHost, st[s]));
-                if (job.peak_idx)
-                    W_CUDA(cudaMemcpy2DAsync((char*)job.peak_idx + g0 * 2, job.nvox * 2, d_idx, cp * 2, cn * 2, 3,
-                                             cudaMemcpyDeviceToHost, st[s]));
-                if (job.valid)
-                    W_CUDA(cudaMemcpyAsync(job.valid + g0, d_valid, cn, cudaMemcpyDeviceToHost, st[s]));
-            }
-            for (int s = 0; s < NSLOT; ++s) W_CUDA(cudaStreamSynchronize(st[s]));
-        }
-        if (recon) {
-            // the one cross-slab datum: odfmax = max over ALL voxels of mean(odf) (src/gqi.jl:164)
-            float mine = -INFINITY;
-            if (n > 0) {
-                int32_t h[2];
-                W_CUDA(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-                mine = ord2f(h[0]);
-            }
-            reached_rv = true;
-            float odfmax = rv->wait_max(mine, true);
-            if (n > 0) {
-                code = launch_qa_scale(d_qa_all, d_qa_all + n, d_qa_all + 2 * n, n, nullptr, odfmax, st[0]);
-                if (code) { err = g_err; goto done; }
-                for (int k = 0; k < 3; ++k)
-                    W_CUDA(cudaMemcpyAsync(job.qa[k] + sh.v0, d_qa_all + (size_t)k * n, sizeof(float) * n,
-                                           cudaMemcpyDeviceToHost, st[0]));
-                W_CUDA(cudaStreamSynchronize(st[0]));
-            }
-        }
-    }
-done:
-    if (recon && !reached_rv) rv->wait_max(-INFINITY, false);
-    if (dc) {                                            // everything stays in the cache for the next call
-        if (code) for (int s = 0; s < NSLOT; ++s) if (dc->st[s]) cudaStreamSynchronize(dc->st[s]);
-        std::lock_guard<std::mutex> lk(dc->mu);
-        dc->busy = false;
-    } else {
-        for (int s = 0; s < NSLOT; ++s) { if (slab[s]) cudaFree(slab[s]); if (st[s]) cudaStreamDestroy(st[s]); }
-        if (d_qa_all) cudaFree(d_qa_all);
-        if (d_stats) cudaFree(d_stats);
-        if (plan) plan_free(plan);
-        if (plan2) plan_free(plan2);
-    }
-    *out_code = code; *out_err = err;
-}
-
-static int run_host_job(const HostJob& job, int ngpu) {
-    if (job.nvox <= 0) return fail(FIBERS_ERR_ARG, "empty volume");
-    if (!job.dwi || !job.mask) return fail(FIBERS_ERR_ARG, "dwi / mask pointer is NULL");
-    std::vector<int> devs = device_list();
-    if (devs.empty()) return fail(FIBERS_ERR_NODEV, "no CUDA device available (libfibers_cuda has no CPU fallback)");
-    if (ngpu < 1) return fail(FIBERS_ERR_ARG, "ngpu must be >= 1");
-    ngpu = std::min<int>(ngpu, (int)devs.size());
-    ngpu = std::min<int>(ngpu, job.nz);
-    std::vector<Shard> shards = partition_slabs(job.mask, job.nxny, job.nz, ngpu);
-    Rendezvous rv; rv.n = ngpu;
-    std::vector<int> codes(ngpu, 0); std::vector<std::string> errs(ngpu);
-    if (ngpu == 1) shard_worker(job, devs[0], shards[0], &rv, &codes[0], &errs[0]);
-    else {
-        std::vector<std::thread> th;
-        for (int g = 0; g < ngpu; ++g)
-            th.emplace_back(shard_worker, std::cref(job), devs[g], shards[g], &rv, &codes[g], &errs[g]);
-        for (auto& t : th) t.join();
-    }
-    for (int g = 0; g < ngpu; ++g) if (codes[g]) return fail(codes[g], errs[g]);
-    return 0;
-}
-
-}  // namespace fibers
-
 extern "C" {
 
-void fibers_cuda_release_cache(void) {
-    for (int d = 0; d < 64; ++d) {
-        DeviceCache& c = g_cache[d];
-        std::lock_guard<std::mutex> lk(c.mu);
-        if (c.busy) continue;
-        bool any = c.plan || c.plan2 || c.qa || c.stats || c.slab[0] || c.st[0];
-        if (!any) continue;
-        int cur = 0; cudaGetDevice(&cur); cudaSetDevice(d);
-        for (int s = 0; s < 3; ++s) { if (c.slab[s]) cudaFree(c.slab[s]); if (c.st[s]) cudaStreamDestroy(c.st[s]); c.slab[s] = nullptr; c.st[s] = nullptr; }
-        if (c.qa) cudaFree(c.qa); if (c.stats) cudaFree(c.stats);
-        if (c.plan) plan_free(c.plan);
-        if (c.plan2) plan_free(c.plan2);
-        c.qa = nullptr; c.stats = nullptr; c.plan = nullptr; c.plan2 = nullptr; c.slab_bytes = c.qa_bytes = 0; c.plan_key = c.plan2_key = 0;
-        cudaSetDevice(cur);
-    }
-}
+void fibers_cuda_release_cache(void) { release_host_caches(); }
 
 int fibers_host_build_matrix(int kind, int nvol, const float* bval, const float* bvec, const float* vertices,
                              int nvert2, float sigma, int hann_width, float* out, int64_t capacity, int* cvol,
@@ -683,7 +381,7 @@ int fibers_dti_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
         return fibers_dti_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval, bvec);
     };
     job.plan_key = fnv1a(fnv1a(fnv1a(1469598103934665603ull, "dti", 3), bval, sizeof(float) * nvol), bvec, sizeof(float) * 3 * nvol);
-    return run_host_job(job, ngpu);
+    return run_host_jobs({job}, ngpu);
 }
 
 int fibers_adc_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol, const float* bval,
@@ -700,21 +398,21 @@ int fibers_adc_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz
         return fibers_adc_plan_create(reinterpret_cast<fibers_plan**>(p), dev, nvol, bval);
     };
     job.plan_key = fnv1a(fnv1a(1469598103934665603ull, "adc", 3), bval, sizeof(float) * nvol);
-    return run_host_job(job, ngpu);
+    return run_host_jobs({job}, ngpu);
 }
 
-static int recon_host(int kind, const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,
-                      const float* bval, const float* bvec, const float* vertices, int nvert2, const int32_t* faces,
-                      int nface, float sigma, int hann_width, float* pdf, float* odf, float* peak1, float* peak2,
-                      float* peak3, float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu,
-                      float* const* dti_out = nullptr) {
+// Builds one subject's GQI / DSI request (optionally with the companion DTI fit of the fused entry point).
+// odf may be NULL: the ODF is still formed on the device (it feeds the peak search) but is not copied back.
+static int recon_job(HostJob& job, int kind, const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,
+                     const float* bval, const float* bvec, const float* vertices, int nvert2, const int32_t* faces,
+                     int nface, float sigma, int hann_width, float* pdf, float* odf, float* peak1, float* peak2,
+                     float* peak3, float* qa1, float* qa2, float* qa3, int16_t* peak_idx, float* const* dti_out = nullptr) {
     if (!bval || nvol <= 0) return fail(FIBERS_ERR_TABLE, "Missing b-value table from input DWI structure");
     if (!bvec) return fail(FIBERS_ERR_TABLE, "Missing gradient table from input DWI structure");
     if (nx <= 0 || ny <= 0 || nz <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions must be positive");
     if (dwi_dtype < FIBERS_F32 || dwi_dtype > FIBERS_U8) return fail(FIBERS_ERR_ARG, "unsupported dwi element type");
-    if (!odf || !peak1 || !peak2 || !peak3 || !qa1 || !qa2 || !qa3 || (kind == PLAN_DSI && !pdf))
+    if (!peak1 || !peak2 || !peak3 || !qa1 || !qa2 || !qa3 || (kind == PLAN_DSI && !pdf))
         return fail(FIBERS_ERR_ARG, "NULL output pointer");
-    HostJob job;
     job.kind = kind; job.nvol = nvol; job.dtype = dwi_dtype;
     job.nxny = (int64_t)nx * ny; job.nz = nz; job.nvox = job.nxny * nz;
     job.dwi = dwi; job.mask = mask; job.peak_idx = peak_idx;
@@ -746,15 +444,17 @@ static int recon_host(int kind, const void* dwi, int dwi_dtype, const uint8_t* m
         };
         job.plan2_key = fnv1a(fnv1a(fnv1a(1469598103934665603ull, "dti", 3), bval, sizeof(float) * nvol), bvec, sizeof(float) * 3 * nvol);
     }
-    return run_host_job(job, ngpu);
+    return 0;
 }
 
 int fibers_gqi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,
                    const float* bval, const float* bvec, const float* vertices, int nvert2, const int32_t* faces,
                    int nface, float sigma, float* odf, float* peak1, float* peak2, float* peak3, float* qa1,
                    float* qa2, float* qa3, int16_t* peak_idx, int ngpu) {
-    return recon_host(PLAN_GQI, dwi, dwi_dtype, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
-                      sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, peak_idx, ngpu);
+    HostJob job;
+    if (int rc = recon_job(job, PLAN_GQI, dwi, dwi_dtype, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
+                           sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, peak_idx)) return rc;
+    return run_host_jobs({job}, ngpu);
 }
 
 int fibers_dti_gqi_fit(const float* dwi, const uint8_t* mask, int nx, int ny, int nz, int nvol, const float* bval,
@@ -763,16 +463,47 @@ int fibers_dti_gqi_fit(const float* dwi, const uint8_t* mask, int nx, int ny, in
                        int nvert2, const int32_t* faces, int nface, float sigma, float* odf, float* peak1,
                        float* peak2, float* peak3, float* qa1, float* qa2, float* qa3, int ngpu) {
     float* const dti_out[10] = {s0, eval1, eval2, eval3, evec1, evec2, evec3, rd, md, fa};
-    return recon_host(PLAN_GQI, dwi, FIBERS_F32, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
-                      sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, nullptr, ngpu, dti_out);
+    HostJob job;
+    if (int rc = recon_job(job, PLAN_GQI, dwi, FIBERS_F32, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
+                           sigma, 0, nullptr, odf, peak1, peak2, peak3, qa1, qa2, qa3, nullptr, dti_out)) return rc;
+    return run_host_jobs({job}, ngpu);
+}
+
+int fibers_dti_gqi_fit_batch(int nsub, const float* const* dwi, const uint8_t* const* mask, int nx, int ny, int nz, int nvol,
+                             const float* bval, const float* bvec, float* const* dti_out, const float* vertices,
+                             int nvert2, const int32_t* faces, int nface, float sigma, float* const* gqi_out, int ngpu) {
+    if (nsub < 0 || (nsub > 0 && (!dwi || !mask || !gqi_out))) return fail(FIBERS_ERR_ARG, "NULL subject table");
+    std::vector<HostJob> jobs((size_t)nsub);
+    for (int i = 0; i < nsub; ++i) {
+        float* const* g = gqi_out + (size_t)i * 7;
+        if (int rc = recon_job(jobs[i], PLAN_GQI, dwi[i], FIBERS_F32, mask[i], nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces,
+                               nface, sigma, 0, nullptr, g[0], g[1], g[2], g[3], g[4], g[5], g[6], nullptr,
+                               dti_out ? dti_out + (size_t)i * 10 : nullptr)) return rc;
+    }
+    return run_host_jobs(jobs, ngpu);
 }
 
 int fibers_dsi_rec(const void* dwi, int dwi_dtype, const uint8_t* mask, int nx, int ny, int nz, int nvol,
                    const float* bval, const float* bvec, const float* vertices, int nvert2, const int32_t* faces,
                    int nface, int hann_width, float* pdf, float* odf, float* peak1, float* peak2, float* peak3,
                    float* qa1, float* qa2, float* qa3, int16_t* peak_idx, int ngpu) {
-    return recon_host(PLAN_DSI, dwi, dwi_dtype, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
-                      0.f, hann_width, pdf, odf, peak1, peak2, peak3, qa1, qa2, qa3, peak_idx, ngpu);
+    HostJob job;
+    if (int rc = recon_job(job, PLAN_DSI, dwi, dwi_dtype, mask, nx, ny, nz, nvol, bval, bvec, vertices, nvert2, faces, nface,
+                           0.f, hann_width, pdf, odf, peak1, peak2, peak3, qa1, qa2, qa3, peak_idx)) return rc;
+    return run_host_jobs({job}, ngpu);
+}
+
+int fibers_cuda_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return fail(FIBERS_ERR_ARG, "NULL pointer / zero size");
+    if (device_count_raw() <= 0) return fail(FIBERS_ERR_NODEV, "no CUDA device available (libfibers_cuda has no CPU fallback)");
+    FB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+
+int fibers_cuda_host_unregister(void* ptr) {
+    if (!ptr) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    FB_CUDA(cudaHostUnregister(ptr));
+    return 0;
 }
 
 }  // extern "C"

@@ -103,7 +103,7 @@ def dti_fit(dwi: MRI, mask: MRI, ngpu: int = 1) -> DTI:
     return DTI(*outs, valid=valid.astype(bool))
 
 
-def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int):
+def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int, want_odf: bool = True):
     _check_tables(dwi, True)
     L = _lib.lib(); _lib.require_device()
     nx, ny, nz, nvol = dwi.vol.shape
@@ -111,7 +111,7 @@ def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int):
     vol = np.asfortranarray(dwi.vol)
     code = _lib.dtype_code(vol.dtype)
     M = odf_dirs.nvert
-    odf = MRI.like(mask, M)
+    odf = MRI.like(mask, M) if want_odf else None        # odf=NULL: peaks / QA only, the ODF never crosses PCIe
     peak = [MRI.like(mask, 3) for _ in range(3)]
     qa = [MRI.like(mask, 1) for _ in range(3)]
     idx = np.zeros((nx, ny, nz, 3), np.int16, order="F")
@@ -120,7 +120,7 @@ def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int):
     F = np.asfortranarray(odf_dirs.faces, np.int32)            # Matrix{Integer} -> Matrix{Int32}
     common = (_lib.ptr(vol), code, _lib.ptr(m), nx, ny, nz, nvol, _lib.ptr(dwi.bval), _lib.ptr(bvec),
               _lib.ptr(V), V.shape[0], _lib.ptr(F), F.shape[0])
-    tail = (_lib.ptr(odf.vol), *[_lib.ptr(p.vol) for p in peak], *[_lib.ptr(q.vol) for q in qa], _lib.ptr(idx), ngpu)
+    tail = (_lib.ptr(odf.vol) if want_odf else None, *[_lib.ptr(p.vol) for p in peak], *[_lib.ptr(q.vol) for q in qa], _lib.ptr(idx), ngpu)
     if kind == "gqi":
         _lib.check(L.fibers_gqi_rec(*common, float(np.float32(param)), *tail))
         return GQI(odf, peak, qa, idx)
@@ -129,9 +129,10 @@ def _recon(kind, dwi: MRI, mask: MRI, odf_dirs: ODF, param, ngpu: int):
     return DSI(pdf, odf, peak, qa, idx)
 
 
-def gqi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1) -> GQI:
-    """Generalized q-sampling imaging reconstruction; returns a `GQI` structure."""
-    return _recon("gqi", dwi, mask, odf_dirs, sigma, ngpu)
+def gqi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1, want_odf: bool = True) -> GQI:
+    """Generalized q-sampling imaging reconstruction; returns a `GQI` structure.
+    `want_odf=False` (extension): `.odf` is None, only peaks and QA come back (what `stream` consumes)."""
+    return _recon("gqi", dwi, mask, odf_dirs, sigma, ngpu, want_odf)
 
 
 def dti_gqi_fit(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1):
@@ -159,6 +160,49 @@ def dti_gqi_fit(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, sigma: float = 
     return DTI(*douts), GQI(odf, peak, qa, None)
 
 
-def dsi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, hann_width: int = 32, ngpu: int = 1) -> DSI:
+def dsi_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_642, hann_width: int = 32, ngpu: int = 1, want_odf: bool = True) -> DSI:
     """Diffusion spectrum imaging reconstruction; returns a `DSI` structure."""
-    return _recon("dsi", dwi, mask, odf_dirs, hann_width, ngpu)
+    return _recon("dsi", dwi, mask, odf_dirs, hann_width, ngpu, want_odf)
+
+
+def dti_gqi_fit_batch(dwis, masks, odf_dirs: ODF = sphere_642, sigma: float = 1.25, ngpu: int = 1, want_dti: bool = True,
+                      want_odf: bool = True):
+    """`dti_fit` + `gqi_rec` of a batch of subjects that share one protocol and one volume shape (BASELINE cfg4) in
+    ONE library call: subjects are queued over `ngpu` devices and every device overlaps the transfers of the next
+    subject with the kernels of the current one.  Returns a list of `(DTI | None, GQI)`, bit-identical to calling
+    `dti_gqi_fit` per subject (src/dti.jl:221, src/gqi.jl:109)."""
+    import ctypes as C
+    nsub = len(dwis)
+    if nsub != len(masks):
+        raise _lib.FibersCudaError(1, "dwis and masks must have the same length")
+    if nsub == 0:
+        return []
+    for d in dwis:
+        _check_tables(d, True)
+        if d.vol.dtype != np.float32:
+            raise TypeError("dti_fit requires a Float32 DWI volume (reference method signature, src/dti.jl:286)")
+        if d.vol.shape != dwis[0].vol.shape or not np.array_equal(d.bval, dwis[0].bval) or not np.array_equal(d.bvec, dwis[0].bvec):
+            raise _lib.FibersCudaError(1, "all subjects of a batch must share the volume shape and the b-table")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwis[0].vol.shape
+    ms = [_mask_u8(m, (nx, ny, nz)) for m in masks]
+    vols = [np.asfortranarray(d.vol) for d in dwis]
+    bvec = np.asfortranarray(dwis[0].bvec, np.float32)
+    V = np.asfortranarray(odf_dirs.vertices, np.float32)
+    Fc = np.asfortranarray(odf_dirs.faces, np.int32)
+    res, dptr, gptr = [], [], []
+    for m in masks:
+        douts = [MRI.like(m, n) for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)] if want_dti else None
+        odf = MRI.like(m, odf_dirs.nvert) if want_odf else None
+        peak = [MRI.like(m, 3) for _ in range(3)]
+        qa = [MRI.like(m, 1) for _ in range(3)]
+        if want_dti:
+            dptr += [o.vol.ctypes.data for o in douts]
+        gptr += [odf.vol.ctypes.data if want_odf else None] + [p.vol.ctypes.data for p in peak] + [q.vol.ctypes.data for q in qa]
+        res.append((DTI(*douts) if want_dti else None, GQI(odf, peak, qa, None)))
+    parr = lambda xs: (C.c_void_p * len(xs))(*xs)
+    _lib.check(L.fibers_dti_gqi_fit_batch(nsub, parr([v.ctypes.data for v in vols]), parr([m.ctypes.data for m in ms]),
+                                          nx, ny, nz, nvol, _lib.ptr(dwis[0].bval), _lib.ptr(bvec),
+                                          parr(dptr) if want_dti else None, _lib.ptr(V), V.shape[0], _lib.ptr(Fc), Fc.shape[0],
+                                          float(np.float32(sigma)), parr(gptr), ngpu))
+    return res

@@ -28,10 +28,21 @@
  *    FIBERS_ERR_NODEV.
  *  - ngpu: number of GPUs to shard z-slabs over (>=1; clipped to the configured device list).
  *    No inter-GPU collective is used; the host gathers slabs and reduces the one scalar (odfmax).
+ *  - Host memory: arrays in PINNED / registered memory (cudaHostAlloc, cudaHostRegister,
+ *    fibers_cuda_host_register) are copied by DMA straight from / into the caller's buffers.  Arrays in
+ *    ordinary PAGEABLE memory (what a Julia `Array` is, src/mri.jl:249-255) are accepted as they are and go
+ *    through an internal pinned bounce ring filled / emptied by a few host copy threads; the choice is made per
+ *    call from cudaPointerGetAttributes (override: env FIBERS_CUDA_HOST_PATH=direct|bounce;
+ *    FIBERS_CUDA_COPY_THREADS, default 8 per GPU).  The worker and copy threads of a GPU are bound to the CPUs
+ *    local to it (FIBERS_CUDA_AFFINITY=0 disables).
+ *  - gqi_rec / dsi_rec / dti_gqi_fit: `odf` may be NULL when the caller only needs peaks and QA (the only
+ *    downstream consumer, stream(), reads nothing else: src/stream.jl:76-173); the ODF is then formed on the
+ *    device for the peak search but never crosses PCIe (4.7 of the 4.9 GB a HCP-shaped subject returns).
  */
 #ifndef FIBERS_CUDA_H
 #define FIBERS_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -118,6 +129,25 @@ int fibers_dti_gqi_fit(const float* dwi, const uint8_t* mask, int nx, int ny, in
                        const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma,
                        float* odf, float* peak1, float* peak2, float* peak3,
                        float* qa1, float* qa2, float* qa3, int ngpu);
+
+/* cfg4-style batch: dti_fit + gqi_rec (src/dti.jl:221, src/gqi.jl:109) of `nsub` subjects that share one
+ * protocol and one volume shape, in one call.  dwi[i], mask[i]: subject i's arrays; dti_out: nsub x 10 pointers
+ * (s0, eval1-3, evec1-3, rd, md, fa per subject; the whole table may be NULL = GQI only); gqi_out: nsub x 7
+ * pointers (odf, peak1-3, qa1-3 per subject; an odf entry may be NULL).  Subjects are handed to the `ngpu`
+ * devices from an ordered queue; each device keeps its stream ring rolling across subject boundaries, so the H2D
+ * of subject i+1 overlaps the kernels and the D2H of subject i, and the plans are built once per device.  With
+ * fewer subjects than GPUs every subject is also split into z-slabs.  Results are bit-identical to nsub calls
+ * of fibers_dti_gqi_fit. */
+int fibers_dti_gqi_fit_batch(int nsub, const float* const* dwi, const uint8_t* const* mask,
+                             int nx, int ny, int nz, int nvol, const float* bval, const float* bvec,
+                             float* const* dti_out,
+                             const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma,
+                             float* const* gqi_out, int ngpu);
+
+/* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
+ * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
+int fibers_cuda_host_register(void* ptr, size_t bytes);
+int fibers_cuda_host_unregister(void* ptr);
 
 /* ---- device-resident entry points (kernel-only timing, slab pipelines, batch drivers) ---
  * A plan holds the per-protocol constants on ONE device (reconstruction matrix, neighbour

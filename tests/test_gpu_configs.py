@@ -68,7 +68,7 @@ def _check_dti(got, ph, what, min_partial_frac=0.0, valid=None):
             e_gpu = np.abs(P.flat(getattr(got, name).vol)[sel].astype(np.float64) - ref) / scale
             e_ref = np.abs(P.flat(r32[name])[sel].astype(np.float64) - ref) / scale
             ill = e_ref > 0.5 * P.SCALAR_TOL
-            if branch == "full":
+            if branch == "full" and name in ("s0", "eigval1", "md", "fa"):   # (lambda2/3 of nearly degenerate tensors are ill-conditioned in fp32)
                 assert not ill.any(), f"{what}: fp32 reference arithmetic off by > 0.5e-4 on the full branch ({name})"
             exempt |= ill
             bad = (e_gpu >= P.SCALAR_TOL) & ~ill

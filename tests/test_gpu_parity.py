@@ -372,3 +372,85 @@ def test_two_live_plans_with_different_spheres_interleaved_and_concurrent(F):
         del plans
     finally:
         F.device.set_kernel("auto")
+
+
+def _same_recon(a, b, odf=True):
+    if odf:
+        assert np.array_equal(a.odf.vol, b.odf.vol)
+    for k in range(3):
+        assert np.array_equal(a.peak[k].vol, b.peak[k].vol) and np.array_equal(a.qa[k].vol, b.qa[k].vol, equal_nan=True)
+
+
+def test_pageable_bounce_ring_equals_direct_copies(F, sphere642, monkeypatch):
+    """Host transfer paths: the pinned bounce ring (what pageable caller arrays get) and the direct pitched DMA
+    give the same bits; several chunks per slot so that the ring wraps, all four entry points, non-float input."""
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((26, 22, 14), seed=61, mask_fill=0.6)     # 8008 voxels
+    pd = phantom.dsi_phantom((14, 12, 7), seed=62, mask_fill=0.8)
+    pd["dwi"] = np.asfortranarray(np.round(pd["dwi"]).astype(np.int16))
+    monkeypatch.setenv("FIBERS_CUDA_CHUNK_VOXELS", "4096")
+    res = {}
+    for path in ("direct", "bounce"):
+        monkeypatch.setenv("FIBERS_CUDA_HOST_PATH", path)
+        F._lib.lib().fibers_cuda_release_cache()
+        res[path] = (F.gqi_rec(*_mri(F, ph)), F.dti_fit(*_mri(F, ph)), F.adc_fit(*_mri(F, ph)), F.dsi_rec(*_mri(F, pd)),
+                     F.dti_gqi_fit(*_mri(F, ph)))
+    F._lib.lib().fibers_cuda_release_cache()
+    g0, d0, a0, s0, f0 = res["direct"]; g1, d1, a1, s1, f1 = res["bounce"]
+    _same_recon(g0, g1); assert np.array_equal(g0.peak_idx, g1.peak_idx)
+    _same_recon(s0, s1); assert np.array_equal(s0.pdf.vol, s1.pdf.vol) and np.array_equal(s0.peak_idx, s1.peak_idx)
+    for name in ("s0", "eigval1", "eigvec1", "eigvec3", "rd", "md", "fa"):
+        assert np.array_equal(getattr(d0, name).vol, getattr(d1, name).vol, equal_nan=True), name
+        assert np.array_equal(getattr(f0[0], name).vol, getattr(f1[0], name).vol, equal_nan=True), name
+    assert np.array_equal(d0.valid, d1.valid)
+    assert np.array_equal(a0[0].vol, a1[0].vol) and np.array_equal(a0[1].vol, a1[1].vol)
+    _same_recon(f0[1], f1[1])
+    # and against the oracle, so that "both paths agree" cannot mean "both are wrong"
+    v, f = sphere642
+    r64 = O.gqi_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, f, 1.25, np.float64)
+    _check_recon(g1, None, r64, v, f, 321, "gqi through the bounce ring")
+
+
+def test_pinned_caller_buffers_take_the_direct_path(F, sphere642):
+    """Caller arrays registered with fibers_cuda_host_register (what bench.py's e2e leg passes) and odf = NULL."""
+    from fibers_jl_b200 import phantom, _lib
+    ph = phantom.gqi_phantom((20, 18, 10), seed=63, mask_fill=0.7)
+    ref = F.gqi_rec(*_mri(F, ph))
+    L = _lib.lib()
+    dwi = np.asfortranarray(ph["dwi"])
+    _lib.check(L.fibers_cuda_host_register(_lib.ptr(dwi), dwi.nbytes))
+    try:
+        got = F.gqi_rec(F.MRI(dwi, ph["bval"], ph["bvec"]), F.MRI(ph["mask"]))
+        _same_recon(ref, got)
+        noodf = F.gqi_rec(F.MRI(dwi, ph["bval"], ph["bvec"]), F.MRI(ph["mask"]), want_odf=False)
+        assert noodf.odf is None
+        _same_recon(ref, noodf, odf=False)
+        assert np.array_equal(ref.peak_idx, noodf.peak_idx)
+    finally:
+        _lib.check(L.fibers_cuda_host_unregister(_lib.ptr(dwi)))
+
+
+def test_batch_of_subjects_equals_single_calls(F, monkeypatch):
+    """fibers_dti_gqi_fit_batch (BASELINE cfg4 shape of work: DTI + GQI per subject, one protocol): the stream ring
+    keeps rolling across subject boundaries; results must be bit-identical to one fused call per subject.
+    Runs on every visible GPU count up to 4 (1 on the single-GPU box; gpurun --gpus 2/4 covers the queue)."""
+    from fibers_jl_b200 import phantom
+    monkeypatch.setenv("FIBERS_CUDA_CHUNK_VOXELS", "4096")
+    phs = [phantom.gqi_phantom((22, 18, 11), seed=70 + i, mask_fill=0.5 + 0.1 * i) for i in range(5)]
+    single = [F.dti_gqi_fit(*_mri(F, ph)) for ph in phs]
+    ngpus = [n for n in (1, 2, 4) if n <= F.device_count()]
+    F.device.set_devices(list(range(max(ngpus))))
+    try:
+        for ngpu in ngpus:
+            for nsub in (5, 1):         # more subjects than GPUs (queue) / fewer (z-slab split with the host-side odfmax reduce)
+                got = F.dti_gqi_fit_batch([_mri(F, ph)[0] for ph in phs[:nsub]], [_mri(F, ph)[1] for ph in phs[:nsub]], ngpu=ngpu)
+                for (d1, g1), (d2, g2) in zip(single, got):
+                    _same_recon(g1, g2)
+                    for name in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "eigvec2", "eigvec3", "rd", "md", "fa"):
+                        assert np.array_equal(getattr(d1, name).vol, getattr(d2, name).vol, equal_nan=True), (ngpu, nsub, name)
+        g_only = F.dti_gqi_fit_batch([_mri(F, ph)[0] for ph in phs[:2]], [_mri(F, ph)[1] for ph in phs[:2]], want_dti=False, want_odf=False)
+        for (d1, g1), (d2, g2) in zip(single, g_only):
+            assert d2 is None and g2.odf is None
+            _same_recon(g1, g2, odf=False)
+    finally:
+        F.device.set_devices([0])
