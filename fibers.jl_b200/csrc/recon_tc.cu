@@ -48,11 +48,13 @@ namespace {
 
 constexpr int N_EPI = 12;            // epilogue warps: 3 groups of 4 (one warp per TMEM lane quarter); group k also writes peak k
 constexpr int N_CONV = 4;            // converter warps (multiple of 4)
-constexpr int W_MMA = 1, W_CONV0 = 2, W_EPI0 = W_CONV0 + N_CONV;
+constexpr int W_MMA = 1, W_DWI = 2, W_CONV0 = 3, W_EPI0 = W_CONV0 + N_CONV;   // (every group of 4 consecutive warps covers the 4 TMEM lane quarters: quarter = warp & 3)
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
 constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
-constexpr int NSTAGE = 3;            // B ring: K32 chunks (two K16 sub-tiles each); 2 when shared memory is short (M > 335)
-constexpr int DSTAGE = 3;            // raw DWI ring of the converters: K32 chunks of 128 voxels (16 KB each)
+constexpr int NSTAGE = 4;            // B ring, K16 sub-tiles (hi rows + lo rows); fewer when shared memory is short (M > 335)
+constexpr int DSTAGE = 3;            // cp.async mode: raw DWI ring of the converters, K32 chunks of 128 voxels (16 KB each)
+constexpr int TSTAGE = 4;            // TMA mode: raw DWI ring, K16 boxes of 128 voxels (8 KB each), filled by the DWI producer warp
+constexpr int OBOX_BYTES = 16 * 128 * 4;   // TMA mode: ODF staging box = 16 vertex rows x 128 voxels fp32, one TMA store each
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
 constexpr int VOX_CTA = 128;
@@ -61,7 +63,7 @@ static_assert(N_EPI == 12, "the output stage maps warp group k to peak k");
 constexpr float FP16_TARGET = 8192.f;   // the sampled maximum is scaled to <= 8192 (8x headroom to 65504)
 
 constexpr int KEY_ROW = VOX_CTA * 2;    // bytes per vertex row of the key tile
-constexpr int CAND_CAP = 2048;          // listed (voxel, vertex) pairs per 128-voxel tile; overflow -> SIMT fix-up
+constexpr int CAND_CAP = 1024;          // listed (voxel, vertex) pairs per 128-voxel tile (typically ~170); overflow -> SIMT fix-up
 constexpr float KEY_WINDOW = 8.f;       // keys cover [0, 8 x mean(ODF of the voxel)) in 32767 steps (bit 15 is always set)
 
 // Folded-mesh neighbour table as a KERNEL PARAMETER (constant bank 0, private to the launch): byte offsets
@@ -84,6 +86,7 @@ struct TcParams {
     const int* tile_list; const int* tile_count;   // tiles that contain at least one mask voxel (built by tile_scan_kernel)
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
     int nstage;                  // depth of the B ring (<= NSTAGE)
+    int obuf;                    // TMA mode: ODF staging boxes per column part (1 or 2)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // DWI staging copies: 2 = 16 bytes (base 16-byte aligned, pitch % 4 == 0), 1 = 8 bytes, 0 = 4 bytes
@@ -100,7 +103,9 @@ struct TcPass {
     int rows = 0, row0 = 0;      // matrix rows [row0, row0 + rows) of the plan's matrix
     int Npad = 0, N1 = 0, N2 = 0;
     int plain = 0;               // 1: pdf rows
-    int nstage = NSTAGE;         // B ring depth that fits in shared memory for this pass
+    int nstage = NSTAGE;         // B ring depth that fits in shared memory for this pass (TMA mode)
+    int obuf = 2;                // ODF staging boxes per column part (TMA mode)
+    int nstage_ca = NSTAGE;      // the same for the cp.async mode (its DWI ring is larger, it has no ODF staging)
 };
 
 struct TcState {
@@ -108,7 +113,7 @@ struct TcState {
     void* encode = nullptr;      // cuTensorMapEncodeTiled
     int Kpad = 0, nbw = 8;
     NbrOffTable nbr_off;                     // [M + 8][NBR_W] byte offsets (rows >= M: sentinel); passed by value with every launch
-    size_t smem = 0;
+    size_t smem = 0, smem_ca = 0;  // dynamic shared memory of the TMA / cp.async instantiation
     int* d_scratch = nullptr;    // [0] maxbits, [1] fix_count, [2..] fix list
     int64_t scratch_cap = 0;
 };
@@ -273,8 +278,14 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
     return pred != 0;
 }
 
+// kTma: the DWI slab arrives by TMA (K16 x 128-voxel boxes, issued by the DWI producer warp) and the ODF tile leaves by
+// TMA stores from a small staging ring, so that the accumulator drain is not paced by the SM's 32 B/clk store port
+// (tools/store_probe.cu: 172 KB of ODF per tile = 5.4 k cycles of that port); needs 16-byte aligned slab / output
+// rows.  !kTma: cp.async staging + direct stores (any alignment).
+template <bool kTma>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ NbrOffTable nbt) {
+recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ NbrOffTable nbt,
+                const __grid_constant__ CUtensorMap tmapD, const __grid_constant__ CUtensorMap tmapO) {
     const uint32_t* const c_nbr_off = nbt.off;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the warp index is rebuilt from warp votes so that the compiler can prove it warp-uniform (uniform registers,
@@ -286,10 +297,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     const uint32_t rank = cluster_rank();
     const int cluster_id = blockIdx.x >> 1, ncluster = gridDim.x >> 1;
     const int Nh = (p.N1 + p.N2) >> 1, N1h = p.N1 >> 1;
-    const uint32_t sub_bytes = (uint32_t)(2 * Nh * 32);          // one K16 sub-tile: hi rows then lo rows (SWIZZLE_32B)
-    const uint32_t stage_bytes = 2 * sub_bytes;                  // K32 stage
-    const int nk32 = p.Kpad >> 5;
-    const uint32_t stage_rows = stage_bytes >> 9;                // 512-byte rows of the pre-tiled global image
+    const uint32_t sub_bytes = (uint32_t)(2 * Nh * 32);          // one K16 sub-tile = one B stage: hi rows then lo rows (SWIZZLE_32B)
+    const int nk32 = p.Kpad >> 5, nk16 = p.Kpad >> 4;
+    const uint32_t stage_rows = sub_bytes >> 9;                  // 512-byte rows of the pre-tiled global image per stage
     const int ntl = min(*p.tile_count, p.ntiles);      // non-empty tiles; every role walks the same list
     const bool ident = ntl == p.ntiles;                // nothing skipped: the list is the identity
 
@@ -300,25 +310,29 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     //  array holds for the dynamic window; a misaligned base would corrupt the swizzled tiles: trap.
     uint8_t* base = smem_raw;
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
-    uint8_t* sB = base;                                                   // NSTAGE * stage_bytes
-    uint16_t* keys = (uint16_t*)(sB + p.nstage * stage_bytes);              // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
+    uint8_t* sB = base;                                                   // nstage * sub_bytes
+    uint16_t* keys = (uint16_t*)(sB + p.nstage * sub_bytes);                // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
     const int Mk = p.plain ? 0 : p.M;                                     // plain passes stage no keys
     unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [3][128] best (value, ~index) per voxel
     uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
     float* s_min = (float*)(s_cand + CAND_CAP);                           // [N_CPART][128]
     float* s_mean = s_min + N_CPART * VOX_CTA;                            // [128] mean ODF per voxel (from the extra matrix row)
-    float* s_dwi = s_mean + VOX_CTA;                             // [DSTAGE][32][128] raw samples (converters)
-    uint4* s_nbr = (uint4*)(s_dwi + DSTAGE * 32 * VOX_CTA);               // [M] 8 x uint16 neighbour ids per vertex
+    // raw DWI ring (128-byte aligned: TMA destination), then (TMA mode) the ODF staging boxes
+    float* s_dwi = (float*)(((uintptr_t)(s_mean + VOX_CTA) + 127) & ~(uintptr_t)127);   // cp.async: [DSTAGE][32][128]; TMA: [TSTAGE][16][128]
+    uint8_t* s_obox = (uint8_t*)(s_dwi + (kTma ? TSTAGE * 16 : DSTAGE * 32) * VOX_CTA);   // [N_CPART][obuf][16][128] fp32
+    uint4* s_nbr = (uint4*)(s_obox + (kTma ? (size_t)N_CPART * p.obuf * OBOX_BYTES : 0));  // [M] 8 x uint16 neighbour ids per vertex
     float* s_vert = (float*)(s_nbr + Mk);                                 // [M][3] first-half vertices (peak vectors); padded to 4 floats
     uint64_t* bars = (uint64_t*)(s_vert + ((3 * Mk + 3) & ~3));
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
-    uint32_t* s_ncand = (uint32_t*)(d_empty + 1);
+    uint64_t* w_full = d_empty + 1, *w_empty = w_full + TSTAGE;           // DWI ring (TMA mode)
+    uint32_t* s_ncand = (uint32_t*)(w_empty + TSTAGE);
     uint32_t* tmem_ptr_s = s_ncand + 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < ASLOT; ++i) { mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1); }   // 4 converter warps x 2 CTAs
+        for (int i = 0; i < TSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], N_CONV); }
         mbar_init(d_full, 1); mbar_init(d_empty, 2 * N_EPI);                                      // epilogue warps x 2 CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -359,14 +373,14 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             TRACE(13);
-            for (int c = 0; c < nk32; ++c, ++g) {
+            for (int c = 0; c < nk16; ++c, ++g) {
                 const int s = g % p.nstage; const uint32_t use = g / p.nstage;
                 mbar_wait<200>(&b_empty[s], (use & 1) ^ 1);
                 if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&b_full[s], 2 * stage_bytes);       // both CTAs' bytes land on the leader's barrier
+                    if (rank == 0) mbar_expect_tx(&b_full[s], 2 * sub_bytes);         // both CTAs' bytes land on the leader's barrier
                     // one bulk tensor copy per stage: the global image is already in shared-memory order
                     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(smem_u32(sB + s * stage_bytes)), "l"(&tmapB), "r"(0), "r"((int)((rank * nk32 + c) * stage_rows)),
+                                 ::"r"(smem_u32(sB + s * sub_bytes)), "l"(&tmapB), "r"(0), "r"((int)((rank * nk16 + c) * stage_rows)),
                                    "r"(full0 + s * 8) : "memory");
                 }
                 __syncwarp();
@@ -383,22 +397,23 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 mbar_wait<100>(d_empty, (it & 1) ^ 1);              // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 TRACE(0);
+                uint32_t g16 = 2 * g32;
                 for (int c = 0; c < nk32; ++c, ++g32) {
-                    const int s = g32 % p.nstage;
                     const int slot = g32 % ASLOT;
-                    long long t0 = p.trace ? clock64() : 0;
-                    mbar_wait(&b_full[s], (g32 / p.nstage) & 1);
                     long long t1 = p.trace ? clock64() : 0;
                     mbar_wait(&a_full[slot], (g32 / ASLOT) & 1);
-                    if (p.trace) { long long t2 = clock64(); TRACE_ADD(15, t1 - t0); TRACE_ADD(16, t2 - t1); }
-                    tc_fence_after();
+                    if (p.trace) { long long t2 = clock64(); TRACE_ADD(16, t2 - t1); }
                     const uint32_t a_base = tmem_base + TMEM_A_COL + slot * 32;
-                    const uint32_t bs = smem_u32(sB + s * stage_bytes);
-                    if (elect_one()) {
 #pragma unroll
-                        for (int sub = 0; sub < 2; ++sub) {
+                    for (int sub = 0; sub < 2; ++sub, ++g16) {
+                        const int s = g16 % p.nstage;
+                        long long t0 = p.trace ? clock64() : 0;
+                        mbar_wait(&b_full[s], (g16 / p.nstage) & 1);
+                        if (p.trace) { long long t3 = clock64(); TRACE_ADD(15, t3 - t0); }
+                        tc_fence_after();
+                        const uint32_t b0 = smem_u32(sB + s * sub_bytes);
+                        if (elect_one()) {
                             const uint32_t a_hi = a_base + sub * 8, a_lo = a_hi + 16;
-                            const uint32_t b0 = bs + sub * sub_bytes;
                             const uint32_t acc = (c | sub) ? 1u : 0u;
                             const uint64_t bhi1 = make_sdesc_sw32(b0), blo1 = make_sdesc_sw32(b0 + Nh * 32);
                             mma_ts2(tmem_base, a_lo, bhi1, idesc1, acc);       // small terms first
@@ -410,14 +425,36 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                                 mma_ts2(tmem_base + p.N1, a_hi, blo2, idesc2, 1u);
                                 mma_ts2(tmem_base + p.N1, a_hi, bhi2, idesc2, 1u);
                             }
+                            mma_commit2(&b_empty[s]);                      // B stage reusable once these MMAs retire
+                            if (sub == 1) {
+                                mma_commit2(&a_empty[slot]);               // ... and the A slot after its second half
+                                if (c == nk32 - 1) mma_commit2(d_full);
+                            }
                         }
-                        mma_commit2(&b_empty[s]);                          // B stage and A slot reusable once these MMAs retire
-                        mma_commit2(&a_empty[slot]);
-                        if (c == nk32 - 1) mma_commit2(d_full);
+                        __syncwarp();
+                    }
+                }
+                TRACE(1);
+            }
+        }
+    } else if (warp == W_DWI) {
+        // ===== DWI producer (TMA mode): one K16 x 128-voxel box of the raw slab per stage, TSTAGE stages ahead of the
+        //       converters across tile boundaries.  Voxels past the end of the slab and volumes past K arrive as zeros. ====
+        if (kTma) {
+            uint32_t g = 0;
+            for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster) {
+                const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
+                const int vox0 = tile * 256 + (int)rank * VOX_CTA;
+                for (int c = 0; c < nk16; ++c, ++g) {
+                    const int s = g % TSTAGE;
+                    mbar_wait<200>(&w_empty[s], ((g / TSTAGE) & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&w_full[s], 16 * VOX_CTA * 4);
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                     ::"r"(smem_u32(s_dwi + s * 16 * VOX_CTA)), "l"(&tmapD), "r"(vox0), "r"(c * 16), "r"(smem_u32(&w_full[s])) : "memory");
                     }
                     __syncwarp();
                 }
-                TRACE(1);
             }
         }
     } else if (warp < W_EPI0) {
@@ -489,8 +526,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             asm volatile("cp.async.commit_group;" ::: "memory");         // (an empty group keeps the group count in step)
             ++p_g;
         };
+        if (!kTma) {
 #pragma unroll 1
-        for (int i = 0; i < PF; ++i) prefetch();
+            for (int i = 0; i < PF; ++i) prefetch();
+        }
         uint32_t it = 0, g32 = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
@@ -499,13 +538,25 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             if (warp == W_CONV0) TRACE(9);
 #pragma unroll 1
             for (int c = 0; c < nk32; ++c, ++g32) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");   // this thread's copies of chunk g32 have landed
-                named_bar(2, N_CONV * 32);                              // ... everybody's have; chunk g32 - 1 is no longer read
-                prefetch();                                             // refills the stage chunk g32 - 1 used
-                const uint32_t sbase = sd0 + (g32 % DSTAGE) * STAGE_B + vl * 4;
                 float x[32];
+                if (kTma) {
+                    // two K16 boxes of the DWI ring per A slot; the stage goes back to the producer once this warp has its values
 #pragma unroll
-                for (int j = 0; j < 32; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(sbase + j * (VOX_CTA * 4)));
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t g16 = 2 * g32 + h; const int s = g16 % TSTAGE;
+                        mbar_wait<20>(&w_full[s], (g16 / TSTAGE) & 1);
+                        const uint32_t sbase = sd0 + s * (16 * VOX_CTA * 4) + vl * 4;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[16 * h + j]) : "r"(sbase + j * (VOX_CTA * 4)));
+                    }
+                } else {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");   // this thread's copies of chunk g32 have landed
+                    named_bar(2, N_CONV * 32);                              // ... everybody's have; chunk g32 - 1 is no longer read
+                    prefetch();                                             // refills the stage chunk g32 - 1 used
+                    const uint32_t sbase = sd0 + (g32 % DSTAGE) * STAGE_B + vl * 4;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[j]) : "r"(sbase + j * (VOX_CTA * 4)));
+                }
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -516,6 +567,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
                     hi[j] = *reinterpret_cast<const uint32_t*>(&h);
                     lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                if (kTma) {                                             // (the conversions above consumed every x[]: the loads have completed)
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[(2 * g32) % TSTAGE])) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[(2 * g32 + 1) % TSTAGE])) : "memory");
+                    }
                 }
                 const int slot = g32 % ASLOT;
                 if (warp == W_CONV0 && c == 0) TRACE(10);
@@ -531,7 +589,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             }
             if (warp == W_CONV0) TRACE(12);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!kTma) asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         // ===== epilogue ==========================================================================
         // phase 1 roles: warp quarter q owns TMEM lanes 32q..32q+31, `cpart` selects the column range
@@ -544,6 +602,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         const int M = p.M;
         const int cper = ((p.Npad + N_CPART - 1) / N_CPART + 15) & ~15;
         const int c_begin = cpart * cper, c_end = min(min(c_begin + cper, p.Npad), (M + 15) & ~15);
+        // TMA mode: this warp's ODF staging boxes ([16 rows][32 voxels] fp32 each) and its running box counter
+        constexpr uint32_t WBOX = 16 * 32 * 4;
+        const uint32_t obox0 = smem_u32(s_obox) + (uint32_t)(ew * p.obuf) * WBOX;
+        uint32_t oc = 0;
         uint32_t it = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
@@ -615,16 +677,63 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     }
                     gp += 16 * pitch; kp += 16 * VOX_CTA;
                 };
+                // TMA mode: the 16 x 32 values of a chunk go to this warp's staging box and leave with ONE bulk tensor store
+                // (rows >= M and voxels >= nvox are clipped by the tensor map); the box is reused two chunks later, once the
+                // TMA unit has read it.  The drain then runs at TMEM / issue speed instead of the store port's.
+                const int vcoord = (int)vox0 + q * 32;
+                auto process_tma = [&](const uint32_t (&r)[16], int c0) {
+                    const int nrow = min(16, M - c0);                   // warp-uniform
+                    const uint32_t bx = obox0 + (oc % (uint32_t)p.obuf) * WBOX + lane * 4;
+                    if (lane == 0) {
+                        if (p.obuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    __syncwarp();
+                    if (plain) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(__uint_as_float(r[j]) * scl) : "memory");
+                    } else if (nrow == 16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float val = __uint_as_float(r[j]) * scl;
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
+                            const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                            kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                            mn = fminf(mn, val);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float val = __uint_as_float(r[j]) * scl;
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
+                            if (j < nrow) {
+                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                                mn = fminf(mn, val);
+                            }
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmapO), "r"(vcoord), "r"(c0), "r"(bx) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    kp += 16 * VOX_CTA; ++oc;
+                };
+                auto step = [&](const uint32_t (&r)[16], int c0) { if (kTma) process_tma(r, c0); else process(r, c0); };
                 uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
                 if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                     tmem_wait_ld();
                     if (c0 + 16 < c_end) tmem_ld16(lane_addr + c0 + 16, rb);
-                    process(ra, c0);
+                    step(ra, c0);
                     if (c0 + 16 < c_end) {
                         tmem_wait_ld();
                         if (c0 + 32 < c_end) tmem_ld16(lane_addr + c0 + 32, ra);
-                        process(rb, c0 + 16);
+                        step(rb, c0 + 16);
                     }
                 }
             }
@@ -728,6 +837,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     }
                 }
             }
+            if (kTma && lane == 0) {                                    // the settle step re-reads this tile's ODF values (L2)
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             named_bar(1, EPI_THREADS);
             if (warp == W_EPI0) TRACE(5);
             // ---- phase 3: settle the listed pairs on the exact fp32 values (this CTA wrote them a moment ago: L2 hits).
@@ -820,6 +933,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     }
 
     // ---- teardown --------------------------------------------------------------------------
+    if (kTma && warp >= W_EPI0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes still being read
     if (p.trace && warp == W_EPI0 && lane == 0 && rank == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[16 * 32 + 2 * cluster_id + 1] = (long long)t;
@@ -833,17 +947,20 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-size_t tc_smem_bytes(int M, int Nh, int nstage) {
-    size_t b = (size_t)nstage * 4 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + (size_t)CAND_CAP * 4 + (size_t)M * 16 + (size_t)M * 12 + 16 + 3 * VOX_CTA * 8 +
-               (N_CPART + 1) * VOX_CTA * 4 + (size_t)DSTAGE * 32 * VOX_CTA * 4 + (2 * NSTAGE + 2 * ASLOT + 2) * 8 + 16;
+// dynamic shared memory of one instantiation (carve-up of recon_tc_kernel; M = 0 for plain passes)
+size_t tc_smem_bytes(bool tma, int M, int Nh, int nstage, int obuf) {
+    size_t b = (size_t)nstage * 2 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + 3 * VOX_CTA * 8 + (size_t)CAND_CAP * 4 + (N_CPART + 1) * VOX_CTA * 4;
+    b = (b + 127) & ~(size_t)127;
+    b += tma ? (size_t)TSTAGE * 16 * VOX_CTA * 4 + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
+    b += (size_t)M * 16 + (size_t)((3 * M + 3) & ~3) * 4 + (2 * NSTAGE + 2 * ASLOT + 2 + 2 * TSTAGE) * 8 + 16;
     return b + 1024 + 64;
 }
 
 // The dynamic shared-memory limit is an attribute of (function, device), shared by all plans: it is only ever
 // raised (a plan with a smaller tile must not lower it under a live plan with a larger one).
 std::mutex g_smem_mu;
-size_t g_smem_limit[64] = {};
-int raise_smem_limit(int device, size_t smem);
+size_t g_smem_limit[2][64] = {};
+int raise_smem_limit(int device, bool tma, size_t smem);
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -889,7 +1006,7 @@ int tc_plan_init(Plan* p) {
     // passes: ODF rows, then (DSI) the pdf rows in blocks of <= 336
     std::vector<std::pair<int, int>> ranges = {{0, M}};
     if (p->kind == PLAN_DSI) for (int r0 = 0; r0 < K; r0 += 336) ranges.push_back({M + r0, std::min(336, K - r0)});
-    size_t smem = 0;
+    size_t smem = 0, smem_ca = 0;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess) dev_smem = 0;
     for (size_t i = 0; i < ranges.size(); ++i) {
@@ -898,9 +1015,15 @@ int tc_plan_init(Plan* p) {
         const int img_rows_n = ps.rows + (ps.plain ? 0 : 1);          // ODF pass: one extra row = mean of the ODF rows
         split_dims(img_rows_n, ps.Npad, ps.N1, ps.N2);
         const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
-        ps.nstage = NSTAGE;                                            // the deepest B ring that fits beside the key tile
-        while (ps.nstage > 2 && tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh, ps.nstage) > (size_t)dev_smem) --ps.nstage;
-        smem = std::max(smem, tc_smem_bytes(ps.plain ? 0 : ps.rows, Nh, ps.nstage));
+        // the deepest B ring / ODF staging that fits beside the key tile, per instantiation
+        const int Mk = ps.plain ? 0 : ps.rows;
+        ps.nstage = NSTAGE; ps.obuf = 2; ps.nstage_ca = NSTAGE;
+        while (tc_smem_bytes(true, Mk, Nh, ps.nstage, ps.obuf) > (size_t)dev_smem) {
+            if (ps.nstage > 3) --ps.nstage; else if (ps.obuf > 1) --ps.obuf; else if (ps.nstage > 2) --ps.nstage; else break;
+        }
+        while (ps.nstage_ca > 2 && tc_smem_bytes(false, Mk, Nh, ps.nstage_ca, 0) > (size_t)dev_smem) --ps.nstage_ca;
+        smem = std::max(smem, tc_smem_bytes(true, Mk, Nh, ps.nstage, ps.obuf));
+        smem_ca = std::max(smem_ca, tc_smem_bytes(false, Mk, Nh, ps.nstage_ca, 0));
         // Split operand as a ready-made shared-memory image: [rank][K32 chunk][K16 sub-tile][hi | lo][row][16 halves],
         // rows in the order (blk1 rows 0..N1h, blk2 rows 0..N2h) of that rank, with the SWIZZLE_32B pattern the
         // tcgen05 descriptors expect already applied (16-byte chunk ^= bit 2 of the row).  A stage is then ONE
@@ -941,7 +1064,7 @@ int tc_plan_init(Plan* p) {
         const cuuint64_t img_rows = (cuuint64_t)2 * nk32 * (stage_halves / 256);
         cuuint64_t gdim[2] = {256, img_rows};
         cuuint64_t gstr[1] = {512};
-        cuuint32_t box[2] = {256, (cuuint32_t)(stage_halves / 256)};
+        cuuint32_t box[2] = {256, (cuuint32_t)(stage_halves / 512)};          // one K16 sub-tile (hi rows + lo rows) per stage
         cuuint32_t estr[2] = {1, 1};
         if (((EncodeFn)fn)(&st->pass.back().tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ps.d_split, gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -949,21 +1072,21 @@ int tc_plan_init(Plan* p) {
             set_error("tensor-core path: cuTensorMapEncodeTiled failed"); tc_state_free(st); return 1;
         }
     }
-    if (smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
-    st->smem = smem;
-    if (raise_smem_limit(p->device, smem)) { tc_state_free(st); return 1; }
+    if (smem > (size_t)dev_smem || smem_ca > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
+    st->smem = smem; st->smem_ca = smem_ca;
+    if (raise_smem_limit(p->device, true, smem) || raise_smem_limit(p->device, false, smem_ca)) { tc_state_free(st); return 1; }
     p->tc = st;
     return 0;
 }
 
 namespace {
-int raise_smem_limit(int device, size_t smem) {
+int raise_smem_limit(int device, bool tma, size_t smem) {
     std::lock_guard<std::mutex> lk(g_smem_mu);
-    size_t& cur = g_smem_limit[device & 63];
+    size_t& cur = g_smem_limit[tma ? 1 : 0][device & 63];
     if (smem <= cur) return 0;
-    if (cudaFuncSetAttribute(recon_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); return 1;
-    }
+    const cudaError_t e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(recon_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); return 1; }
     cur = smem;
     return 0;
 }
@@ -1024,7 +1147,11 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.fix_cap = (int)(2 * ntile64);
         tp.ntiles = (int)((a.nvox + 255) / 256);
         tp.nbw = st->nbw;
-        tp.nstage = ps.nstage;
+        // TMA instantiation when the slab rows and the output rows are 16-byte aligned (always true for the host entry points)
+        const bool tma = getenv("FIBERS_TC_NO_TMA") == nullptr && (uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0 &&
+                         (uintptr_t)out % 16 == 0 && a.out_pitch % 4 == 0 && a.nvox < (1ll << 31) - 512;
+        tp.nstage = tma ? ps.nstage : ps.nstage_ca;
+        tp.obuf = ps.obuf;
         tp.plain = ps.plain;
         tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
@@ -1035,7 +1162,24 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
             tp.trace = d_trace;
             if (const char* sk = getenv("FIBERS_TC_TRACE_SKIP")) tp.trace_skip = (uint32_t)atoi(sk);
         }
-        recon_tc_kernel<<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, st->nbr_off);
+        if (tma) {
+            // per-launch tensor maps: the DWI slab [K][nvox] fp32 (row pitch dwi_pitch) in K16 x 128-voxel boxes, the output
+            // rows [rows][nvox] fp32 (row pitch out_pitch) in 16 x 32 boxes; out-of-range voxels / rows are zero-filled / clipped
+            CUtensorMap mD, mO;
+            cuuint32_t estr[2] = {1, 1};
+            cuuint64_t dD[2] = {(cuuint64_t)a.nvox, (cuuint64_t)p->nvol}, sD[1] = {(cuuint64_t)a.dwi_pitch * 4};
+            cuuint32_t bD[2] = {VOX_CTA, 16};
+            cuuint64_t dO[2] = {(cuuint64_t)a.nvox, (cuuint64_t)ps.rows}, sO[1] = {(cuuint64_t)a.out_pitch * 4};
+            cuuint32_t bO[2] = {32, 16};
+            if (((EncodeFn)st->encode)(&mD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.dwi, dD, sD, bD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+                ((EncodeFn)st->encode)(&mO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)out, dO, sO, bO, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail(FIBERS_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed for the slab / output map");
+            recon_tc_kernel<true><<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+        } else {
+            recon_tc_kernel<false><<<2 * nclusters, TC_THREADS, st->smem_ca, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
+        }
         count_launch(1);
         FB_CUDA(cudaGetLastError());
         if (d_trace) {

@@ -68,6 +68,10 @@ def _check_dti(got, ph, what, min_partial_frac=0.0, valid=None):
             e_gpu = np.abs(P.flat(getattr(got, name).vol)[sel].astype(np.float64) - ref) / scale
             e_ref = np.abs(P.flat(r32[name])[sel].astype(np.float64) - ref) / scale
             ill = e_ref > 0.5 * P.SCALAR_TOL
+            if name in ("eigval2", "eigval3"):          # closed-form roots of a nearly degenerate pair (gap < 1e-3)
+                l2, l3 = P.flat(r64["eigval2"])[sel], P.flat(r64["eigval3"])[sel]
+                gap = np.abs(l2 - l3) if name == "eigval3" else np.minimum(np.abs(l2 - l3), np.abs(l1[sel] - np.abs(l2)))
+                ill |= gap < 1e-3 * l1[sel]
             if branch == "full" and name in ("s0", "eigval1", "md", "fa"):   # (lambda2/3 of nearly degenerate tensors are ill-conditioned in fp32)
                 assert not ill.any(), f"{what}: fp32 reference arithmetic off by > 0.5e-4 on the full branch ({name})"
             exempt |= ill
