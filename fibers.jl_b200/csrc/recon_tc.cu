@@ -51,9 +51,9 @@ constexpr int N_CONV = 4;            // converter warps (multiple of 4)
 constexpr int W_MMA = 1, W_DWI = 2, W_CONV0 = 3, W_EPI0 = W_CONV0 + N_CONV;   // (every group of 4 consecutive warps covers the 4 TMEM lane quarters: quarter = warp & 3)
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
 constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
-constexpr int NSTAGE = 4;            // B ring, K16 sub-tiles (hi rows + lo rows); fewer when shared memory is short (M > 335)
+constexpr int NSTAGE = 8;            // B ring, K16 sub-tiles (hi rows + lo rows): maximum depth; the launch picks what fits (p.nstage)
 constexpr int DSTAGE = 3;            // cp.async mode: raw DWI ring of the converters, K32 chunks of 128 voxels (16 KB each)
-constexpr int TSTAGE = 4;            // TMA mode: raw DWI ring, K16 boxes of 128 voxels (8 KB each), filled by the DWI producer warp
+constexpr int TSTAGE = 8;            // TMA mode: raw DWI ring, K16 boxes of 128 voxels (8 KB each), filled by the DWI producer warp: maximum depth (p.tstage)
 constexpr int OBOX_BYTES = 16 * 128 * 4;   // TMA mode: ODF staging box = 16 vertex rows x 128 voxels fp32, one TMA store each
 constexpr int ASLOT = 4;             // A ring in TMEM: K32 chunks, 32 columns each
 constexpr int TMEM_A_COL = 384;
@@ -86,10 +86,14 @@ struct TcParams {
     const int* tile_list; const int* tile_count;   // tiles that contain at least one mask voxel (built by tile_scan_kernel)
     int nbw;                     // max neighbour count of the folded mesh (<= 8)
     int nstage;                  // depth of the B ring (<= NSTAGE)
-    int obuf;                    // TMA mode: ODF staging boxes per column part (1 or 2)
+    int tstage;                  // TMA mode: depth of the raw DWI ring (<= TSTAGE, even)
+    int obuf;                    // TMA mode: ODF staging boxes per epilogue warp (1 or 2); 0 = direct stores, no staging
+    int abl;                     // ABLATION bits for timing experiments only (FIBERS_TC_ABLATE; results are then wrong by design)
+    int l2pf;                    // TMA mode: the DWI producer prefetches the boxes of the tile l2pf rounds ahead into L2 (0 = off)
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // DWI staging copies: 2 = 16 bytes (base 16-byte aligned, pitch % 4 == 0), 1 = 8 bytes, 0 = 4 bytes
+    uint32_t conv_sleep, prod_sleep;   // back-off (ns) of the converters' a_empty wait and of the producers' ring waits
     int cand_cap;                // capacity of the candidate list (<= CAND_CAP; tests shrink it to force the fall-back)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
     uint32_t trace_skip;         // first traced tile iteration
@@ -103,9 +107,6 @@ struct TcPass {
     int rows = 0, row0 = 0;      // matrix rows [row0, row0 + rows) of the plan's matrix
     int Npad = 0, N1 = 0, N2 = 0;
     int plain = 0;               // 1: pdf rows
-    int nstage = NSTAGE;         // B ring depth that fits in shared memory for this pass (TMA mode)
-    int obuf = 2;                // ODF staging boxes per column part (TMA mode)
-    int nstage_ca = NSTAGE;      // the same for the cp.async mode (its DWI ring is larger, it has no ODF staging)
 };
 
 struct TcState {
@@ -113,7 +114,7 @@ struct TcState {
     void* encode = nullptr;      // cuTensorMapEncodeTiled
     int Kpad = 0, nbw = 8;
     NbrOffTable nbr_off;                     // [M + 8][NBR_W] byte offsets (rows >= M: sentinel); passed by value with every launch
-    size_t smem = 0, smem_ca = 0;  // dynamic shared memory of the TMA / cp.async instantiation
+    int dev_smem = 0;            // opt-in shared memory per block of the device
     int* d_scratch = nullptr;    // [0] maxbits, [1] fix_count, [2..] fix list
     int64_t scratch_cap = 0;
 };
@@ -154,6 +155,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (spin > (1u << 26)) __trap();        // never hang the GPU: a lost signal becomes a launch error
     }
 }
+// run-time back-off (tuning experiments): ns == 0 -> hardware-suspended try_wait with a long time hint, no polling loop
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        if (ns == 0)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+        else {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+            if (!ok) __nanosleep(ns);
+        }
+        if (spin > (1u << 26)) __trap();
+    }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
@@ -192,8 +209,8 @@ __device__ __forceinline__ uint64_t make_sdesc_sw32(uint32_t saddr) {          /
 }
 
 // (16 consecutive tiles of CTA 0, starting at tile iteration p.trace_skip: FIBERS_TC_TRACE_SKIP, default 0)
-#define TRACE(slot) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] = clock64(); } while (0)
-#define TRACE_ADD(slot, dt) do { if (p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] += (dt); } while (0)
+#define TRACE(slot) do { if (kTrace && p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] = clock64(); } while (0)
+#define TRACE_ADD(slot, dt) do { if (kTrace && p.trace && blockIdx.x == 0 && lane == 0 && it - p.trace_skip < 16u) p.trace[(it - p.trace_skip) * 32 + (slot)] += (dt); } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // strided sample of the slab: max over 32-voxel runs every 2048 voxels of every volume
@@ -282,7 +299,8 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
 // TMA stores from a small staging ring, so that the accumulator drain is not paced by the SM's 32 B/clk store port
 // (tools/store_probe.cu: 172 KB of ODF per tile = 5.4 k cycles of that port); needs 16-byte aligned slab / output
 // rows.  !kTma: cp.async staging + direct stores (any alignment).
-template <bool kTma>
+// kTrace: per-role clock trace of cluster 0 (FIBERS_TC_TRACE); compiled out of the production instantiations.
+template <bool kTma, bool kTrace>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ NbrOffTable nbt,
                 const __grid_constant__ CUtensorMap tmapD, const __grid_constant__ CUtensorMap tmapO) {
@@ -319,7 +337,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     float* s_mean = s_min + N_CPART * VOX_CTA;                            // [128] mean ODF per voxel (from the extra matrix row)
     // raw DWI ring (128-byte aligned: TMA destination), then (TMA mode) the ODF staging boxes
     float* s_dwi = (float*)(((uintptr_t)(s_mean + VOX_CTA) + 127) & ~(uintptr_t)127);   // cp.async: [DSTAGE][32][128]; TMA: [TSTAGE][16][128]
-    uint8_t* s_obox = (uint8_t*)(s_dwi + (kTma ? TSTAGE * 16 : DSTAGE * 32) * VOX_CTA);   // [N_CPART][obuf][16][128] fp32
+    uint8_t* s_obox = (uint8_t*)(s_dwi + (kTma ? p.tstage * 16 : DSTAGE * 32) * VOX_CTA);   // [N_CPART][obuf][16][128] fp32
     uint4* s_nbr = (uint4*)(s_obox + (kTma ? (size_t)N_CPART * p.obuf * OBOX_BYTES : 0));  // [M] 8 x uint16 neighbour ids per vertex
     float* s_vert = (float*)(s_nbr + Mk);                                 // [M][3] first-half vertices (peak vectors); padded to 4 floats
     uint64_t* bars = (uint64_t*)(s_vert + ((3 * Mk + 3) & ~3));
@@ -349,7 +367,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
-    if (p.trace && threadIdx.x == 0 && rank == 0) {           // per-cluster wall-clock span (debug trace only)
+    if (kTrace && p.trace && threadIdx.x == 0 && rank == 0) {           // per-cluster wall-clock span (debug trace only)
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[16 * 32 + 2 * cluster_id] = (long long)t;
         if (cluster_id == 0) p.trace[16 * 32 + 2 * 127] = clock64();            // SM cycles over the same span -> effective clock
@@ -369,13 +387,12 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         // ===== TMA producer: this CTA's half of the split matrix rows, K32 per stage ===========
         // (the whole warp runs the loop so that control flow stays uniform; one elected lane issues)
         const uint32_t full0 = mapa(smem_u32(&b_full[0]), 0);
-        uint32_t g = 0, it = 0;
+        uint32_t it = 0;
+        int s = 0; uint32_t ph = 0;                         // ring stage and its phase bit (no run-time division in the loop)
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
-            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             TRACE(13);
-            for (int c = 0; c < nk16; ++c, ++g) {
-                const int s = g % p.nstage; const uint32_t use = g / p.nstage;
-                mbar_wait<200>(&b_empty[s], (use & 1) ^ 1);
+            for (int c = 0; c < nk16; ++c) {
+                mbar_wait_ns(&b_empty[s], ph ^ 1, p.prod_sleep);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(&b_full[s], 2 * sub_bytes);         // both CTAs' bytes land on the leader's barrier
                     // one bulk tensor copy per stage: the global image is already in shared-memory order
@@ -384,6 +401,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                                    "r"(full0 + s * 8) : "memory");
                 }
                 __syncwarp();
+                if (++s == p.nstage) { s = 0; ph ^= 1u; }
             }
             TRACE(14);
         }
@@ -392,68 +410,85 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         if (rank == 0) {
             const uint32_t idesc1 = make_idesc_f16(256, p.N1);
             const uint32_t idesc2 = p.N2 ? make_idesc_f16(256, p.N2) : 0u;
-            uint32_t g32 = 0, it = 0;
+            uint32_t it = 0;
+            int bs = 0; uint32_t bph = 0;                   // B ring stage / phase
+            int slot = 0; uint32_t aph = 0;                 // A ring slot / phase
+            // shared-memory descriptors of stage 0 (the start-address field is additive: + (stage * sub_bytes) >> 4)
+            const uint32_t sB0 = smem_u32(sB);
+            const uint64_t dhi1 = make_sdesc_sw32(sB0), dlo1 = make_sdesc_sw32(sB0 + Nh * 32);
+            const uint64_t dhi2 = make_sdesc_sw32(sB0 + N1h * 32), dlo2 = make_sdesc_sw32(sB0 + Nh * 32 + N1h * 32);
+            const uint32_t dstep = sub_bytes >> 4;
+            const bool two = p.N2 != 0, one_product = (p.abl & 1) != 0;
             for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {             // (this role only needs the tile count)
                 mbar_wait<100>(d_empty, (it & 1) ^ 1);              // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
                 TRACE(0);
-                uint32_t g16 = 2 * g32;
-                for (int c = 0; c < nk32; ++c, ++g32) {
-                    const int slot = g32 % ASLOT;
-                    long long t1 = p.trace ? clock64() : 0;
-                    mbar_wait(&a_full[slot], (g32 / ASLOT) & 1);
-                    if (p.trace) { long long t2 = clock64(); TRACE_ADD(16, t2 - t1); }
+                long long wait_a = 0, wait_b = 0;                       // (trace only)
+                for (int c = 0; c < nk32; ++c) {
+                    long long t1 = kTrace ? clock64() : 0;
+                    mbar_wait(&a_full[slot], aph);
+                    if (kTrace) wait_a += clock64() - t1;
                     const uint32_t a_base = tmem_base + TMEM_A_COL + slot * 32;
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub, ++g16) {
-                        const int s = g16 % p.nstage;
-                        long long t0 = p.trace ? clock64() : 0;
-                        mbar_wait(&b_full[s], (g16 / p.nstage) & 1);
-                        if (p.trace) { long long t3 = clock64(); TRACE_ADD(15, t3 - t0); }
+                    for (int sub = 0; sub < 2; ++sub) {
+                        long long t0 = kTrace ? clock64() : 0;
+                        mbar_wait(&b_full[bs], bph);
+                        if (kTrace) wait_b += clock64() - t0;
                         tc_fence_after();
-                        const uint32_t b0 = smem_u32(sB + s * sub_bytes);
                         if (elect_one()) {
                             const uint32_t a_hi = a_base + sub * 8, a_lo = a_hi + 16;
                             const uint32_t acc = (c | sub) ? 1u : 0u;
-                            const uint64_t bhi1 = make_sdesc_sw32(b0), blo1 = make_sdesc_sw32(b0 + Nh * 32);
-                            mma_ts2(tmem_base, a_lo, bhi1, idesc1, acc);       // small terms first
-                            mma_ts2(tmem_base, a_hi, blo1, idesc1, 1u);
-                            mma_ts2(tmem_base, a_hi, bhi1, idesc1, 1u);
-                            if (p.N2) {
-                                const uint64_t bhi2 = make_sdesc_sw32(b0 + N1h * 32), blo2 = make_sdesc_sw32(b0 + Nh * 32 + N1h * 32);
-                                mma_ts2(tmem_base + p.N1, a_lo, bhi2, idesc2, acc);
-                                mma_ts2(tmem_base + p.N1, a_hi, blo2, idesc2, 1u);
-                                mma_ts2(tmem_base + p.N1, a_hi, bhi2, idesc2, 1u);
+                            const uint64_t off = (uint64_t)((uint32_t)bs * dstep);
+                            if (!one_product) {
+                                mma_ts2(tmem_base, a_lo, dhi1 + off, idesc1, acc);       // small terms first
+                                mma_ts2(tmem_base, a_hi, dlo1 + off, idesc1, 1u);
+                                mma_ts2(tmem_base, a_hi, dhi1 + off, idesc1, 1u);
+                                if (two) {
+                                    mma_ts2(tmem_base + p.N1, a_lo, dhi2 + off, idesc2, acc);
+                                    mma_ts2(tmem_base + p.N1, a_hi, dlo2 + off, idesc2, 1u);
+                                    mma_ts2(tmem_base + p.N1, a_hi, dhi2 + off, idesc2, 1u);
+                                }
+                            } else {                                    // (timing ablation)
+                                mma_ts2(tmem_base, a_hi, dhi1 + off, idesc1, acc);
+                                if (two) mma_ts2(tmem_base + p.N1, a_hi, dhi2 + off, idesc2, acc);
                             }
-                            mma_commit2(&b_empty[s]);                      // B stage reusable once these MMAs retire
+                            mma_commit2(&b_empty[bs]);                     // B stage reusable once these MMAs retire
                             if (sub == 1) {
                                 mma_commit2(&a_empty[slot]);               // ... and the A slot after its second half
                                 if (c == nk32 - 1) mma_commit2(d_full);
                             }
                         }
                         __syncwarp();
+                        if (++bs == p.nstage) { bs = 0; bph ^= 1u; }
                     }
+                    if (++slot == ASLOT) { slot = 0; aph ^= 1u; }
                 }
                 TRACE(1);
+                if (kTrace) { TRACE_ADD(15, wait_b); TRACE_ADD(16, wait_a); }
             }
         }
     } else if (warp == W_DWI) {
         // ===== DWI producer (TMA mode): one K16 x 128-voxel box of the raw slab per stage, TSTAGE stages ahead of the
         //       converters across tile boundaries.  Voxels past the end of the slab and volumes past K arrive as zeros. ====
         if (kTma) {
-            uint32_t g = 0;
+            int s = 0; uint32_t ph = 0;
             for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster) {
                 const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
                 const int vox0 = tile * 256 + (int)rank * VOX_CTA;
-                for (int c = 0; c < nk16; ++c, ++g) {
-                    const int s = g % TSTAGE;
-                    mbar_wait<200>(&w_empty[s], ((g / TSTAGE) & 1) ^ 1);
+                for (int c = 0; c < nk16; ++c) {
+                    mbar_wait_ns(&w_empty[s], ph ^ 1, p.prod_sleep);
                     if (elect_one()) {
+                        if (p.l2pf > 0 && ti_ + p.l2pf * ncluster < ntl) {     // the same box of a later tile of this cluster -> L2
+                            const int t2 = ident ? ti_ + p.l2pf * ncluster : __ldg(p.tile_list + ti_ + p.l2pf * ncluster);
+                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                                         ::"l"(&tmapD), "r"(t2 * 256 + (int)rank * VOX_CTA), "r"(c * 16) : "memory");
+                        }
                         mbar_expect_tx(&w_full[s], 16 * VOX_CTA * 4);
                         asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                                      ::"r"(smem_u32(s_dwi + s * 16 * VOX_CTA)), "l"(&tmapD), "r"(vox0), "r"(c * 16), "r"(smem_u32(&w_full[s])) : "memory");
                     }
                     __syncwarp();
+                    if (++s == p.tstage) { s = 0; ph ^= 1u; }
                 }
             }
         }
@@ -531,6 +566,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             for (int i = 0; i < PF; ++i) prefetch();
         }
         uint32_t it = 0, g32 = 0;
+        int ws = 0; uint32_t wph = 0;                       // DWI ring stage / phase (TMA mode; the depth is even)
+        int slot = 0; uint32_t aph = 0;                     // A ring slot / phase
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
@@ -539,13 +576,23 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 #pragma unroll 1
             for (int c = 0; c < nk32; ++c, ++g32) {
                 float x[32];
-                if (kTma) {
+                if (p.abl & 8) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = 1.f;
+                    if (kTma) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) mbar_wait<20>(&w_full[ws + h], wph);
+                    } else {
+                        asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");
+                        named_bar(2, N_CONV * 32);
+                        prefetch();
+                    }
+                } else if (kTma) {
                     // two K16 boxes of the DWI ring per A slot; the stage goes back to the producer once this warp has its values
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t g16 = 2 * g32 + h; const int s = g16 % TSTAGE;
-                        mbar_wait<20>(&w_full[s], (g16 / TSTAGE) & 1);
-                        const uint32_t sbase = sd0 + s * (16 * VOX_CTA * 4) + vl * 4;
+                        mbar_wait<20>(&w_full[ws + h], wph);
+                        const uint32_t sbase = sd0 + (ws + h) * (16 * VOX_CTA * 4) + vl * 4;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[16 * h + j]) : "r"(sbase + j * (VOX_CTA * 4)));
                     }
@@ -571,13 +618,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 if (kTma) {                                             // (the conversions above consumed every x[]: the loads have completed)
                     __syncwarp();
                     if (lane == 0) {
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[(2 * g32) % TSTAGE])) : "memory");
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[(2 * g32 + 1) % TSTAGE])) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[ws])) : "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&w_empty[ws + 1])) : "memory");
                     }
+                    ws += 2; if (ws == p.tstage) { ws = 0; wph ^= 1u; }
                 }
-                const int slot = g32 % ASLOT;
                 if (warp == W_CONV0 && c == 0) TRACE(10);
-                mbar_wait<100>(&a_empty[slot], ((g32 / ASLOT) & 1) ^ 1);
+                mbar_wait_ns(&a_empty[slot], aph ^ 1, p.conv_sleep);
                 if (warp == W_CONV0 && c == 0) TRACE(11);
                 tc_fence_after();
                 const uint32_t col = lane_addr + TMEM_A_COL + slot * 32;
@@ -586,6 +633,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(afull0 + slot * 8);
+                if (++slot == ASLOT) { slot = 0; aph ^= 1u; }
             }
             if (warp == W_CONV0) TRACE(12);
         }
@@ -605,6 +653,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         // TMA mode: this warp's ODF staging boxes ([16 rows][32 voxels] fp32 each) and its running box counter
         constexpr uint32_t WBOX = 16 * 32 * 4;
         const uint32_t obox0 = smem_u32(s_obox) + (uint32_t)(ew * p.obuf) * WBOX;
+        const uint32_t obufm = (uint32_t)max(p.obuf, 1);
         uint32_t oc = 0;
         uint32_t it = 0;
         for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
@@ -681,14 +730,17 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 // (rows >= M and voxels >= nvox are clipped by the tensor map); the box is reused two chunks later, once the
                 // TMA unit has read it.  The drain then runs at TMEM / issue speed instead of the store port's.
                 const int vcoord = (int)vox0 + q * 32;
+                long long box_wait = 0;                                // (trace only)
                 auto process_tma = [&](const uint32_t (&r)[16], int c0) {
                     const int nrow = min(16, M - c0);                   // warp-uniform
-                    const uint32_t bx = obox0 + (oc % (uint32_t)p.obuf) * WBOX + lane * 4;
+                    const uint32_t bx = obox0 + (oc % obufm) * WBOX + lane * 4;
+                    const long long tw0 = (kTrace && p.trace && warp == W_EPI0) ? clock64() : 0;
                     if (lane == 0) {
                         if (p.obuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
                     __syncwarp();
+                    if (kTrace && p.trace && warp == W_EPI0) { box_wait += clock64() - tw0; TRACE(17 + ((c0 - c_begin) >> 4)); }
                     if (plain) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
@@ -723,7 +775,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     }
                     kp += 16 * VOX_CTA; ++oc;
                 };
-                auto step = [&](const uint32_t (&r)[16], int c0) { if (kTma) process_tma(r, c0); else process(r, c0); };
+                const bool staged = kTma && p.obuf > 0;
+                auto step = [&](const uint32_t (&r)[16], int c0) { if (p.abl & 4) { mn = fminf(mn, __uint_as_float(r[0])); return; } if (staged) process_tma(r, c0); else process(r, c0); };
                 uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
                 if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
                 for (int c0 = c_begin; c0 < c_end; c0 += 32) {
@@ -736,6 +789,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                         step(rb, c0 + 16);
                     }
                 }
+                if (kTma && kTrace && p.trace && warp == W_EPI0) TRACE_ADD(24, box_wait);
             }
             tc_fence_before();
             __syncwarp();
@@ -751,15 +805,16 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             //      listed.  Two vertices per iteration; software-pipelined: the keys of pair i+1 and the offsets of
             //      pair i+2 are in flight while pair i is tested.  (Prefetches past the warp's range touch rows
             //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
-            {
+            if (!(p.abl & 2)) {
                 uint32_t kb = smem_u32(keys) + lane * 8;
                 asm volatile("mov.u32 %0, %0;" : "+r"(kb));             // pin: keeps the compiler from re-deriving the base in every iteration
                 const uint32_t ncand32 = smem_u32(s_ncand);
                 auto ld = [&](uint32_t off) {
                     uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
                 };
+                // max of the six neighbour keys and of the threshold key 1 (two packed voxels): three 3-input packed max
                 auto max6 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
-                    return umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f));
+                    return umax2(umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f)), 0x80018001u);
                 };
                 const bool wide = p.nbw > 6;                            // warp-uniform (meshes with degree 7-8)
                 // Vertex pairs are dealt round-robin to the warps (pair ew, ew + N_EPI, ...): ODF peaks are spatially
@@ -801,8 +856,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     // stored keys have bit 15 set, so per 16-bit half  (k - t + 0x8000) has bit 15 set  <=>  k >= t,
                     // and the two halves cannot borrow from each other: one 32-bit subtraction tests two voxels.
                     // threshold t = max(neighbour keys, 1)
-                    const uint32_t hAx = kA.x - umax2(mAx, 0x80018001u) + 0x80008000u, hAy = kA.y - umax2(mAy, 0x80018001u) + 0x80008000u;
-                    const uint32_t hBx = kB.x - umax2(mBx, 0x80018001u) + 0x80008000u, hBy = kB.y - umax2(mBy, 0x80018001u) + 0x80008000u;
+                    const uint32_t hAx = kA.x - mAx + 0x80008000u, hAy = kA.y - mAy + 0x80008000u;
+                    const uint32_t hBx = kB.x - mBx + 0x80008000u, hBy = kB.y - mBy + 0x80008000u;
                     // No branch in the loop: the 8 result bits of the pair (0-3 = vertex v, voxels 4*lane + 0..3; 4-7 =
                     // vertex v + 1) go into a per-lane bit field, one byte per iteration, and are listed after the loop.
                     const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
@@ -934,7 +989,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 
     // ---- teardown --------------------------------------------------------------------------
     if (kTma && warp >= W_EPI0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes still being read
-    if (p.trace && warp == W_EPI0 && lane == 0 && rank == 0) {
+    if (kTrace && p.trace && warp == W_EPI0 && lane == 0 && rank == 0) {
         unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[16 * 32 + 2 * cluster_id + 1] = (long long)t;
         if (cluster_id == 0) p.trace[16 * 32 + 2 * 127 + 1] = clock64();
@@ -948,10 +1003,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 }
 
 // dynamic shared memory of one instantiation (carve-up of recon_tc_kernel; M = 0 for plain passes)
-size_t tc_smem_bytes(bool tma, int M, int Nh, int nstage, int obuf) {
+size_t tc_smem_bytes(bool tma, int M, int Nh, int nstage, int tstage, int obuf) {
     size_t b = (size_t)nstage * 2 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + 3 * VOX_CTA * 8 + (size_t)CAND_CAP * 4 + (N_CPART + 1) * VOX_CTA * 4;
     b = (b + 127) & ~(size_t)127;
-    b += tma ? (size_t)TSTAGE * 16 * VOX_CTA * 4 + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
+    b += tma ? (size_t)tstage * 16 * VOX_CTA * 4 + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
     b += (size_t)M * 16 + (size_t)((3 * M + 3) & ~3) * 4 + (2 * NSTAGE + 2 * ASLOT + 2 + 2 * TSTAGE) * 8 + 16;
     return b + 1024 + 64;
 }
@@ -1006,7 +1061,7 @@ int tc_plan_init(Plan* p) {
     // passes: ODF rows, then (DSI) the pdf rows in blocks of <= 336
     std::vector<std::pair<int, int>> ranges = {{0, M}};
     if (p->kind == PLAN_DSI) for (int r0 = 0; r0 < K; r0 += 336) ranges.push_back({M + r0, std::min(336, K - r0)});
-    size_t smem = 0, smem_ca = 0;
+    size_t smem = 0;
     int dev_smem = 0;
     if (cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device) != cudaSuccess) dev_smem = 0;
     for (size_t i = 0; i < ranges.size(); ++i) {
@@ -1015,15 +1070,9 @@ int tc_plan_init(Plan* p) {
         const int img_rows_n = ps.rows + (ps.plain ? 0 : 1);          // ODF pass: one extra row = mean of the ODF rows
         split_dims(img_rows_n, ps.Npad, ps.N1, ps.N2);
         const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
-        // the deepest B ring / ODF staging that fits beside the key tile, per instantiation
+        // smallest configuration of either instantiation must fit (the launch picks the ring depths)
         const int Mk = ps.plain ? 0 : ps.rows;
-        ps.nstage = NSTAGE; ps.obuf = 2; ps.nstage_ca = NSTAGE;
-        while (tc_smem_bytes(true, Mk, Nh, ps.nstage, ps.obuf) > (size_t)dev_smem) {
-            if (ps.nstage > 3) --ps.nstage; else if (ps.obuf > 1) --ps.obuf; else if (ps.nstage > 2) --ps.nstage; else break;
-        }
-        while (ps.nstage_ca > 2 && tc_smem_bytes(false, Mk, Nh, ps.nstage_ca, 0) > (size_t)dev_smem) --ps.nstage_ca;
-        smem = std::max(smem, tc_smem_bytes(true, Mk, Nh, ps.nstage, ps.obuf));
-        smem_ca = std::max(smem_ca, tc_smem_bytes(false, Mk, Nh, ps.nstage_ca, 0));
+        smem = std::max(smem, std::max(tc_smem_bytes(true, Mk, Nh, 2, 4, 0), tc_smem_bytes(false, Mk, Nh, 2, 0, 0)));
         // Split operand as a ready-made shared-memory image: [rank][K32 chunk][K16 sub-tile][hi | lo][row][16 halves],
         // rows in the order (blk1 rows 0..N1h, blk2 rows 0..N2h) of that rank, with the SWIZZLE_32B pattern the
         // tcgen05 descriptors expect already applied (16-byte chunk ^= bit 2 of the row).  A stage is then ONE
@@ -1072,9 +1121,9 @@ int tc_plan_init(Plan* p) {
             set_error("tensor-core path: cuTensorMapEncodeTiled failed"); tc_state_free(st); return 1;
         }
     }
-    if (smem > (size_t)dev_smem || smem_ca > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
-    st->smem = smem; st->smem_ca = smem_ca;
-    if (raise_smem_limit(p->device, true, smem) || raise_smem_limit(p->device, false, smem_ca)) { tc_state_free(st); return 1; }
+    if (smem > (size_t)dev_smem) { set_error("tensor-core path: tile does not fit in shared memory"); tc_state_free(st); return 1; }
+    st->dev_smem = dev_smem;
+    if (raise_smem_limit(p->device, true, (size_t)dev_smem) || raise_smem_limit(p->device, false, (size_t)dev_smem)) { tc_state_free(st); return 1; }
     p->tc = st;
     return 0;
 }
@@ -1084,8 +1133,11 @@ int raise_smem_limit(int device, bool tma, size_t smem) {
     std::lock_guard<std::mutex> lk(g_smem_mu);
     size_t& cur = g_smem_limit[tma ? 1 : 0][device & 63];
     if (smem <= cur) return 0;
-    const cudaError_t e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                              : cudaFuncSetAttribute(recon_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(recon_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                : cudaFuncSetAttribute(recon_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); return 1; }
     cur = smem;
     return 0;
@@ -1137,6 +1189,9 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.dwi = a.dwi; tp.dwi_pitch = a.dwi_pitch; tp.mask = a.mask; tp.nvox = a.nvox;
         tp.dwi_vec = ((uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0) ? 2 : ((uintptr_t)a.dwi % 8 == 0 && a.dwi_pitch % 2 == 0) ? 1 : 0;
         tp.cand_cap = CAND_CAP;
+        tp.conv_sleep = 100; tp.prod_sleep = 200;
+        if (const char* e = getenv("FIBERS_TC_CONV_SLEEP")) tp.conv_sleep = (uint32_t)atoi(e);
+        if (const char* e = getenv("FIBERS_TC_PROD_SLEEP")) tp.prod_sleep = (uint32_t)atoi(e);
         if (const char* cap = getenv("FIBERS_TC_CAND_CAP")) tp.cand_cap = std::max(0, std::min(CAND_CAP, atoi(cap)));
         tp.K = p->nvol; tp.Kpad = st->Kpad; tp.M = ps.rows; tp.Npad = ps.Npad; tp.N1 = ps.N1; tp.N2 = ps.N2;
         tp.odf = out; tp.out_pitch = a.out_pitch;
@@ -1150,8 +1205,26 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         // TMA instantiation when the slab rows and the output rows are 16-byte aligned (always true for the host entry points)
         const bool tma = getenv("FIBERS_TC_NO_TMA") == nullptr && (uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0 &&
                          (uintptr_t)out % 16 == 0 && a.out_pitch % 4 == 0 && a.nvox < (1ll << 31) - 512;
-        tp.nstage = tma ? ps.nstage : ps.nstage_ca;
-        tp.obuf = ps.obuf;
+        // ring depths: the deepest B ring (L2 latency), a DWI ring that covers L2 latency (HBM latency is covered by the L2
+        // prefetch one tile ahead) and one ODF staging box per epilogue warp, shrunk until the tile fits in shared memory
+        const int Mk = ps.plain ? 0 : ps.rows, Nhh = (ps.N1 + ps.N2) / 2;
+        auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+        tp.nstage = std::max(2, std::min(NSTAGE, envi("FIBERS_TC_BSTAGES", 6)));
+        tp.tstage = std::max(2, std::min(TSTAGE, envi("FIBERS_TC_DSTAGES", 4))) & ~1;
+        tp.obuf = std::max(0, std::min(2, envi("FIBERS_TC_OBUF", 0)));
+        tp.l2pf = std::max(0, envi("FIBERS_TC_L2PF", 0));
+        tp.abl = envi("FIBERS_TC_ABLATE", 0);
+        if (!tma) { tp.tstage = 0; tp.obuf = 0; tp.l2pf = 0; }
+        while (tc_smem_bytes(tma, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf) > (size_t)st->dev_smem) {
+            if (tp.nstage > 4) --tp.nstage; else if (tp.obuf > 0) --tp.obuf; else if (tp.tstage > 4) tp.tstage -= 2; else if (tp.nstage > 2) --tp.nstage;
+            else return fail(FIBERS_ERR_ARG, "tensor-core path: tile does not fit in shared memory");
+        }
+        const size_t smem_launch = tc_smem_bytes(tma, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf);
+        if (getenv("FIBERS_TC_VERBOSE")) {
+            static std::atomic<int> once{0};
+            if (once.fetch_add(1) < 4) fprintf(stderr, "[fibers tc] pass %zu: tma %d, B stages %d, DWI stages %d, ODF boxes %d, L2 prefetch %d, smem %zu\n",
+                                               ip, (int)tma, tp.nstage, tp.tstage, tp.obuf, tp.l2pf, smem_launch);
+        }
         tp.plain = ps.plain;
         tp.cvol = p->kind == PLAN_DSI ? p->cvol : -1; tp.dscale = p->dscale;
         const int nclusters = std::max(1, std::min(nsm / 2, tp.ntiles));
@@ -1176,9 +1249,11 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
                 ((EncodeFn)st->encode)(&mO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)out, dO, sO, bO, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return fail(FIBERS_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed for the slab / output map");
-            recon_tc_kernel<true><<<2 * nclusters, TC_THREADS, st->smem, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            if (tp.trace) recon_tc_kernel<true, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            else recon_tc_kernel<true, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
         } else {
-            recon_tc_kernel<false><<<2 * nclusters, TC_THREADS, st->smem_ca, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
+            if (tp.trace) recon_tc_kernel<false, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
+            else recon_tc_kernel<false, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
         }
         count_launch(1);
         FB_CUDA(cudaGetLastError());

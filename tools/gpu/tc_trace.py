@@ -49,4 +49,5 @@ names = {0: "mma:start", 1: "mma:done", 2: "epi:d_full", 3: "epi:tmem_read_done"
 for it in range(8):
     ev = sorted((int(t[it, k] - t0), names[k]) for k in names if t[it, k])
     print(f"tile {it}: " + "  ".join(f"{n}@{c}" for c, n in ev))
-    print(f"         mma wait b_full {int(t[it,15])} cyc, wait a_full {int(t[it,16])} cyc")
+    print(f"         mma wait b_full {int(t[it,15])} cyc, wait a_full {int(t[it,16])} cyc; drain chunk starts (rel. d_full) "
+          + " ".join(str(int(t[it, k] - t[it, 2])) for k in range(17, 24) if t[it, k]) + f"; staging-box waits {int(t[it,24])} cyc")
