@@ -12,10 +12,18 @@ is used only for the barrier and the max-over-ranks of the timed region.
 
   value     : device-resident throughput (inputs already in HBM), K steps, CUDA events, max over ranks
   e2e       : same metric through the host-pointer C-ABI call fibers_gqi_rec (what Julia ccalls):
-              pinned HOST buffers in, HOST buffers out, H2D + D2H inside the timed region
+              pinned HOST buffers in, HOST buffers out, H2D + D2H inside the timed region; reported beside the
+              box's measured PCIe ceiling (concurrent H2D + D2H of pinned buffers) as `frac_of_ceiling`
+  e2e_pageable : the same call on ordinary pageable numpy arrays (what a Julia Array is): the library's pinned
+              bounce ring + host copy threads (N = 1 only)
+  e2e_no_odf: the same call with odf = NULL (peaks + QA only, what stream() consumes)
   roofline  : dominant kernel (fused GQI contraction + peak epilogue) against the measured HBM peak
   cpu_baseline / --impl reference : the C/OpenMP port of the reference voxel loop (oracle/), all host
               cores, on a bounded z-sub-slab of the same workload
+  zslab / batch (N > 1, rank 0 after the weak-scaling legs, other ranks idle): the IN-LIBRARY multi-GPU paths,
+              fibers_gqi_rec(..., ngpu = N) on ONE cfg2 subject (strong scaling, host gather, host odfmax reduce) and
+              fibers_dti_gqi_fit_batch on 16 cfg2-shaped subjects (BASELINE cfg4) over the N GPUs
+  --mode zslab|batch [--config cfg2|cfg5] : only those paths, from a single process (python bench.py --mode zslab --gpus 8)
 """
 from __future__ import annotations
 
@@ -222,6 +230,126 @@ def run_cpu_reference(shape, steps, warmup, nz_sample=None, budget_s=12.0):
     return nv / dt, dt * 1e3, cores, f"z-sub-slab {nx}x{ny}x{nz_sample} of {nx}x{ny}x{nz} ({nv} voxels/step), C/OpenMP port of the reference loop, {cores} threads"
 
 
+# ----------------------------------------------------------------------------------------------
+# host-side helpers of the end-to-end legs
+# ----------------------------------------------------------------------------------------------
+def pcie_ceiling(torch, dev_index, nbytes=1 << 29, reps=4):
+    """What this box moves between PINNED host memory and one GPU with H2D and D2H running at the same time
+    (GB/s each way): the ceiling of every host-pointer call.  tools/gpu/pcie_probe.py is the long form."""
+    dev = torch.device("cuda", dev_index)
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev); d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(n):
+        for _ in range(n):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize(dev)
+    run(1)
+    t = time.perf_counter(); run(reps); dt = time.perf_counter() - t
+    return nbytes * reps / dt / 1e9
+
+
+class HostSubject:
+    """One subject's host arrays for the C-ABI calls: pinned (torch) or pageable (numpy, Fortran order)."""
+
+    def __init__(self, torch, shape, nvol, pinned, dwi_src=None, want_odf=True, want_dti=False, share_dwi=None):
+        nvox = int(np.prod(shape))
+        self.keep = []
+
+        def alloc(rows, dtype=np.float32):
+            if pinned:
+                t = torch.empty((rows, nvox) if rows > 1 else (nvox,), dtype={np.float32: torch.float32, np.uint8: torch.uint8}[dtype], pin_memory=True)
+                self.keep.append(t)
+                return t.data_ptr(), t
+            a = np.zeros((nvox, rows) if rows > 1 else (nvox,), dtype, order="F")     # [nvox, frames] column-major == [frames][nvox]
+            self.keep.append(a)
+            return a.ctypes.data, a
+        if share_dwi is not None:
+            self.dwi_ptr, self.dwi = share_dwi.dwi_ptr, share_dwi.dwi
+            self.mask_ptr, self.mask = share_dwi.mask_ptr, share_dwi.mask
+        else:
+            self.dwi_ptr, self.dwi = alloc(nvol)
+            self.mask_ptr, self.mask = alloc(1, np.uint8)
+            if pinned:
+                self.dwi.copy_(dwi_src[0][:, :nvox]); self.mask.copy_(dwi_src[1])
+            else:
+                self.dwi.T[...] = dwi_src[0][:, :nvox].cpu().numpy(); self.mask[...] = dwi_src[1].cpu().numpy()
+        self.odf_ptr = alloc(M_VERT)[0] if want_odf else None
+        self.peak = [alloc(3)[0] for _ in range(3)]
+        self.qa = [alloc(1) for _ in range(3)]
+        self.dti = [alloc(n)[0] for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)] if want_dti else None
+        self.h2d = nvox * (4 * nvol + 1)
+        self.d2h = nvox * 4 * ((M_VERT if want_odf else 0) + 9 + 3 + (16 if want_dti else 0))
+
+    def gqi_out(self):
+        return [self.odf_ptr] + self.peak + [q[0] for q in self.qa]
+
+
+def timed_calls(fn, nwarm, nrep):
+    for _ in range(nwarm):
+        fn()
+    ts = []
+    for _ in range(nrep):
+        t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), float(np.mean(ts))
+
+
+def library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, dwi_src, nsub=16, reps=2, config="cfg2"):
+    """The in-library multi-GPU paths from ONE process (what a Julia session with FIBERS_CUDA_NGPU=N gets):
+       zslab : fibers_gqi_rec(..., ngpu) on one subject = strong scaling, z-slabs balanced by mask count, host gather,
+               host-side odfmax reduce (north_star "slab partitioner")
+       batch : fibers_dti_gqi_fit_batch on `nsub` subjects (BASELINE cfg4), subjects queued over the GPUs."""
+    import ctypes as C
+    L = F._lib.lib()
+    nvox, nvol = int(np.prod(shape)), int(bval.shape[0])
+    V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces); bv = np.asfortranarray(bvec)
+    F.device.set_devices(list(range(ngpu)))
+    out = {}
+    subj = HostSubject(torch, shape, nvol, True, dwi_src)
+
+    def zslab(s=subj):
+        F._lib.check(L.fibers_gqi_rec(s.dwi_ptr, 0, s.mask_ptr, shape[0], shape[1], shape[2], nvol, F._lib.ptr(bval), F._lib.ptr(bv),
+                                      F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25, *s.gqi_out(), None, ngpu))
+    med, mean = timed_calls(zslab, 2, max(3, reps))
+    out["zslab"] = {"api": f"fibers_gqi_rec(..., ngpu={ngpu}): one {config} subject, z-slabs over {ngpu} GPUs, host gather + host odfmax reduce, no collective",
+                    "scaling": "strong", "value": nvox / med, "unit": "voxels/s", "ms_per_call": med * 1e3, "ms_per_call_mean": mean * 1e3,
+                    "h2d_bytes": subj.h2d, "d2h_bytes": subj.d2h, "host_memory": "pinned"}
+    # ---- cfg4: 16 subjects, DTI + GQI each.  The subjects share ONE synthetic DWI buffer (read-only); every subject owns its
+    #      outputs.  Full outputs need 16 x 5.1 GB of pinned host memory: attempted only when the box has the RAM to spare.
+    def batch_leg(want_odf):
+        subs = [HostSubject(torch, shape, nvol, True, want_odf=want_odf, want_dti=True, share_dwi=subj) for _ in range(nsub)]
+        parr = lambda xs: (C.c_void_p * len(xs))(*xs)
+        dwi_t = parr([s.dwi_ptr for s in subs]); mask_t = parr([s.mask_ptr for s in subs])
+        dti_t = parr([p for s in subs for p in s.dti]); gqi_t = parr([p for s in subs for p in s.gqi_out()])
+
+        def call():
+            F._lib.check(L.fibers_dti_gqi_fit_batch(nsub, dwi_t, mask_t, shape[0], shape[1], shape[2], nvol, F._lib.ptr(bval), F._lib.ptr(bv),
+                                                    dti_t, F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25, gqi_t, ngpu))
+        med, mean = timed_calls(call, 1, reps)
+        return {"api": f"fibers_dti_gqi_fit_batch: {nsub} {config}-shaped subjects, DTI + GQI each, queued over {ngpu} GPUs" + ("" if want_odf else ", odf = NULL"),
+                "subjects": nsub, "value": nsub * nvox / med, "unit": "voxels/s", "s_per_batch": med, "ms_per_subject": med / nsub * 1e3,
+                "h2d_bytes": nsub * subs[0].h2d, "d2h_bytes": nsub * subs[0].d2h, "host_memory": "pinned; the subjects share one DWI buffer, outputs are per subject"}
+    try:
+        out["batch_no_odf"] = batch_leg(False)
+    except Exception as ex:          # noqa: BLE001
+        out["batch_no_odf"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    try:
+        import psutil
+        need = nsub * nvox * 4 * (M_VERT + 28) * 1.15
+        if psutil.virtual_memory().available > need + 64e9:
+            out["batch"] = batch_leg(True)
+        else:
+            out["batch"] = {"skipped": f"full outputs need {need / 1e9:.0f} GB of pinned host memory; available {psutil.virtual_memory().available / 1e9:.0f} GB"}
+    except Exception as ex:          # noqa: BLE001
+        out["batch"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+    L.fibers_cuda_release_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -233,8 +361,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--mask", default="ones", choices=["ones", "ellipsoid"],
                     help="ones: roofline run (every voxel computed); ellipsoid: ~25 %% fill brain-like mask (SURVEY 8d second run)")
+    ap.add_argument("--mode", default="default", choices=["default", "zslab", "batch"],
+                    help="zslab / batch: only the in-library multi-GPU legs, single process over --gpus devices")
+    ap.add_argument("--subjects", type=int, default=16)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-multi", action="store_true", help="skip the in-library zslab / batch legs at N > 1")
     args = ap.parse_args()
     shape = tuple(int(x) for x in args.shape.split(","))
     nvox = int(np.prod(shape))
@@ -258,7 +390,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0,
+                "gpu_launches": 0, "host_cores": cores,
                 "note": "Fibers.jl is pure Julia and Julia is not installed: this is the C/OpenMP restatement of its voxel loop, not Fibers.jl itself"}
         print(json.dumps(line))
         return 0
@@ -271,11 +403,26 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: libfibers_cuda has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    D.set_kernel(args.kernel)
+
+    if args.mode != "default":              # in-library multi-GPU legs only (single process, no torch.distributed)
+        ngpu = min(args.gpus, F.device_count())
+        dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000, dev)
+        mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
+        legs = library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, (dwi, mask), nsub=args.subjects, reps=max(2, args.e2e_steps // 2))
+        key = "zslab" if args.mode == "zslab" else ("batch" if "value" in legs.get("batch", {}) else "batch_no_odf")
+        line = {"metric": "voxels/sec (GQI recon+peaks)" if args.mode == "zslab" else "voxels/sec (DTI fit + GQI recon+peaks, batch of subjects)",
+                "value": legs[key].get("value"), "unit": "voxels/s", "n_gpus": ngpu, "mode": args.mode, "scaling": "strong",
+                "higher_is_better": True, "dtype": "f32", "data": "synthetic", "config": config, "host_cores": len(os.sched_getaffinity(0)), **legs}
+        print(json.dumps(line))
+        return 0
+
     dist = None
+    side = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    D.set_kernel(args.kernel)
+        side = dist.new_group(backend="gloo")          # host-side barrier for the legs in which only rank 0 works (no kernel spinning on the idle GPUs)
     D.set_devices([local_rank])
 
     pitch = (nvox + 63) // 64 * 64          # frame pitch of the DWI slab and of the outputs: 256-byte aligned rows
@@ -324,15 +471,15 @@ def main():
     barrier()
     launches = D.launch_count() - l0
     clocks = sampler.stop()
-    elapsed_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    elapsed_ms = F.batch.reduce_max(elapsed_ms, dist if world > 1 else None, dev)      # max over ranks
-    ms_per_step = elapsed_ms / steps
-    value = world * nvox / (ms_per_step * 1e-3)
+    dd = dist if world > 1 else None
+    # whole-job throughput = voxels of all ranks / max over ranks of the timed region (device clock)
+    value = F.batch.whole_job_throughput(steps * nvox, e0.elapsed_time(e1) * 1e-3, dd, dev)
+    ms_per_step = world * nvox / value * 1e3
 
     # One extra, untimed launch with the kernel's own trace switched on: SM cycles (clock64) against wall-clock
-    # nanoseconds (globaltimer) over the kernel.  The tensor-core kernel runs at a lower effective SM clock than the
-    # NVML figure sampled above (no throttle reason is raised for it); the JSON line reports both.
+    # nanoseconds (globaltimer) over the kernel.  Under tensor load the part runs below the NVML figure sampled above
+    # (no throttle reason is raised for it); the JSON line reports both.
     if rank == 0 and plan.kernel == "tc":
         import tempfile
         tf = os.path.join(tempfile.gettempdir(), f"fibers_tc_trace_{os.getpid()}.bin")
@@ -354,35 +501,35 @@ def main():
     # ---- end to end through the host-pointer C ABI (what the Julia wrapper ccalls) ----------
     e2e = None
     e2e_error = None
+    extra = {}
     if not args.no_e2e:
         # Set-up can fail on a box that cannot pin 9 GB of host memory per rank: every rank then agrees (one reduction)
         # to report "e2e": null instead of hanging in a barrier or losing the whole line.
         e2e_step = None
-        try:
-            h_dwi = torch.empty((nvol, nvox), dtype=torch.float32, pin_memory=True)
-            h_dwi.copy_(dwi[:, :nvox])
-            torch.cuda.synchronize()
-            del dwi, odf, peak
-            torch.cuda.empty_cache()
-            h_mask = torch.empty(nvox, dtype=torch.uint8, pin_memory=True); h_mask.copy_(mask)
-            h_odf = torch.empty((M_VERT, nvox), dtype=torch.float32, pin_memory=True)
-            h_peak = [torch.empty((3, nvox), dtype=torch.float32, pin_memory=True) for _ in range(3)]
-            h_qa = [torch.empty(nvox, dtype=torch.float32, pin_memory=True) for _ in range(3)]
-            L = F._lib.lib()
-            V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces)
-            bv = np.asfortranarray(bvec)
+        L = F._lib.lib()
+        V = np.asfortranarray(F.sphere_642.vertices); Fc = np.asfortranarray(F.sphere_642.faces)
+        bv = np.asfortranarray(bvec)
 
-            def e2e_step():
-                F._lib.check(L.fibers_gqi_rec(h_dwi.data_ptr(), 0, h_mask.data_ptr(), shape[0], shape[1], shape[2], nvol,
-                                              F._lib.ptr(bval), F._lib.ptr(bv), F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc),
-                                              Fc.shape[0], 1.25, h_odf.data_ptr(), *[p.data_ptr() for p in h_peak],
-                                              *[q.data_ptr() for q in h_qa], None, 1))
+        def call(s, odf=True):
+            F._lib.check(L.fibers_gqi_rec(s.dwi_ptr, 0, s.mask_ptr, shape[0], shape[1], shape[2], nvol, F._lib.ptr(bval), F._lib.ptr(bv),
+                                          F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25,
+                                          s.odf_ptr if odf else None, *s.peak, *[q[0] for q in s.qa], None, 1))
+        try:
+            ceiling = pcie_ceiling(torch, local_rank)
+            subj = HostSubject(torch, shape, nvol, True, (dwi, mask))
+            torch.cuda.synchronize()
+            dwi_keep = dwi if (world == 1 or rank == 0) else None
+            del odf, peak
+            if dwi_keep is None:
+                del dwi
+            torch.cuda.empty_cache()
+            e2e_step = lambda: call(subj)
             e2e_step(); e2e_step()                  # warm-up: first-touch of the pinned pages, context cache
             ok = 1.0
         except Exception as ex:                     # noqa: BLE001 - reported in the JSON line
             ok = 0.0
             e2e_error = f"{type(ex).__name__}: {ex}"[:200]
-        ok_all = -F.batch.reduce_max(-ok, dist if world > 1 else None, dev)      # min over ranks
+        ok_all = -F.batch.reduce_max(-ok, dd, dev)      # min over ranks
         if ok_all > 0.5:
             barrier()
             per_step = []
@@ -392,11 +539,45 @@ def main():
                 per_step.append(time.perf_counter() - t0)
             # host / PCIe side of a shared box is noisy: the median step is reported, the mean is kept beside it
             dt = float(np.median(per_step)); dt_mean = float(np.mean(per_step))
-            dt = F.batch.reduce_max(dt, dist if world > 1 else None, dev)
-            e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": nvox * (4 * nvol + 1),
-                   "d2h_bytes_per_step": nvox * 4 * (M_VERT + 9 + 3), "ms_per_step": dt * 1e3, "ms_per_step_mean": dt_mean * 1e3,
+            dt = F.batch.reduce_max(dt, dd, dev)
+            ceil_min = -F.batch.reduce_max(-ceiling, dd, dev)          # the slowest rank's link while ALL ranks copy
+            floor_ms = max(subj.h2d, subj.d2h) / ceil_min / 1e6
+            e2e = {"value": world * nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": subj.h2d,
+                   "d2h_bytes_per_step": subj.d2h, "ms_per_step": dt * 1e3, "ms_per_step_mean": dt_mean * 1e3,
                    "statistic": "median of per-step wall times", "steps": args.e2e_steps,
-                   "api": "fibers_gqi_rec (host pointers, pinned buffers)"}
+                   "api": "fibers_gqi_rec (host pointers, pinned buffers)",
+                   "pcie_ceiling_GBps_each_way": ceil_min, "ceiling_ms_per_step": floor_ms, "frac_of_ceiling": floor_ms / (dt * 1e3),
+                   "ceiling_note": "concurrent H2D + D2H of 512 MiB pinned buffers on this rank's GPU, measured in this run" +
+                                   (" by every rank one after the other (not all links at once: see tools/gpu/pcie_probe.py)" if world > 1 else "")}
+            if world == 1:
+                try:                                # odf = NULL: peaks + QA only
+                    med, _ = timed_calls(lambda: call(subj, odf=False), 1, 3)
+                    extra["e2e_no_odf"] = {"value": nvox / med, "unit": "voxels/s", "ms_per_step": med * 1e3, "h2d_bytes_per_step": subj.h2d,
+                                           "d2h_bytes_per_step": nvox * 4 * 12, "api": "fibers_gqi_rec(odf = NULL): peaks and QA only (src/stream.jl:76-173 reads nothing else)"}
+                except Exception as ex:             # noqa: BLE001
+                    extra["e2e_no_odf"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+                try:                                # pageable numpy arrays = what a Julia Array is
+                    pg = HostSubject(torch, shape, nvol, False, (dwi_keep, mask))
+                    med, mean = timed_calls(lambda: call(pg), 1, 3)
+                    extra["e2e_pageable"] = {"value": nvox / med, "unit": "voxels/s", "ms_per_step": med * 1e3, "ms_per_step_mean": mean * 1e3,
+                                             "h2d_bytes_per_step": pg.h2d, "d2h_bytes_per_step": pg.d2h,
+                                             "api": "fibers_gqi_rec on pageable numpy Fortran arrays (what ccall passes, src/mri.jl:249-255): pinned bounce ring + host copy threads",
+                                             "copy_threads": int(os.environ.get("FIBERS_CUDA_COPY_THREADS", "8"))}
+                    del pg
+                except Exception as ex:             # noqa: BLE001
+                    extra["e2e_pageable"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+            # ---- N > 1: the in-library multi-GPU paths, rank 0 alone (the other ranks release their GPUs and wait on the host)
+            if world > 1 and not args.no_multi:
+                L.fibers_cuda_release_cache()
+                del subj
+                torch.cuda.empty_cache()
+                dist.barrier(group=side)
+                if rank == 0:
+                    try:
+                        extra.update(library_multi_gpu_legs(torch, F, shape, bval, bvec, world, (dwi_keep, mask), nsub=args.subjects))
+                    except Exception as ex:         # noqa: BLE001
+                        extra["zslab"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+                dist.barrier(group=side)
         elif e2e_error is None:
             e2e_error = "end-to-end set-up failed on another rank"
 
@@ -411,9 +592,11 @@ def main():
         line = {"metric": "voxels/sec (GQI recon+peaks)", "value": value, "unit": "voxels/s", "n_gpus": world,
                 "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "kernel": plan.kernel, "gpu_launches": int(launches), "clocks": clocks,
+                "kernel": plan.kernel, "gpu_launches": int(launches), "clocks": clocks, "host_cores": len(os.sched_getaffinity(0)),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                             "frac": achieved / peak_gbs, "traffic": profiled_traffic(plan.kernel, nvox) if fill == 1.0 else None, "peak_source": peak_src,
+                             "frac": achieved / peak_gbs, "traffic": profiled_traffic(plan.kernel, nvox) if fill == 1.0 else None,
+                             "traffic_source": "committed ncu --set full capture (profiles/roofline_traffic.json), not measured in this run",
+                             "peak_source": peak_src,
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_voxel": bpv_avg, "mask_fill": fill,
                              "algorithmic_tflops": 2.0 * nvol * M_VERT * fill * nvox / (kern_ms * 1e-3) / 1e12}}
         if e2e:
@@ -421,12 +604,13 @@ def main():
         elif e2e_error:
             line["e2e"] = None
             line["e2e_error"] = e2e_error
+        line.update(extra)
         if not args.no_cpu and world == 1:              # reported baseline: rank 0 at N = 1 only
             vps, ms, cores, sample = run_cpu_reference(shape, 2, 1, budget_s=12.0)
             line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=side)
         dist.destroy_process_group()
     return 0
 

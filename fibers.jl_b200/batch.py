@@ -1,4 +1,4 @@
-"""Host-side helpers for the one-process-per-GPU drivers (bench.py, batch-of-subjects runs).
+"""Host-side helpers for the one-process-per-GPU driver (bench.py under torchrun).
 
 The reconstruction path shards by subject / z-slab with NO data-path collective; the only things
 ranks exchange are a barrier and scalar reductions (max of the timed region, voxel counts), which
@@ -13,24 +13,6 @@ def rank_info():
     """(rank, world_size, local_rank) from the torchrun environment (defaults: single process)."""
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
             int(os.environ.get("LOCAL_RANK", "0")))
-
-
-def assign_subjects(nsub: int, world: int, rank: int) -> list[int]:
-    """Subjects of a batch handled by `rank`: contiguous blocks, sizes differ by at most one
-    (cfg4: 16 HCP-shaped subjects over 2/4/8 GPUs)."""
-    if world < 1 or not (0 <= rank < world) or nsub < 0:
-        raise ValueError("bad rank/world/nsub")
-    base, extra = divmod(nsub, world)
-    start = rank * base + min(rank, extra)
-    return list(range(start, start + base + (1 if rank < extra else 0)))
-
-
-def slab_ranges(nz: int, nxny: int, world: int) -> list[tuple[int, int]]:
-    """Voxel ranges of `world` contiguous, non-empty z-slabs of a volume (uniform split; the
-    library's own partitioner additionally balances by masked-voxel count)."""
-    world = min(world, nz)
-    cuts = [round(g * nz / world) for g in range(world + 1)]
-    return [(cuts[g] * nxny, cuts[g + 1] * nxny) for g in range(world)]
 
 
 def reduce_max(value: float, dist=None, device=None) -> float:

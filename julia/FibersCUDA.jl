@@ -19,7 +19,7 @@ module FibersCUDA
 
 using ..Fibers: MRI, ODF, DTI, GQI, DSI, sphere_642
 
-export adc_fit, dti_fit, gqi_rec, dsi_rec, dti_gqi_fit, device_count
+export adc_fit, dti_fit, gqi_rec, dsi_rec, dti_gqi_fit, dti_gqi_fit_batch, device_count
 
 const libfibers = get(ENV, "FIBERS_CUDA_LIB", "libfibers_cuda.so")
 const NGPU = Ref{Cint}(parse(Cint, get(ENV, "FIBERS_CUDA_NGPU", "1")))
@@ -43,12 +43,42 @@ dtype_code(::Type{UInt8})   = Cint(5)
 mask_u8(mask::MRI) = UInt8.(reshape(mask.vol, size(mask.vol)[1:3]) .!= 0)    # masks may be [nx,ny,nz,1] label maps
 
 """
+The C ABI receives bare pointers and takes every length from the dwi volume: a mask of another size or a short
+b-table would be read / written out of bounds.  The reference throws BoundsError / DimensionMismatch in these
+cases (its loops index the arrays); the wrapper checks explicitly and raises the same kind of exception.
+"""
+function check_dims(dwi::MRI, mask::MRI; need_bvec::Bool=true, odf_dirs::Union{ODF,Nothing}=nothing)
+  ndims(dwi.vol) == 4 || throw(DimensionMismatch("dwi.vol must be [nx, ny, nz, nvol], got size $(size(dwi.vol))"))
+  nx, ny, nz, nvol = size(dwi.vol)
+  msz = size(mask.vol)
+  (length(msz) >= 3 && msz[1:3] == (nx, ny, nz) && prod(msz) == nx * ny * nz) ||
+    throw(DimensionMismatch("mask size $(msz) does not match dwi size $((nx, ny, nz))"))
+  length(dwi.bval) == nvol ||
+    throw(DimensionMismatch("b-value table has $(length(dwi.bval)) entries for $nvol volumes"))
+  eltype(dwi.bval) == Float32 || throw(ArgumentError("dwi.bval must be Vector{Float32} (as mri_read returns it)"))
+  if need_bvec
+    size(dwi.bvec) == (nvol, 3) ||
+      throw(DimensionMismatch("gradient table has size $(size(dwi.bvec)), expected ($nvol, 3)"))
+  end
+  if odf_dirs !== nothing
+    nv2 = size(odf_dirs.vertices, 1)
+    (size(odf_dirs.vertices, 2) == 3 && iseven(nv2) && nv2 > 0) ||
+      throw(DimensionMismatch("odf_dirs.vertices must be [2M, 3], got $(size(odf_dirs.vertices))"))
+    eltype(odf_dirs.vertices) == Float32 || throw(ArgumentError("odf_dirs.vertices must be Matrix{Float32}"))
+    size(odf_dirs.faces, 2) == 3 || throw(DimensionMismatch("odf_dirs.faces must be [F, 3]"))
+    all(f -> 1 <= f <= nv2, odf_dirs.faces) || throw(BoundsError(odf_dirs.vertices, maximum(odf_dirs.faces)))
+  end
+  return nx, ny, nz, nvol
+end
+
+"""
     adc_fit(dwi::MRI, mask::MRI)
 
 GPU version of `Fibers.adc_fit` (src/dti.jl:164-213).
 """
 function adc_fit(dwi::MRI, mask::MRI)
   isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
+  check_dims(dwi, mask; need_bvec=false)
   adc = MRI(mask, 1, Float32)
   s0  = MRI(mask, 1, Float32)
   vol = dwi.vol::Array{Float32,4}                      # reference method signature is Float32-only
@@ -68,6 +98,7 @@ GPU version of `Fibers.dti_fit` / `dti_fit_ls` (src/dti.jl:221-316, maps :325-33
 function dti_fit(dwi::MRI, mask::MRI)
   isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
   isempty(dwi.bvec) && error("Missing gradient table from input DWI structure")
+  check_dims(dwi, mask)
   S0    = MRI(mask, 1, Float32); Eval1 = MRI(mask, 1, Float32)
   Eval2 = MRI(mask, 1, Float32); Eval3 = MRI(mask, 1, Float32)
   Evec1 = MRI(mask, 3, Float32); Evec2 = MRI(mask, 3, Float32); Evec3 = MRI(mask, 3, Float32)
@@ -91,12 +122,15 @@ end
 
 GPU version of `Fibers.gqi_rec` (src/gqi.jl:109-171, peaks :180-201).
 """
-function gqi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
+function gqi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25); want_odf::Bool=true)
   isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
   isempty(dwi.bvec) && error("Missing gradient table from input DWI structure")
+  check_dims(dwi, mask; odf_dirs=odf_dirs)
   npeak = 3
   nvert = div(size(odf_dirs.vertices, 1), 2)
-  odf  = MRI(mask, nvert, Float32)
+  # want_odf=false (extension): the ODF is formed on the GPU for the peak search but not copied back; `.odf` is then
+  # a 1-frame placeholder.  `stream` reads peaks and QA only (src/stream.jl:76-173).
+  odf  = MRI(mask, want_odf ? nvert : 1, Float32)
   peak = [MRI(mask, 3, Float32) for _ in 1:npeak]
   qa   = [MRI(mask, 1, Float32) for _ in 1:npeak]
   nx, ny, nz, nvol = size(dwi.vol)
@@ -110,7 +144,8 @@ function gqi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Floa
                Ptr{Int16}, Cint),
               dwi.vol, dtype_code(eltype(dwi.vol)), m, nx, ny, nz, nvol, dwi.bval, bvec,
               odf_dirs.vertices, size(odf_dirs.vertices, 1), faces, size(faces, 1), σ,
-              odf.vol, peak[1].vol, peak[2].vol, peak[3].vol, qa[1].vol, qa[2].vol, qa[3].vol,
+              want_odf ? pointer(odf.vol) : Ptr{Float32}(C_NULL),
+              peak[1].vol, peak[2].vol, peak[3].vol, qa[1].vol, qa[2].vol, qa[3].vol,
               C_NULL, NGPU[]))
   return GQI(odf, peak, qa)
 end
@@ -124,6 +159,7 @@ copied to the GPU once and feeds both kernels); returns `(DTI, GQI)`, bit-identi
 function dti_gqi_fit(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
   isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
   isempty(dwi.bvec) && error("Missing gradient table from input DWI structure")
+  check_dims(dwi, mask; odf_dirs=odf_dirs)
   S0    = MRI(mask, 1, Float32); Eval1 = MRI(mask, 1, Float32)
   Eval2 = MRI(mask, 1, Float32); Eval3 = MRI(mask, 1, Float32)
   Evec1 = MRI(mask, 3, Float32); Evec2 = MRI(mask, 3, Float32); Evec3 = MRI(mask, 3, Float32)
@@ -158,6 +194,7 @@ GPU version of `Fibers.dsi_rec` (src/dsi.jl:171-270).
 function dsi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, hann_width::Int=32)
   isempty(dwi.bval) && error("Missing b-value table from input DWI structure")
   isempty(dwi.bvec) && error("Missing gradient table from input DWI structure")
+  check_dims(dwi, mask; odf_dirs=odf_dirs)
   npeak = 3
   nvert = div(size(odf_dirs.vertices, 1), 2)
   nx, ny, nz, nvol = size(dwi.vol)
@@ -178,6 +215,49 @@ function dsi_rec(dwi::MRI, mask::MRI, odf_dirs::ODF=sphere_642, hann_width::Int=
               pdf.vol, odf.vol, peak[1].vol, peak[2].vol, peak[3].vol, qa[1].vol, qa[2].vol, qa[3].vol,
               C_NULL, NGPU[]))
   return DSI(pdf, odf, peak, qa)
+end
+
+"""
+    dti_gqi_fit_batch(dwis::Vector{MRI}, masks::Vector{MRI}, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
+
+`dti_gqi_fit` of a batch of subjects that share one protocol and one volume shape in ONE library call: the
+subjects are queued over `FIBERS_CUDA_NGPU` devices and every device overlaps the transfers of the next subject
+with the kernels of the current one.  Returns a vector of `(DTI, GQI)`.
+"""
+function dti_gqi_fit_batch(dwis::Vector{MRI}, masks::Vector{MRI}, odf_dirs::ODF=sphere_642, σ::Float32=Float32(1.25))
+  length(dwis) == length(masks) || throw(DimensionMismatch("dwis and masks must have the same length"))
+  isempty(dwis) && return Tuple{DTI,GQI}[]
+  d1 = dwis[1]
+  isempty(d1.bval) && error("Missing b-value table from input DWI structure")
+  isempty(d1.bvec) && error("Missing gradient table from input DWI structure")
+  for (d, m) in zip(dwis, masks)
+    check_dims(d, m; odf_dirs=odf_dirs)
+    (size(d.vol) == size(d1.vol) && d.bval == d1.bval && d.bvec == d1.bvec) ||
+      throw(DimensionMismatch("all subjects of a batch must share the volume shape and the b-table"))
+  end
+  nx, ny, nz, nvol = size(d1.vol)
+  nvert = div(size(odf_dirs.vertices, 1), 2)
+  vols = [d.vol::Array{Float32,4} for d in dwis]
+  ms   = [mask_u8(m) for m in masks]
+  res  = [(DTI(MRI(m, 1, Float32), MRI(m, 1, Float32), MRI(m, 1, Float32), MRI(m, 1, Float32), MRI(m, 3, Float32),
+               MRI(m, 3, Float32), MRI(m, 3, Float32), MRI(m, 1, Float32), MRI(m, 1, Float32), MRI(m, 1, Float32)),
+           GQI(MRI(m, nvert, Float32), [MRI(m, 3, Float32) for _ in 1:3], [MRI(m, 1, Float32) for _ in 1:3])) for m in masks]
+  dti_tab = Ptr{Float32}[]; gqi_tab = Ptr{Float32}[]
+  for (d, g) in res
+    append!(dti_tab, pointer.([d.s0.vol, d.eigval1.vol, d.eigval2.vol, d.eigval3.vol, d.eigvec1.vol, d.eigvec2.vol,
+                               d.eigvec3.vol, d.rd.vol, d.md.vol, d.fa.vol]))
+    append!(gqi_tab, pointer.([g.odf.vol, g.peak[1].vol, g.peak[2].vol, g.peak[3].vol, g.qa[1].vol, g.qa[2].vol, g.qa[3].vol]))
+  end
+  bvec  = Matrix{Float32}(d1.bvec)
+  faces = Matrix{Int32}(odf_dirs.faces)
+  GC.@preserve vols ms res begin                        # the pointer tables do not root the arrays they point to
+    check(ccall((:fibers_dti_gqi_fit_batch, libfibers), Cint,
+                (Cint, Ptr{Ptr{Float32}}, Ptr{Ptr{UInt8}}, Cint, Cint, Cint, Cint, Ptr{Float32}, Ptr{Float32},
+                 Ptr{Ptr{Float32}}, Ptr{Float32}, Cint, Ptr{Int32}, Cint, Cfloat, Ptr{Ptr{Float32}}, Cint),
+                length(dwis), pointer.(vols), pointer.(ms), nx, ny, nz, nvol, d1.bval, bvec,
+                dti_tab, odf_dirs.vertices, size(odf_dirs.vertices, 1), faces, size(faces, 1), σ, gqi_tab, NGPU[]))
+  end
+  return res
 end
 
 end # module

@@ -45,8 +45,13 @@ def test_our_arm_prints_one_contract_line_on_the_gpu():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 64 * 32 * 288 * 4 + 64 * 64 * 32
     assert e["d2h_bytes_per_step"] == 64 * 64 * 32 * 4 * (321 + 9 + 3)
+    assert 0 < e["frac_of_ceiling"] <= 1.2 and e["pcie_ceiling_GBps_each_way"] > 1
     c = d["clocks"]
     assert c["sm_max_mhz"] > 0 and isinstance(c["reasons"], list)
+    # extra legs of the N = 1 line: pageable caller arrays (bounce ring) and odf = NULL
+    assert d["e2e_pageable"]["value"] > 0 and d["e2e_pageable"]["d2h_bytes_per_step"] == e["d2h_bytes_per_step"]
+    assert d["e2e_no_odf"]["value"] > 0 and d["e2e_no_odf"]["d2h_bytes_per_step"] == 64 * 64 * 32 * 4 * 12
+    assert d["roofline"]["traffic_source"].startswith("committed ncu")
 
 
 def test_reference_arm_under_torchrun_prints_once():

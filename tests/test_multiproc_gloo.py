@@ -1,5 +1,5 @@
-"""world_size-2 CPU tests (gloo) of the N > 1 host logic: subject/slab sharding, max-over-ranks
-timing and whole-job throughput, and the reference arm's "rank 0 only" rule."""
+"""world_size-2 CPU tests (gloo) of the N > 1 host logic: max-over-ranks timing and whole-job throughput as
+bench.py computes them, the library's z-slab partitioner, and the reference arm's "rank 0 only" rule."""
 import json
 import os
 import subprocess
@@ -17,7 +17,7 @@ import torch, torch.distributed as dist
 from fibers_jl_b200 import batch
 rank, world, local = batch.rank_info()
 dist.init_process_group("gloo", rank=rank, world_size=world)
-subs = batch.assign_subjects(5, world, rank)
+subs = [0, 1, 2] if rank == 0 else [3, 4]
 secs = 1.0 + rank                      # rank 1 is the slow one
 units = 100.0 * len(subs)
 worst = batch.reduce_max(secs, dist)
@@ -44,21 +44,26 @@ def test_gloo_world2_reductions(tmp_path):
     assert out["worst"] == 2.0 and out["total"] == 500.0 and out["thr"] == 250.0
 
 
-def test_assign_subjects_and_slabs():
+def test_library_partitioner_balances_by_mask_count():
+    """fibers_host_partition_slabs (what fibers_*(..., ngpu) and the batch queue use): contiguous, non-empty z-slabs that
+    cover the volume, balanced by masked-voxel count rather than by z."""
     sys.path.insert(0, ROOT)
-    from fibers_jl_b200 import batch
-    for nsub in (0, 1, 7, 16):
-        for world in (1, 2, 4, 8):
-            got = [batch.assign_subjects(nsub, world, r) for r in range(world)]
-            assert sorted(sum(got, [])) == list(range(nsub))
-            sizes = [len(g) for g in got]
-            assert max(sizes) - min(sizes) <= 1
-    for nz, world in ((145, 8), (3, 8), (40, 2)):
-        r = batch.slab_ranges(nz, 100, world)
-        assert r[0][0] == 0 and r[-1][1] == nz * 100
-        assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and all(b > a for a, b in r)
-    with pytest.raises(ValueError):
-        batch.assign_subjects(4, 2, 2)
+    from fibers_jl_b200 import _lib, phantom
+    L = _lib.lib()
+    for shape, ngpu in (((20, 16, 29), 8), ((9, 7, 3), 8), ((30, 30, 40), 2), ((12, 12, 24), 4)):
+        mask = phantom.ellipsoid_mask(shape, 0.4)
+        nxny, nz = shape[0] * shape[1], shape[2]
+        n = min(ngpu, nz)
+        out = np.zeros(2 * n, np.int64)
+        assert L.fibers_host_partition_slabs(_lib.ptr(mask), nxny, nz, ngpu, _lib.ptr(out)) == 0
+        r = out.reshape(n, 2)
+        assert r[0, 0] == 0 and r[-1, 1] == nxny * nz
+        assert np.all(r[1:, 0] == r[:-1, 1]) and np.all(r[:, 1] > r[:, 0]) and np.all(r % nxny == 0)
+        if nz >= 4 * n:                         # balanced: no slab carries more than twice the mean masked count (+ one slice)
+            flat = mask.reshape(-1, order="F")
+            cnt = np.array([flat[a:b].sum() for a, b in r])
+            per_slice = flat.reshape(nz, nxny).sum(axis=1).max()
+            assert cnt.max() <= 2 * cnt.mean() + per_slice
 
 
 def test_reference_arm_runs_only_on_rank0():
