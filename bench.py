@@ -274,7 +274,10 @@ class HostSubject:
         else:
             self.dwi_ptr, self.dwi = alloc(nvol)
             self.mask_ptr, self.mask = alloc(1, np.uint8)
-            if pinned:
+            if callable(dwi_src):                 # volumes that do not fit on one GPU: generated slab by slab (pinned only)
+                self.mask.fill_(1)
+                dwi_src(self.dwi)
+            elif pinned:
                 self.dwi.copy_(dwi_src[0][:, :nvox]); self.mask.copy_(dwi_src[1])
             else:
                 self.dwi.T[...] = dwi_src[0][:, :nvox].cpu().numpy(); self.mask[...] = dwi_src[1].cpu().numpy()
@@ -298,7 +301,7 @@ def timed_calls(fn, nwarm, nrep):
     return float(np.median(ts)), float(np.mean(ts))
 
 
-def library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, dwi_src, nsub=16, reps=2, config="cfg2"):
+def library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, dwi_src, nsub=16, reps=2, config="cfg2", only=None):
     """The in-library multi-GPU paths from ONE process (what a Julia session with FIBERS_CUDA_NGPU=N gets):
        zslab : fibers_gqi_rec(..., ngpu) on one subject = strong scaling, z-slabs balanced by mask count, host gather,
                host-side odfmax reduce (north_star "slab partitioner")
@@ -314,10 +317,14 @@ def library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, dwi_src, nsub=16, 
     def zslab(s=subj):
         F._lib.check(L.fibers_gqi_rec(s.dwi_ptr, 0, s.mask_ptr, shape[0], shape[1], shape[2], nvol, F._lib.ptr(bval), F._lib.ptr(bv),
                                       F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25, *s.gqi_out(), None, ngpu))
-    med, mean = timed_calls(zslab, 2, max(3, reps))
-    out["zslab"] = {"api": f"fibers_gqi_rec(..., ngpu={ngpu}): one {config} subject, z-slabs over {ngpu} GPUs, host gather + host odfmax reduce, no collective",
-                    "scaling": "strong", "value": nvox / med, "unit": "voxels/s", "ms_per_call": med * 1e3, "ms_per_call_mean": mean * 1e3,
-                    "h2d_bytes": subj.h2d, "d2h_bytes": subj.d2h, "host_memory": "pinned"}
+    if only in (None, "zslab"):
+        med, mean = timed_calls(zslab, 2, max(3, reps))
+        out["zslab"] = {"api": f"fibers_gqi_rec(..., ngpu={ngpu}): one {config} subject, z-slabs over {ngpu} GPUs, host gather + host odfmax reduce, no collective",
+                        "scaling": "strong", "value": nvox / med, "unit": "voxels/s", "ms_per_call": med * 1e3, "ms_per_call_mean": mean * 1e3,
+                        "h2d_bytes": subj.h2d, "d2h_bytes": subj.d2h, "host_memory": "pinned"}
+    if only == "zslab":
+        L.fibers_cuda_release_cache()
+        return out
     # ---- cfg4: 16 subjects, DTI + GQI each.  The subjects share ONE synthetic DWI buffer (read-only); every subject owns its
     #      outputs.  Full outputs need 16 x 5.1 GB of pinned host memory: attempted only when the box has the RAM to spare.
     def batch_leg(want_odf):
@@ -364,6 +371,8 @@ def main():
     ap.add_argument("--mode", default="default", choices=["default", "zslab", "batch"],
                     help="zslab / batch: only the in-library multi-GPU legs, single process over --gpus devices")
     ap.add_argument("--subjects", type=int, default=16)
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="--mode zslab only: cfg5 = 400x400x300, 8 b0 + 120 x b=4000 (BASELINE configs[4]), data generated slab by slab")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-multi", action="store_true", help="skip the in-library zslab / batch legs at N > 1")
@@ -407,9 +416,23 @@ def main():
 
     if args.mode != "default":              # in-library multi-GPU legs only (single process, no torch.distributed)
         ngpu = min(args.gpus, F.device_count())
-        dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000, dev)
-        mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
-        legs = library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, (dwi, mask), nsub=args.subjects, reps=max(2, args.e2e_steps // 2))
+        if args.config == "cfg5":
+            from fibers_jl_b200 import phantom
+            shape = (400, 400, 300) if args.shape == ",".join(map(str, HCP_SHAPE)) else shape
+            nvox = int(np.prod(shape))
+            bval, bvec = phantom.shells_table(8, [(4000.0, 120)])
+            config["workload"] = f"cfg5 GQI recon+peaks {shape[0]}x{shape[1]}x{shape[2]}x{bval.shape[0]} (8 b0 + 120x b=4000), sphere_642, mask==1"
+
+            def fill(h_dwi, step=1 << 21):
+                for off in range(0, nvox, step):
+                    n = min(step, nvox - off)
+                    h_dwi[:, off:off + n].copy_(synth_dwi_device(torch, n, bval, bvec, 5000 + off // step, dev))
+                torch.cuda.synchronize()
+            src = fill
+        else:
+            src = (synth_dwi_device(torch, nvox, bval, bvec, 1000, dev), torch.ones(nvox, dtype=torch.uint8, device=dev))
+        legs = library_multi_gpu_legs(torch, F, shape, bval, bvec, ngpu, src, nsub=args.subjects, reps=max(2, args.e2e_steps // 2),
+                                      config=args.config, only=args.mode)
         key = "zslab" if args.mode == "zslab" else ("batch" if "value" in legs.get("batch", {}) else "batch_no_odf")
         line = {"metric": "voxels/sec (GQI recon+peaks)" if args.mode == "zslab" else "voxels/sec (DTI fit + GQI recon+peaks, batch of subjects)",
                 "value": legs[key].get("value"), "unit": "voxels/s", "n_gpus": ngpu, "mode": args.mode, "scaling": "strong",
@@ -562,7 +585,7 @@ def main():
                     extra["e2e_pageable"] = {"value": nvox / med, "unit": "voxels/s", "ms_per_step": med * 1e3, "ms_per_step_mean": mean * 1e3,
                                              "h2d_bytes_per_step": pg.h2d, "d2h_bytes_per_step": pg.d2h,
                                              "api": "fibers_gqi_rec on pageable numpy Fortran arrays (what ccall passes, src/mri.jl:249-255): pinned bounce ring + host copy threads",
-                                             "copy_threads": int(os.environ.get("FIBERS_CUDA_COPY_THREADS", "8"))}
+                                             "copy_threads": min(int(os.environ.get("FIBERS_CUDA_COPY_THREADS", "16")), len(os.sched_getaffinity(0)))}
                     del pg
                 except Exception as ex:             # noqa: BLE001
                     extra["e2e_pageable"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}

@@ -14,6 +14,7 @@
 //   * QA planes stay on the device until odfmax is known; for a subject that lives on one GPU the divisor is
 //     decoded on the device, so nothing forces a host sync between subjects: the ring keeps rolling across subject
 //     boundaries (batch mode).  Subjects split over several GPUs reduce the scalar on the host (no collective).
+#include <emmintrin.h>
 #include <sched.h>
 #include <pthread.h>
 #include <unistd.h>
@@ -127,6 +128,24 @@ private:
     const std::function<void(int)>* fn_ = nullptr; int n_ = 0; std::atomic<int> next_{0};
     int active_ = 0; uint64_t gen_ = 0; bool stop_ = false;
 };
+
+// Row copy with non-temporal stores: the rows are 0.25 - 1 MB and written once, so read-for-ownership traffic and cache
+// pollution are pure cost (glibc's memcpy switches to streaming stores only well above these sizes).
+void stream_copy(void* dst, const void* src, size_t n) {
+    char* d = (char*)dst; const char* s = (const char*)src;
+    if (n < 4096) { memcpy(d, s, n); return; }
+    const size_t head = (16 - ((uintptr_t)d & 15)) & 15;
+    memcpy(d, s, head); d += head; s += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(s + i + 32)), e = _mm_loadu_si128((const __m128i*)(s + i + 48));
+        _mm_stream_si128((__m128i*)(d + i), a); _mm_stream_si128((__m128i*)(d + i + 16), b);
+        _mm_stream_si128((__m128i*)(d + i + 32), c); _mm_stream_si128((__m128i*)(d + i + 48), e);
+    }
+    _mm_sfence();
+    memcpy(d + i, s + i, n - i);
+}
 
 // ---- CPU affinity: the CPUs local to the GPU's PCIe root ------------------------------------------
 bool gpu_local_cpus(int device, cpu_set_t* out) {
@@ -294,7 +313,7 @@ void scatter_chunk(DeviceCtx& c, int s, const PendingScatter& p) {
         for (int f = 0; f < 3; ++f)
             rows.push_back({(char*)p.job->peak_idx + ((int64_t)f * p.job->nvox + p.g0) * 2, base + p.L.idx + (size_t)f * p.cp * 2, (size_t)p.cn * 2});
     if (p.job->valid) rows.push_back({(char*)p.job->valid + p.g0, base + p.L.valid, (size_t)p.cn});
-    c.pool->parallel_for((int)rows.size(), [&](int i) { memcpy(rows[i].dst, rows[i].src, rows[i].bytes); });
+    c.pool->parallel_for((int)rows.size(), [&](int i) { stream_copy(rows[i].dst, rows[i].src, rows[i].bytes); });
 }
 
 int complete_scatter(DeviceCtx& c, int s, Err& e) {
@@ -404,7 +423,7 @@ int run_unit(DeviceCtx& c, const Unit& u, bool* arrived, Err& e) {
         if (!out_direct && grow_host(c.h_out, &c.h_out_bytes, out_need, NSLOT, e)) return e.code;
     }
     if (!c.pool) {
-        int nt = 8;
+        int nt = 16;
         if (const char* tv = getenv("FIBERS_CUDA_COPY_THREADS")) nt = std::max(1, atoi(tv));
         cpu_set_t cur; CPU_ZERO(&cur);
         const bool have = sched_getaffinity(0, sizeof(cur), &cur) == 0;       // the worker is already bound (run_worker)
@@ -461,7 +480,7 @@ int run_unit(DeviceCtx& c, const Unit& u, bool* arrived, Err& e) {
             const char* src = (const char*)job.dwi;
             const int64_t nvox = job.nvox;
             c.pool->parallel_for(job.nvol + 1, [&](int k) {
-                if (k < job.nvol) memcpy(hin + (size_t)k * cp * esz, src + ((int64_t)k * nvox + g0) * esz, (size_t)cn * esz);
+                if (k < job.nvol) stream_copy(hin + (size_t)k * cp * esz, src + ((int64_t)k * nvox + g0) * esz, (size_t)cn * esz);
                 else memcpy(hin + (size_t)job.nvol * cp * esz, job.mask + g0, (size_t)cn);
             });
             P_CUDA(cudaMemcpyAsync(d_in, hin, (size_t)job.nvol * cp * esz, cudaMemcpyHostToDevice, st));

@@ -33,7 +33,7 @@
  *    ordinary PAGEABLE memory (what a Julia `Array` is, src/mri.jl:249-255) are accepted as they are and go
  *    through an internal pinned bounce ring filled / emptied by a few host copy threads; the choice is made per
  *    call from cudaPointerGetAttributes (override: env FIBERS_CUDA_HOST_PATH=direct|bounce;
- *    FIBERS_CUDA_COPY_THREADS, default 8 per GPU).  The worker and copy threads of a GPU are bound to the CPUs
+ *    FIBERS_CUDA_COPY_THREADS, default 16 per GPU, never more than the CPUs the process may use).  The worker and copy threads of a GPU are bound to the CPUs
  *    local to it (FIBERS_CUDA_AFFINITY=0 disables).
  *  - gqi_rec / dsi_rec / dti_gqi_fit: `odf` may be NULL when the caller only needs peaks and QA (the only
  *    downstream consumer, stream(), reads nothing else: src/stream.jl:76-173); the ODF is then formed on the
