@@ -538,7 +538,8 @@ def main():
                                           F._lib.ptr(V), V.shape[0], F._lib.ptr(Fc), Fc.shape[0], 1.25,
                                           s.odf_ptr if odf else None, *s.peak, *[q[0] for q in s.qa], None, 1))
         try:
-            ceiling = pcie_ceiling(torch, local_rank)
+            barrier()
+            ceiling = pcie_ceiling(torch, local_rank)          # N > 1: every rank measures its link at the same time
             subj = HostSubject(torch, shape, nvol, True, (dwi, mask))
             torch.cuda.synchronize()
             dwi_keep = dwi if (world == 1 or rank == 0) else None
@@ -570,8 +571,8 @@ def main():
                    "statistic": "median of per-step wall times", "steps": args.e2e_steps,
                    "api": "fibers_gqi_rec (host pointers, pinned buffers)",
                    "pcie_ceiling_GBps_each_way": ceil_min, "ceiling_ms_per_step": floor_ms, "frac_of_ceiling": floor_ms / (dt * 1e3),
-                   "ceiling_note": "concurrent H2D + D2H of 512 MiB pinned buffers on this rank's GPU, measured in this run" +
-                                   (" by every rank one after the other (not all links at once: see tools/gpu/pcie_probe.py)" if world > 1 else "")}
+                   "ceiling_note": "concurrent H2D + D2H of 512 MiB pinned buffers, measured in this run" +
+                                   (f" by all {world} ranks at the same time (the slowest link is quoted; tools/gpu/pcie_probe.py is the long form)" if world > 1 else "")}
             if world == 1:
                 try:                                # odf = NULL: peaks + QA only
                     med, _ = timed_calls(lambda: call(subj, odf=False), 1, 3)

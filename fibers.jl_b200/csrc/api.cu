@@ -195,6 +195,7 @@ int fibers_dti_plan_create(fibers_plan** plan, int device, int nvol, const float
     if (!rc) { p->rows = 7; p->h_matrix = pA; rc = upload(&p->d_pinv, pA); }
     if (!rc) rc = upload(&p->d_design, A);
     if (!rc) rc = upload(&p->d_ib0, ib0);
+    if (!rc) for (uint8_t f : ib0) p->nb0 += f != 0;
     if (rc) { plan_free(p); return rc; }
     *plan = reinterpret_cast<fibers_plan*>(p);
     return 0;
@@ -209,6 +210,7 @@ int fibers_adc_plan_create(fibers_plan** plan, int device, int nvol, const float
     if (!rc) { p->rows = 2; p->h_matrix = pA; rc = upload(&p->d_pinv, pA); }
     if (!rc) rc = upload(&p->d_design, A);
     if (!rc) rc = upload(&p->d_ib0, ib0);
+    if (!rc) for (uint8_t f : ib0) p->nb0 += f != 0;
     if (rc) { plan_free(p); return rc; }
     *plan = reinterpret_cast<fibers_plan*>(p);
     return 0;

@@ -50,12 +50,14 @@ struct Plan {
     float*    d_pinv = nullptr;    // DTI/ADC: [rows][nvol]
     float*    d_design = nullptr;  // DTI/ADC: design matrix A [nvol][rows] (partial-sample path)
     uint8_t*  d_ib0 = nullptr;     // DTI/ADC: [nvol]
+    int       nb0 = 0;             // DTI/ADC: number of minimum-b volumes (ib0 flags set)
     uint16_t* d_nbr = nullptr;     // [nvert][NBR_W]
     int       nbr_width = NBR_W;   // max folded-mesh degree actually present
     float*    d_vert = nullptr;    // first-half vertices [nvert][3] row-major (peak vectors)
     int*      d_list = nullptr;    // DTI partial-path voxel list (grown on demand)
     int64_t   list_cap = 0;
-    int*      d_count = nullptr;   // DTI partial-path counter
+    int*      d_count = nullptr;   // DTI partial-path counters (two, used alternately: see launch_fit)
+    unsigned  count_flip = 0;
     void*     tc = nullptr;        // tensor-core path state (recon_tc.cu), or null
     cudaEvent_t ev_done = nullptr; // end of the plan's most recent launch (see plan_enter / plan_leave)
 };

@@ -192,14 +192,15 @@ constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] 
 template <int NC>
 __global__ void __launch_bounds__(DTI_THREADS, 3)      // <= 80 registers: the rare float64 downdate may spill, the stream must not
 fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __restrict__ mask, int64_t nvox,
-                int nvol, const float* __restrict__ pinv, const float* __restrict__ design, const uint8_t* __restrict__ ib0,
+                int nvol, int nb0, const float* __restrict__ pinv, const float* __restrict__ design, const uint8_t* __restrict__ ib0,
                 DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
                 int* __restrict__ list, int* __restrict__ count) {
     extern __shared__ __align__(16) float sm[];
-    float* spa = sm;                                     // [nvol][CW]: column j of pinv(A), zero padded
+    // [nvol][CW]: column j of pinv(A) times ln 2 (the loop works on log2 s: MUFU.LG2 without the conversion multiply), zero padded
+    float* spa = sm;
     for (int i = threadIdx.x; i < CW * nvol; i += blockDim.x) {
         const int j = i / CW, k = i - j * CW;
-        spa[i] = k < NC ? pinv[k * nvol + j] : ((k == (NC > 2 ? 7 : 2) && ib0[j]) ? 1.f : 0.f);
+        spa[i] = k < NC ? pinv[k * nvol + j] * 0.693147182f : 0.f;
     }
     __syncthreads();
     const int64_t vox = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,31 +209,26 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
     float d[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) d[k] = 0.f;
-    float nposf = 0.f;                                  // number of positive samples (<= 2^24: exact in fp32, one FADD per sample)
-    int nrem = 0;
+    int nrem = 0, b0rem = 0;                           // removed (non-positive) samples, and how many of them are minimum-b volumes
     int rem[RMAX];
-    float b0acc = 0.f;                                  // > 0 iff some minimum-b volume is positive (flag rides in the padded coefficient row)
+    // Hot loop, 13.5 instructions per sample: a non-positive sample is replaced by 1 (log = 0: it contributes nothing,
+    // src/dti.jl:297-298 drops its row) with one compare + select; WHICH samples were dropped is only looked at when the
+    // minimum of a group of UNROLL samples is not positive (rare), so the loop carries no counters.
     auto sample = [&](float s, int j) {
-        const bool pos = s > 0.f;
-        const float posf = pos ? 1.f : 0.f;
-        nposf += posf;
-        // MUFU.LG2 (<= 2 ulp of log2 outside [0.5, 2], 2^-22 absolute inside) times ln 2.  A denormal sample is
-        // flushed to zero (-inf) and an infinite one gives +inf: both leave a non-finite fit, which is detected
-        // after the loop and sent to the exact-log path -- no per-sample range test.
+        // MUFU.LG2 (<= 2 ulp of log2 outside [0.5, 2], 2^-22 absolute inside).  A denormal sample is flushed to zero
+        // (-inf) and an infinite one gives +inf: both leave a non-finite fit, which is detected after the loop and
+        // sent to the exact-log path -- no per-sample range test.
         float l2;
-        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s));
-        const float lg = pos ? l2 * 0.693147182f : 0.f;  // select, not a branch: garbage for s <= 0 is discarded
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s > 0.f ? s : 1.f));
         const float4 c0 = *reinterpret_cast<const float4*>(spa + j * CW);
-        d[0] = fmaf(c0.x, lg, d[0]); d[1] = fmaf(c0.y, lg, d[1]);
+        d[0] = fmaf(c0.x, l2, d[0]); d[1] = fmaf(c0.y, l2, d[1]);
         if (NC > 2) {
             const float4 c1 = *reinterpret_cast<const float4*>(spa + j * CW + 4);
-            d[2 % NC] = fmaf(c0.z, lg, d[2 % NC]); d[3 % NC] = fmaf(c0.w, lg, d[3 % NC]);
-            d[4 % NC] = fmaf(c1.x, lg, d[4 % NC]); d[5 % NC] = fmaf(c1.y, lg, d[5 % NC]); d[6 % NC] = fmaf(c1.z, lg, d[6 % NC]);
-            b0acc = fmaf(c1.w, posf, b0acc);
-        } else {
-            b0acc = fmaf(c0.z, posf, b0acc);
+            d[2 % NC] = fmaf(c0.z, l2, d[2 % NC]); d[3 % NC] = fmaf(c0.w, l2, d[3 % NC]);
+            d[4 % NC] = fmaf(c1.x, l2, d[4 % NC]); d[5 % NC] = fmaf(c1.y, l2, d[5 % NC]); d[6 % NC] = fmaf(c1.z, l2, d[6 % NC]);
         }
     };
+    auto dropped = [&](int j) { if (nrem < RMAX) rem[nrem] = j; ++nrem; b0rem += ib0[j] ? 1 : 0; };
     if (inside) {
         // the row base (volume j) is warp-uniform and the voxel offset fits 32 bits: the address is formed as
         // uniform base + 32-bit thread offset, without per-thread 64-bit arithmetic
@@ -244,22 +240,24 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) s[u] = __ldg(rb + (int64_t)u * pitch + vox32);
             rb += (int64_t)UNROLL * pitch;
-            const float before = nposf;
+            float mn = s[0];
+#pragma unroll
+            for (int u = 1; u < UNROLL; ++u) asm("min.NaN.f32 %0, %0, %1;" : "+f"(mn) : "f"(s[u]));   // (a NaN sample counts as dropped, like `s > 0` in the reference)
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) sample(s[u], j + u);
-            if (nposf - before != (float)UNROLL) {                          // rare: remember which samples were dropped
+            if (!(mn > 0.f)) {                                              // rare: remember which samples were dropped
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) { if (nrem < RMAX) rem[nrem] = j + u; ++nrem; }
+                for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) dropped(j + u);
             }
         }
         for (int u = 0; j < nvol; ++j, ++u) {
             const float sv = __ldg(rb + (int64_t)u * pitch + vox32);
             sample(sv, j);
-            if (!(sv > 0.f)) { if (nrem < RMAX) rem[nrem] = j; ++nrem; }
+            if (!(sv > 0.f)) dropped(j);
         }
     }
-    const bool b0pos = b0acc > 0.f;
-    const int npos = (int)nposf;
+    const int npos = nvol - nrem;
+    const bool b0pos = nb0 - b0rem > 0;                             // some minimum-b volume is positive
     const bool full = inside && npos == nvol;                       // src/dti.jl:294
     bool part = inside && !full && npos > 6 && b0pos;               // :297 (ADC keeps the same rule, :206)
     bool solved = full;
@@ -278,9 +276,8 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
             for (int k = 0; k < NC; ++k) r = fmaf(ai[k], d[k], r);
             z[i] = r;                                                // U' x0
             for (int jj = 0; jj < nrem; ++jj) {
-                const float* pj = spa + rem[jj] * CW;
                 float t = 0.f;
-                for (int k = 0; k < NC; ++k) t = fmaf(ai[k], pj[k], t);
+                for (int k = 0; k < NC; ++k) t = fmaf(ai[k], pinv[k * nvol + rem[jj]], t);
                 S[i][jj] = (i == jj ? 1.f : 0.f) - t;                // I - U' P_r
             }
         }
@@ -304,9 +301,8 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
                 z[c] = t / S[c][c];
             }
             for (int i = 0; i < nrem; ++i) {
-                const float* pj = spa + rem[i] * CW;
 #pragma unroll
-                for (int k = 0; k < NC; ++k) d[k] = fmaf(pj[k], z[i], d[k]);
+                for (int k = 0; k < NC; ++k) d[k] = fmaf(pinv[k * nvol + rem[i]], z[i], d[k]);
             }
             solved = true; part = false;
         }
@@ -328,7 +324,9 @@ template <int NC>
 __global__ void fit_partial_kernel(const float* __restrict__ dwi, int64_t pitch, int nvol,
                                    const float* __restrict__ design /*[nvol][NC]*/,
                                    DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,
-                                   const int* __restrict__ list, const int* __restrict__ count) {
+                                   const int* __restrict__ list, const int* __restrict__ count, int* __restrict__ next_count) {
+  // the counter of the NEXT launch of this plan is reset here (the two alternate), which saves a memset per call
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
   const int total = *count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int64_t vox = list[i];
@@ -401,7 +399,7 @@ int ensure_list(Plan* p, int64_t nvox) {
     if (p->d_list) cudaFree(p->d_list);
     p->d_list = nullptr;
     FB_CUDA(cudaMalloc(&p->d_list, sizeof(int) * (size_t)nvox));
-    if (!p->d_count) FB_CUDA(cudaMalloc(&p->d_count, sizeof(int)));
+    if (!p->d_count) { FB_CUDA(cudaMalloc(&p->d_count, 2 * sizeof(int))); FB_CUDA(cudaMemset(p->d_count, 0, 2 * sizeof(int))); }
     p->list_cap = nvox;
     return 0;
 }
@@ -414,18 +412,19 @@ int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_
     int rc = ensure_list(p, nvox);
     if (rc) return rc;
     if (int rc2 = plan_enter(p, st)) return rc2;                    // the partial-path list / counter belong to the plan
-    FB_CUDA(cudaMemsetAsync(p->d_count, 0, sizeof(int), st));
+    int* cnt = p->d_count + (p->count_flip & 1); int* cnt_next = p->d_count + ((p->count_flip + 1) & 1);
+    ++p->count_flip;                                               // (launches of one plan are serialised by plan_enter / plan_leave)
     size_t smem = sizeof(float) * CW * p->nvol + p->nvol + 16;
     if (smem > 48 * 1024)
         FB_CUDA(cudaFuncSetAttribute(fit_full_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)((nvox + DTI_THREADS - 1) / DTI_THREADS);
-    fit_full_kernel<NC><<<blocks, DTI_THREADS, smem, st>>>(d_dwi, dwi_pitch, d_mask, nvox, p->nvol, p->d_pinv, p->d_design,
-                                                           p->d_ib0, out, adc, adc_s0, p->d_list, p->d_count);
+    fit_full_kernel<NC><<<blocks, DTI_THREADS, smem, st>>>(d_dwi, dwi_pitch, d_mask, nvox, p->nvol, p->nb0, p->d_pinv, p->d_design,
+                                                           p->d_ib0, out, adc, adc_s0, p->d_list, cnt);
     // The partial path is rare: a fixed 4-CTA-per-SM grid strides over the device-side list
     // (no host sync needed to learn the count).  64-thread blocks: heavy per-thread state.
     unsigned pblocks = (unsigned)std::min<int64_t>((nvox + 63) / 64, 148 * 4);
     fit_partial_kernel<NC><<<pblocks, 64, 0, st>>>(d_dwi, dwi_pitch, p->nvol, p->d_design, out, adc, adc_s0,
-                                                   p->d_list, p->d_count);
+                                                   p->d_list, cnt, cnt_next);
     count_launch(2);
     FB_CUDA(cudaGetLastError());
     return plan_leave(p, st);
