@@ -51,6 +51,7 @@ SIGNATURES = {
     "fibers_dsi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i] + [_p] * 9 + [_i]),
     "fibers_dti_gqi_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 10 + [_p, _i, _p, _i, _f] + [_p] * 7 + [_i]),
     "fibers_dti_gqi_fit_batch": (_i, [_i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i, _f, _p, _i]),
+    "fibers_rumba_rec": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i] + [_p] * 14 + [_i]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "fibers_stats_decode_max": (_f, [C.c_int32]),
     "fibers_cuda_launch_count": (_i64, []),
     "fibers_host_build_matrix": (_i, [_i, _i, _p, _p, _p, _i, _f, _i, _p, _i64, _p, _p]),
+    "fibers_host_build_rumba": (_i, [_i, _p, _p, _p, _i, _f, _f, _f, _f, _f, _p, _i64, _p, _p]),
     "fibers_host_build_neighbours": (_i, [_p, _i, _i, _p]),
     "fibers_host_partition_slabs": (_i, [_p, _i64, _i, _i, _p]),
 }

@@ -190,7 +190,7 @@ constexpr int RMAX = 6;
 constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] = pinv(A)' padded (2 x LDS.128 per sample)
 
 template <int NC>
-__global__ void __launch_bounds__(DTI_THREADS, 3)      // <= 80 registers: the rare float64 downdate may spill, the stream must not
+__global__ void __launch_bounds__(DTI_THREADS, 4)      // <= 64 registers (4 CTAs = 32 warps per SM: the loop is bound by loads in flight); only the rare downdate may spill
 fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __restrict__ mask, int64_t nvox,
                 int nvol, int nb0, const float* __restrict__ pinv, const float* __restrict__ design, const uint8_t* __restrict__ ib0,
                 DtiOut out, float* __restrict__ adc, float* __restrict__ adc_s0,

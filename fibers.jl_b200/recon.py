@@ -17,7 +17,7 @@ import numpy as np
 
 from . import _lib
 from .mri import MRI
-from .odf import ODF, sphere_642
+from .odf import ODF, sphere_362, sphere_642, sphere_724
 
 
 @dataclass
@@ -50,6 +50,19 @@ class DSI:                     # reference: src/dsi.jl:10-15
     peak: list
     qa: list
     peak_idx: np.ndarray | None = None
+
+
+@dataclass
+class RUMBASD:                 # reference: src/rusd.jl:11-20
+    fodf: MRI
+    fgm: MRI
+    fcsf: MRI
+    peak: list
+    gfa: MRI
+    var: MRI
+    snr_mean: float
+    snr_std: float
+    peak_idx: np.ndarray | None = None   # extra (test aid): 0-based vertex index or -1, [nx,ny,nz,5]
 
 
 def _mask_u8(mask: MRI, shape):
@@ -206,3 +219,51 @@ def dti_gqi_fit_batch(dwis, masks, odf_dirs: ODF = sphere_642, sigma: float = 1.
                                           parr(dptr) if want_dti else None, _lib.ptr(V), V.shape[0], _lib.ptr(Fc), Fc.shape[0],
                                           float(np.float32(sigma)), parr(gptr), ngpu))
     return res
+
+
+def rumba_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_724, niter: int = 600, lambda_para: float = 1.7e-3,
+              lambda_perp: float = 0.2e-3, lambda_csf: float = 3.0e-3, lambda_gm: float = 0.8e-4, ncoils: int = 1,
+              coil_combine: str = "SMF-SENSE", ipat_factor: int = 1, use_tv: bool = True, device: int = 0) -> RUMBASD:
+    """Robust and unbiased model-based spherical deconvolution (RUMBA-SD); returns a `RUMBASD` structure.
+    Same arguments, defaults and error behaviour as the reference's `rumba_rec` (src/rusd.jl:419)."""
+    _check_tables(dwi, True)
+    if coil_combine not in ("SMF-SENSE", "SoS-GRAPPA"):
+        raise RuntimeError("Unknown coil combine mode " + coil_combine)          # src/rusd.jl:432-434
+    if ipat_factor < 1:
+        raise RuntimeError("iPAT factor must be a positive integer")              # :436-438
+    if dwi.vol.dtype != np.float32:
+        raise TypeError("rumba_rec requires a Float32 DWI volume (reference method signature, src/rusd.jl:419)")
+    nv2 = odf_dirs.vertices.shape[0]
+    # the reference picks the neighbourhood by comparing with its own spheres (:479-483); any other mesh is an UndefVarError there
+    if nv2 in (724, 642):
+        ang_neig = 12.5
+    elif nv2 == 362:
+        ang_neig = 16.0
+    else:
+        raise RuntimeError("rumba_rec: odf_dirs must be sphere_724, sphere_642 or sphere_362 (angular neighbourhood undefined otherwise)")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz, nvol = dwi.vol.shape
+    m = np.asarray(mask.vol)
+    if m.ndim == 4 and m.shape[3] == 1:
+        m = m[..., 0]
+    if tuple(m.shape) != (nx, ny, nz):
+        raise _lib.FibersCudaError(1, f"mask size {m.shape} does not match dwi size {(nx, ny, nz)}")
+    mpos = np.asfortranarray(m > 0).astype(np.uint8, order="F")
+    many = np.asfortranarray(m != 0).astype(np.uint8, order="F")
+    vol = np.asfortranarray(dwi.vol)
+    bvec = np.asfortranarray(dwi.bvec, np.float32)
+    V = np.asfortranarray(odf_dirs.vertices, np.float32)
+    nvert = nv2 // 2
+    fodf = MRI.like(mask, nvert)
+    fgm, fcsf, gfa, var = (MRI.like(mask, 1) for _ in range(4))
+    peak = [MRI.like(mask, 3) for _ in range(5)]
+    idx = np.zeros((nx, ny, nz, 5), np.int16, order="F")
+    import ctypes as C
+    sm, ss = C.c_float(0), C.c_float(0)
+    _lib.check(L.fibers_rumba_rec(_lib.ptr(vol), _lib.ptr(mpos), _lib.ptr(many), nx, ny, nz, nvol, _lib.ptr(dwi.bval), _lib.ptr(bvec),
+                                  _lib.ptr(V), nv2, float(ang_neig), int(niter), float(np.float32(lambda_para)), float(np.float32(lambda_perp)),
+                                  float(np.float32(lambda_csf)), float(np.float32(lambda_gm)), int(ncoils), 1 if coil_combine == "SoS-GRAPPA" else 0,
+                                  int(ipat_factor), 1 if use_tv else 0, _lib.ptr(fodf.vol), _lib.ptr(fgm.vol), _lib.ptr(fcsf.vol),
+                                  *[_lib.ptr(p.vol) for p in peak], _lib.ptr(gfa.vol), _lib.ptr(var.vol), C.byref(sm), C.byref(ss),
+                                  _lib.ptr(idx), int(device)))
+    return RUMBASD(fodf, fgm, fcsf, peak, gfa, var, float(sm.value), float(ss.value), idx)

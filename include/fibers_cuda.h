@@ -144,6 +144,25 @@ int fibers_dti_gqi_fit_batch(int nsub, const float* const* dwi, const uint8_t* c
                              const float* vertices, int nvert2, const int32_t* faces, int nface, float sigma,
                              float* const* gqi_out, int ngpu);
 
+/* rumba_rec: src/rusd.jl:419-636 (RUMBA-SD: Richardson-Lucy deconvolution with a Rician / noncentral-chi likelihood and
+ * total-variation regularisation).  dwi must be Float32 (the reference's method signature).
+ * mask_pos: uint8, 1 where mask.vol > 0 (voxels that are deconvolved, src/rusd.jl:441); mask_any: 1 where mask.vol != 0 (voxels
+ * whose peaks are extracted, :614; NULL = mask_pos).  ang_neig: angular neighbourhood of the peak search in degrees (12.5
+ * for sphere_724 / sphere_642, 16 for sphere_362, :479-483).  coil_combine: 0 = "SMF-SENSE", 1 = "SoS-GRAPPA".
+ * Outputs: fodf [nx,ny,nz,nvert2/2]; fgm, fcsf, gfa, var [nx,ny,nz]; peak1..5 [nx,ny,nz,3]; *snr_mean, *snr_std;
+ * peak_idx (optional test aid): int16 [nx,ny,nz,5], 0-based vertex or -1.
+ * The total-variation term couples neighbouring voxels in every iteration: the volume is processed on ONE device
+ * (`device` ordinal); a batch of subjects uses one device per subject.  The three matrix products of an iteration are plain
+ * GEMMs and go through cuBLAS, loaded at run time; everything else is fused into two kernels per iteration. */
+int fibers_rumba_rec(const float* dwi, const uint8_t* mask_pos, const uint8_t* mask_any,
+                     int nx, int ny, int nz, int nvol, const float* bval, const float* bvec,
+                     const float* vertices, int nvert2, float ang_neig, int niter,
+                     float lambda_para, float lambda_perp, float lambda_csf, float lambda_gm,
+                     int ncoils, int coil_combine, int ipat_factor, int use_tv,
+                     float* fodf, float* fgm, float* fcsf,
+                     float* peak1, float* peak2, float* peak3, float* peak4, float* peak5,
+                     float* gfa, float* var, float* snr_mean, float* snr_std, int16_t* peak_idx, int device);
+
 /* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
  * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
 int fibers_cuda_host_register(void* ptr, size_t bytes);
@@ -212,6 +231,12 @@ int64_t fibers_cuda_launch_count(void);
 int fibers_host_build_matrix(int kind, int nvol, const float* bval, const float* bvec,
                              const float* vertices, int nvert2, float sigma, int hann_width,
                              float* out, int64_t capacity, int* cvol, float* dscale);
+/* RUMBA-SD set-up (src/rusd.jl:444-520, :478-492): kernel [ndir, nvert2/2 + 2] column-major (capacity in elements, may be NULL),
+ * vol_row int32 [nvol] (0 = minimum-b volume, else the 1-based kernel row), nbr uint16 [nvert2/2, 16] row-major, 0xFFFF
+ * terminated angular neighbourhoods.  Returns ndir or < 0. */
+int fibers_host_build_rumba(int nvol, const float* bval, const float* bvec, const float* vertices, int nvert2, float ang_neig,
+                            float lambda_para, float lambda_perp, float lambda_csf, float lambda_gm,
+                            float* kernel, int64_t capacity, int32_t* vol_row, uint16_t* nbr);
 /* Folded-mesh neighbour table: out is uint16 [nvert, 8] row-major, 0xFFFF = none. */
 int fibers_host_build_neighbours(const int32_t* faces, int nface, int nvert, uint16_t* out);
 /* z-slab partition used by the host entry points: out[2g], out[2g+1] = voxel range of shard g. */
