@@ -51,7 +51,7 @@ SIGNATURES = {
     "fibers_dsi_rec": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _i] + [_p] * 9 + [_i]),
     "fibers_dti_gqi_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 10 + [_p, _i, _p, _i, _f] + [_p] * 7 + [_i]),
     "fibers_dti_gqi_fit_batch": (_i, [_i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i, _f, _p, _i]),
-    "fibers_rumba_rec": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i] + [_p] * 14 + [_i]),
+    "fibers_rumba_rec": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i] + [_p] * 13 + [_i]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),
