@@ -52,6 +52,9 @@ SIGNATURES = {
     "fibers_dti_gqi_fit": (_i, [_p, _p, _i, _i, _i, _i, _p, _p] + [_p] * 10 + [_p, _i, _p, _i, _f] + [_p] * 7 + [_i]),
     "fibers_dti_gqi_fit_batch": (_i, [_i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _i, _f, _p, _i]),
     "fibers_rumba_rec": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i] + [_p] * 13 + [_i]),
+    "fibers_st_eigen": (_i, [_p] * 6 + [_i, _i, _i, _p, _p, _i]),
+    "fibers_st_recon": (_i, [_p, _i, _i, _i, _f, _f, _p, _p, _i]),
+    "fibers_st_eigen_device": (_i, [_p] * 6 + [_i64, _p, _p, _p]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),

@@ -267,3 +267,31 @@ def rumba_rec(dwi: MRI, mask: MRI, odf_dirs: ODF = sphere_724, niter: int = 600,
                                   *[_lib.ptr(p.vol) for p in peak], _lib.ptr(gfa.vol), _lib.ptr(var.vol), C.byref(sm), C.byref(ss),
                                   _lib.ptr(idx), int(device)))
     return RUMBASD(fodf, fgm, fcsf, peak, gfa, var, float(sm.value), float(ss.value), idx)
+
+
+def st_eigen(Sxx, Sxy, Sxz, Syy, Syz, Szz, device: int = 0):
+    """Eigen-decomposition of a structure-tensor field; returns `(eigvec [nx,ny,nz,3,3], eigval [nx,ny,nz,3])` exactly as the
+    reference's `st_eigen` (src/structens.jl:13-34): eigenvalues ascending, `eigvec[x,y,z,:,k]` the k-th eigenvector."""
+    arrs = [np.asfortranarray(a) for a in (Sxx, Sxy, Sxz, Syy, Syz, Szz)]
+    if any(a.dtype != np.float32 for a in arrs):
+        raise TypeError("st_eigen: Float32 volumes only on the GPU path")
+    if any(a.ndim != 3 or a.shape != arrs[0].shape for a in arrs):
+        raise _lib.FibersCudaError(1, "st_eigen: the six tensor components must be 3-D arrays of one size")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz = arrs[0].shape
+    evec = np.zeros((nx, ny, nz, 3, 3), np.float32, order="F"); evals = np.zeros((nx, ny, nz, 3), np.float32, order="F")
+    _lib.check(L.fibers_st_eigen(*[_lib.ptr(a) for a in arrs], nx, ny, nz, _lib.ptr(evec), _lib.ptr(evals), int(device)))
+    return evec, evals
+
+
+def st_recon(vol, sigma: float, rho: float, device: int = 0):
+    """Structure-tensor reconstruction of a 3-D image (src/structens.jl:40-88): Gaussian pre-smoothing `sigma`, Scharr gradients,
+    Gaussian tensor smoothing `rho`, eigen-decomposition.  Returns `(eigvec, eigval)` like `st_eigen`."""
+    v = np.asfortranarray(vol)
+    if v.dtype != np.float32 or v.ndim != 3:
+        raise TypeError("st_recon: a 3-D Float32 volume is required on the GPU path")
+    L = _lib.lib(); _lib.require_device()
+    nx, ny, nz = v.shape
+    evec = np.zeros((nx, ny, nz, 3, 3), np.float32, order="F"); evals = np.zeros((nx, ny, nz, 3), np.float32, order="F")
+    _lib.check(L.fibers_st_recon(_lib.ptr(v), nx, ny, nz, float(sigma), float(rho), _lib.ptr(evec), _lib.ptr(evals), int(device)))
+    return evec, evals

@@ -163,6 +163,18 @@ int fibers_rumba_rec(const float* dwi, const uint8_t* mask_pos, const uint8_t* m
                      float* peak1, float* peak2, float* peak3, float* peak4, float* peak5,
                      float* gfa, float* var, float* snr_mean, float* snr_std, int16_t* peak_idx, int device);
 
+/* st_eigen / st_recon: src/structens.jl:13-34, :40-88 (structure tensor).  Float32 volumes [nx,ny,nz].
+ * eigvec: [nx,ny,nz,3,3] with eigvec[x,y,z,:,k] the k-th eigenvector, eigval: [nx,ny,nz,3] ascending -- what
+ * StaticArrays' eigen(Symmetric(S, :L)) returns, i.e. the reference's output arrays verbatim.  st_recon applies
+ * ImageFiltering's separable Gaussian (sigma: pre-smoothing, rho: tensor smoothing; <= 0 skips) and Scharr factors with
+ * "reflect" borders, forms the six products and calls st_eigen.  The _device variant works on device pointers
+ * (frame f of eigvec / eigval starts at f * nvox). */
+int fibers_st_eigen(const float* sxx, const float* sxy, const float* sxz, const float* syy, const float* syz, const float* szz,
+                    int nx, int ny, int nz, float* eigvec, float* eigval, int device);
+int fibers_st_recon(const float* vol, int nx, int ny, int nz, float sigma, float rho, float* eigvec, float* eigval, int device);
+int fibers_st_eigen_device(const float* d_sxx, const float* d_sxy, const float* d_sxz, const float* d_syy, const float* d_syz,
+                           const float* d_szz, int64_t nvox, float* d_eigvec, float* d_eigval, void* stream);
+
 /* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
  * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
 int fibers_cuda_host_register(void* ptr, size_t bytes);
