@@ -572,6 +572,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
             const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
             const int64_t vox = (int64_t)tile * 256 + rank * VOX_CTA + vl;
             const bool inside = vox < p.nvox && p.mask[vox] != 0;
+            const float vscale = inside ? scale : 0.f;
             if (warp == W_CONV0) TRACE(9);
 #pragma unroll 1
             for (int c = 0; c < nk32; ++c, ++g32) {
@@ -607,8 +608,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    // s[s<0] = 0; voxels outside the mask contribute zeros
-                    const float v0 = inside ? fmaxf(x[2 * j], 0.f) * scale : 0.f, v1 = inside ? fmaxf(x[2 * j + 1], 0.f) * scale : 0.f;
+                    // s[s<0] = 0; voxels outside the mask contribute zeros: their scale factor is 0 (fmaxf drops a NaN; a +Inf
+                    // sample of a masked-out voxel gives a non-finite accumulator, which sends the tile to the exact fix-up)
+                    const float v0 = fmaxf(x[2 * j], 0.f) * vscale, v1 = fmaxf(x[2 * j + 1], 0.f) * vscale;
                     const __half2 h = __floats2half2_rn(v0, v1);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -691,40 +693,46 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                 const bool plain = p.plain != 0;
                 // key = 0x8000 | ceil(32767 * sat(val * ks)): two instructions (FMUL.SAT, FFMA.RP), the low 16 bits of
                 // the second result are the stored key
+                // Row addresses: one 64-bit pointer advanced by an opaque add per row (IADD3 + IADD3.X).  Left to itself the
+                // compiler rebuilds every row address from the chunk base with IMAD.WIDE chains (3-4 instructions per store).
+                const int64_t pitch_b = pitch * 4;
+                auto next_row = [&](float*& g) { asm volatile("add.s64 %0, %0, %1;" : "+l"(g) : "l"(pitch_b)); };
+                auto st_row = [](float* g, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(g), "f"(v)); };   // (the opaque add hides the address space)
                 auto process = [&](const uint32_t (&r)[16], int c0) {
                     const int nrow = min(16, M - c0);                   // warp-uniform
+                    float* g = gp;
                     if (plain) {
-                        float* g = gp;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            if (j < nrow && vok) *g = __uint_as_float(r[j]) * scl;
-                            g += pitch;
+                            if (j < nrow && vok) st_row(g, __uint_as_float(r[j]) * scl);
+                            next_row(g);
                         }
                     } else if (nrow == 16) {
-                        float* g = gp;
+                        float prev = CUDART_INF_F;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float val = __uint_as_float(r[j]) * scl;
-                            if (vok) *g = val;
-                            g += pitch;
+                            if (vok) st_row(g, val);
+                            next_row(g);
                             const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                             kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                            mn = fminf(mn, val);
+                            if (j & 1) asm("min.f32 %0, %0, %1, %2;" : "+f"(mn) : "f"(prev), "f"(val));   // FMNMX3: one instruction per two values
+                            else prev = val;
                         }
                     } else {
-                        float* g = gp;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j, g += pitch) {
+                        for (int j = 0; j < 16; ++j) {
                             if (j < nrow) {
                                 const float val = __uint_as_float(r[j]) * scl;
-                                if (vok) *g = val;
+                                if (vok) st_row(g, val);
                                 const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
                                 kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
                                 mn = fminf(mn, val);
                             }
+                            next_row(g);
                         }
                     }
-                    gp += 16 * pitch; kp += 16 * VOX_CTA;
+                    gp = g; kp += 16 * VOX_CTA;
                 };
                 // TMA mode: the 16 x 32 values of a chunk go to this warp's staging box and leave with ONE bulk tensor store
                 // (rows >= M and voxels >= nvox are clipped by the tensor map); the box is reused two chunks later, once the
@@ -860,25 +868,34 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     // threshold t = max(neighbour keys, 1)
                     const uint32_t hAx = kA.x - mAx + 0x80008000u, hAy = kA.y - mAy + 0x80008000u;
                     const uint32_t hBx = kB.x - mBx + 0x80008000u, hBy = kB.y - mBy + 0x80008000u;
-                    // No branch in the loop: the 8 result bits of the pair (0-3 = vertex v, voxels 4*lane + 0..3; 4-7 =
-                    // vertex v + 1) go into a per-lane bit field, one byte per iteration, and are listed after the loop.
-                    const uint32_t w = ((hAx >> 15) & 0x00010001u) | ((hAy >> 13) & 0x00040004u) |
-                                       ((hBx >> 11) & 0x00100010u) | ((hBy >> 9) & 0x00400040u);
-                    const uint32_t fl = (w & 0x55u) | ((w >> 15) & 0xAAu);
-                    const uint32_t sh = (uint32_t)(iter & 3) * 8u;
+                    // No branch in the loop: the result bits of the pair are bit 15 / 31 of the four words.  Two byte
+                    // permutes collect the bytes that hold them (byte b of pA = vertex v, voxel 4*lane + b; same for pB and
+                    // vertex v + 1), one mask + shift + or interleaves them (A at bit 7, B at bit 6 of every byte) and the
+                    // pair of iteration j lands 2 j bits lower: four iterations fill a 32-bit word.
+                    uint32_t pA, pB;
+                    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pA) : "r"(hAx), "r"(hAy));
+                    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pB) : "r"(hBx), "r"(hBy));
+                    const uint32_t fl = (pA & 0x80808080u) | ((pB >> 1) & 0x40404040u);
+                    const uint32_t sh = (uint32_t)(iter & 3) * 2u;
                     switch (iter >> 2) {                                // (warp-uniform)
-                        case 0: fw0 |= fl << sh; break;
-                        case 1: fw1 |= fl << sh; break;
-                        case 2: fw2 |= fl << sh; break;
-                        default: fw3 |= fl << sh; break;
+                        case 0: fw0 |= fl >> sh; break;
+                        case 1: fw1 |= fl >> sh; break;
+                        case 2: fw2 |= fl >> sh; break;
+                        default: fw3 |= fl >> sh; break;
                     }
                     ++iter;
                 }
-                // list the hits: one shared-memory atomic per lane that has any (typically a dozen lanes per warp and tile)
+                // List the hits (typically a dozen lanes per warp and tile have one or two).  The slots come from ONE shared-memory
+                // atomic per warp (warp prefix sum of the per-lane counts): per-lane atomics on the single counter serialise.
                 const uint32_t nhit = (p.abl & 48) ? 0u : __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);   // (ablations 16 / 32: nothing is listed)
-                if (nhit) {
-                    uint32_t slot;
-                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(ncand32), "r"(nhit) : "memory");
+                if (__any_sync(0xffffffffu, nhit != 0u)) {
+                    uint32_t incl = nhit;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                    uint32_t base = 0u;
+                    if (lane == 31) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(ncand32), "r"(incl) : "memory");
+                    base = __shfl_sync(0xffffffffu, base, 31);
+                    uint32_t slot = base + incl - nhit;
                     const uint32_t fws[4] = {fw0, fw1, fw2, fw3};
 #pragma unroll
                     for (int wi = 0; wi < 4; ++wi) {
@@ -886,9 +903,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                         while (bits) {
                             const int h = __ffs(bits) - 1;
                             bits &= bits - 1;
-                            const int it_ = wi * 4 + (h >> 3), bit = h & 7;
-                            const int vv = pair_vertex(ew + it_ * N_EPI) + (bit >> 2);
-                            if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)vv << 8) | (uint32_t)(4 * lane + (bit & 3));
+                            const int r = 7 - (h & 7);                  // 2 * (iteration within the word) + (vertex v + 1 ?)
+                            const int vv = pair_vertex(ew + (wi * 4 + (r >> 1)) * N_EPI) + (r & 1);
+                            if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)vv << 8) | (uint32_t)(4 * lane + (h >> 3));
                             ++slot;
                         }
                     }

@@ -1,0 +1,155 @@
+"""CPU restatement of the reference's deterministic streamline tractography (TEST INFRASTRUCTURE: only
+tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this; the product path never does).
+
+Follows /root/reference/src/stream.jl line by line for the regime the GPU path covers: orientation vectors
+given as 3-D vectors, no local connection matrices (`lcms === nothing`; that branch draws from
+`rand(Categorical(...))` and has no deterministic answer) and the macroscopic regime (voxel size > 50 um,
+`domicro == false`).
+
+    StreamWork (mask / vector masking)        src/stream.jl:72-140
+    stream_pick_by_angle!                     src/stream.jl:355-387
+    stream_new_point!                         src/stream.jl:497-541
+    stream_new_line                           src/stream.jl:621-690
+    stream (seed order, len_min filter)       src/stream.jl:730-790
+
+PARITY UNPINNED: the reference ships no tests or vectors for this path and Julia is not available.  Arithmetic
+that lives outside /root/reference is restated from its published behaviour:
+  * `round(Int, x)`                     round-half-to-even;
+  * `dot(::Vector{Float32}, ::SubArray)` LinearAlgebra -> BLAS sdot; restated as the sequential fp32 sum
+                                        (a1 b1 + a2 b2) + a3 b3 with every product and sum rounded to fp32 (the
+                                        true kernel is platform dependent: OpenBLAS may keep a wider accumulator);
+  * `norm(::Vector{Float32})` (n < 32)  LinearAlgebra.generic_norm2: squares in fp32, sum and sqrt in fp64,
+                                        result converted to fp32;
+  * `argmax`                            first maximum, NaN counts as the largest value;
+  * `cosd(T(ang))`                      evaluated by the caller (the wrapper), passed in as `cosang_thresh`.
+The sub-voxel offsets are random in the reference (`rand(Uniform(-.5+eps(), .5-eps()), 3)`, :177-183): they are
+an INPUT here and in the C ABI, so that both sides track the same seeds.
+
+Coordinates are the reference's: 1-based voxel indices, positions in voxel units.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F = np.float32
+
+
+def stream_work(ovecs, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None):
+    """StreamWork constructor, src/stream.jl:72-140: returns (mask_array [nx,ny,nz] bool, ovec_array [3,nvec,nx,ny,nz] f32).
+    ovecs: list of [nx,ny,nz,3] arrays; f: list of [nx,ny,nz] or None; fa, mask: [nx,ny,nz] or None."""
+    ovecs = [np.asarray(o, dtype=F) for o in ovecs]
+    nx, ny, nz = ovecs[0].shape[:3]
+    if mask is None:                                         # :107-112
+        m = np.zeros((nx, ny, nz), dtype=bool)
+        for o in ovecs:
+            m |= np.any(o != 0, axis=3)
+    else:                                                    # :114
+        mk = np.asarray(mask)
+        m = (mk.reshape(nx, ny, nz, -1)[..., 0] > 0)
+    if fa is not None:                                       # :117-128
+        m = m & (np.asarray(fa, dtype=F).reshape(nx, ny, nz, -1)[..., 0] >= F(fa_thresh))
+    arr = np.zeros((3, len(ovecs), nx, ny, nz), dtype=F)
+    for i, o in enumerate(ovecs):                            # :133-147
+        om = m if f is None else (m & (np.asarray(f[i], dtype=F).reshape(nx, ny, nz) >= F(f_thresh)))
+        for d in range(3):
+            arr[d, i] = o[..., d] * om
+    return m, arr
+
+
+def _dot3(a, b):
+    return F(F(F(a[0] * b[0]) + F(a[1] * b[1])) + F(a[2] * b[2]))
+
+
+def _rnd(x):
+    return int(np.rint(x))                                   # half to even, like Julia's round(Int, x)
+
+
+class _State:
+    __slots__ = ("pos_now", "vec_now", "pos_next", "vec_next", "ivec_next")
+
+
+def _pick_by_angle(st, ix, iy, iz, ovec):
+    """src/stream.jl:355-387 (ix, iy, iz 1-based)."""
+    nvec = ovec.shape[1]
+    cos = np.empty(nvec, dtype=F)
+    cab = np.empty(nvec, dtype=F)
+    for i in range(nvec):
+        v = ovec[:, i, ix - 1, iy - 1, iz - 1]
+        if v[0] == 0 and v[1] == 0 and v[2] == 0:
+            cos[i] = cab[i] = -np.inf
+        else:
+            cos[i] = _dot3(st.vec_now, v)
+            cab[i] = abs(cos[i])
+    nan = np.isnan(cab)
+    k = int(np.argmax(nan)) if nan.any() else int(np.argmax(cab))     # Julia argmax: first NaN wins, else first maximum
+    if not np.isfinite(cos[k]):
+        return False
+    v = ovec[:, k, ix - 1, iy - 1, iz - 1]
+    st.vec_next = v.copy() if cos[k] > 0 else (-v).astype(F)
+    st.ivec_next = k + 1
+    return True
+
+
+def _new_point(st, mask, ovec, step):
+    """src/stream.jl:497-541 without LCMs."""
+    st.pos_next = (st.pos_now + (st.vec_now * step).astype(F)).astype(F)
+    ix, iy, iz = _rnd(st.pos_next[0]), _rnd(st.pos_next[1]), _rnd(st.pos_next[2])
+    nx, ny, nz = mask.shape
+    if not (1 <= ix <= nx and 1 <= iy <= ny and 1 <= iz <= nz):
+        return False
+    if not mask[ix - 1, iy - 1, iz - 1]:
+        return False
+    return _pick_by_angle(st, ix, iy, iz, ovec)
+
+
+def new_line(seed_vox, sub_vox, mask, ovec, len_max, cosang_thresh, step, smooth):
+    """src/stream.jl:621-690: returns the [3, npts] streamline of one (seed voxel, sub-voxel offset)."""
+    step, smooth, cosang_thresh = F(step), F(smooth), F(cosang_thresh)
+    st = _State()
+    st.ivec_next = 1                                          # :646 (NOT reset between the two directions)
+    npts = 0
+    fwd_pts, bwd_pts = [], []
+    seed = np.asarray(seed_vox, dtype=F)
+    for fwd in (1, -1):
+        st.pos_now = (seed + np.asarray(sub_vox, dtype=F)).astype(F)
+        st.vec_now = (ovec[:, st.ivec_next - 1, seed_vox[0] - 1, seed_vox[1] - 1, seed_vox[2] - 1] * F(fwd)).astype(F)
+        while True:
+            if not _new_point(st, mask, ovec, step):
+                break
+            (fwd_pts if fwd == 1 else bwd_pts).append(st.pos_now.copy())     # prepend! / append! (:660, :666)
+            npts += 1
+            if _dot3(st.vec_now, st.vec_next) < cosang_thresh:                # :677
+                break
+            if npts > len_max:                                                # :681
+                break
+            if smooth != 0:                                                   # :684-688
+                one_minus = F(F(1) - smooth)
+                vn = ((smooth * st.vec_now).astype(F) + (one_minus * st.vec_next).astype(F)).astype(F)
+                nrm = F(np.sqrt(np.float64(F(vn[0] * vn[0])) + np.float64(F(vn[1] * vn[1])) + np.float64(F(vn[2] * vn[2]))))
+                st.vec_next = (vn / nrm).astype(F)
+            st.pos_now = st.pos_next
+            st.vec_now = st.vec_next
+    pts = fwd_pts[::-1] + bwd_pts
+    return np.array(pts, dtype=F).reshape(-1, 3).T
+
+
+def stream(ovecs, sublist, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, len_min=3, len_max=None,
+           cosang_thresh=None, step_size=0.5, smooth_coeff=0.2):
+    """src/stream.jl:730-790.  Returns the list of [3, npts] streamlines in the reference's order (seed voxels in
+    column-major order, sub-voxel samples innermost), lines shorter than len_min dropped."""
+    m, arr = stream_work(ovecs, f, f_thresh, fa, fa_thresh, mask)
+    nx, ny, nz = m.shape
+    if len_max is None:
+        len_max = max(nx, ny, nz)
+    if cosang_thresh is None:
+        cosang_thresh = F(np.cos(np.deg2rad(45.0)))
+    sm = m if seed is None else (np.asarray(seed).reshape(nx, ny, nz, -1)[..., 0] > 0)
+    lin = np.flatnonzero(sm.reshape(-1, order="F"))           # findall: column-major order
+    out = []
+    for l in lin:
+        vox = [int(l % nx) + 1, int((l // nx) % ny) + 1, int(l // (nx * ny)) + 1]
+        for sub in sublist:
+            s = new_line(vox, sub, m, arr, len_max, cosang_thresh, step_size, smooth_coeff)
+            if s.shape[1] >= len_min:
+                out.append(s)
+    return out
