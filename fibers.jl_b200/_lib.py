@@ -55,6 +55,10 @@ SIGNATURES = {
     "fibers_st_eigen": (_i, [_p] * 6 + [_i, _i, _i, _p, _p, _i]),
     "fibers_st_recon": (_i, [_p, _i, _i, _i, _f, _f, _p, _p, _i]),
     "fibers_st_eigen_device": (_i, [_p] * 6 + [_i64, _p, _p, _p]),
+    "fibers_stream": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p]),
+    "fibers_stream_device": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p]),
+    "fibers_stream_fetch": (_i, [_p, _p, _p]),
+    "fibers_stream_free": (None, [_p]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),

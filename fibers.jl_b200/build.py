@@ -21,10 +21,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 EXTRA = {
     "dti.cu": ["-fmad=false"],          # eigen-solver follows the reference's unfused fp32 order
     "structens.cu": ["-fmad=false"],
+    "stream.cu": ["-fmad=false"],        # propagation follows the reference's unfused fp32 order
     "setup.cpp": ["-Xcompiler", "-ffp-contract=off"],
     "recon_simt.cu": ["-diag-suppress", "128"],   # "loop is not reachable" in the plain-rows instantiation (early return)
 }
-SOURCES = ["api.cu", "host_pipeline.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu", "rumba.cu", "structens.cu"]
+SOURCES = ["api.cu", "host_pipeline.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu", "rumba.cu", "structens.cu", "stream.cu"]
 
 
 def _nvcc() -> str:

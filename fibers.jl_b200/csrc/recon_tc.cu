@@ -331,12 +331,13 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     uint8_t* sB = base;                                                   // nstage * sub_bytes
     uint16_t* keys = (uint16_t*)(sB + p.nstage * sub_bytes);                // [M + 1][128] 16-bit keys; row M = 0 (sentinel)
     const int Mk = p.plain ? 0 : p.M;                                     // plain passes stage no keys
-    unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [3][128] best (value, ~index) per voxel
-    uint32_t* s_cand = (uint32_t*)(s_top + 3 * VOX_CTA);                  // [CAND_CAP] listed (tie, vertex, voxel)
-    float* s_min = (float*)(s_cand + CAND_CAP);                           // [N_CPART][128]
-    float* s_mean = s_min + N_CPART * VOX_CTA;                            // [128] mean ODF per voxel (from the extra matrix row)
+    // (double-buffered: the settle step and the outputs of a tile run one loop iteration later, beside the next tile's drain)
+    unsigned long long* s_top = (unsigned long long*)(keys + (size_t)(Mk + 8) * VOX_CTA);   // [2][3][128] best (value, ~index) per voxel
+    uint32_t* s_cand = (uint32_t*)(s_top + 2 * 3 * VOX_CTA);              // [2][CAND_CAP] listed (vertex, voxel)
+    float* s_min = (float*)(s_cand + 2 * CAND_CAP);                       // [2][N_CPART][128]
+    float* s_mean = s_min + 2 * N_CPART * VOX_CTA;                        // [2][128] mean ODF per voxel (from the extra matrix row)
     // raw DWI ring (128-byte aligned: TMA destination), then (TMA mode) the ODF staging boxes
-    float* s_dwi = (float*)(((uintptr_t)(s_mean + VOX_CTA) + 127) & ~(uintptr_t)127);   // cp.async: [DSTAGE][32][128]; TMA: [TSTAGE][16][128]
+    float* s_dwi = (float*)(((uintptr_t)(s_mean + 2 * VOX_CTA) + 127) & ~(uintptr_t)127);   // cp.async: [DSTAGE][32][128]; TMA: [TSTAGE][16][128]
     uint8_t* s_obox = (uint8_t*)(s_dwi + (kTma ? p.tstage * 16 : DSTAGE * 32) * VOX_CTA);   // [N_CPART][obuf][16][128] fp32
     uint4* s_nbr = (uint4*)(s_obox + (kTma ? (size_t)N_CPART * p.obuf * OBOX_BYTES : 0));  // [M] 8 x uint16 neighbour ids per vertex
     float* s_vert = (float*)(s_nbr + Mk);                                 // [M][3] first-half vertices (peak vectors); padded to 4 floats
@@ -344,8 +345,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     uint64_t* b_full = bars, *b_empty = bars + NSTAGE, *a_full = bars + 2 * NSTAGE, *a_empty = bars + 2 * NSTAGE + ASLOT;
     uint64_t* d_full = bars + 2 * NSTAGE + 2 * ASLOT, *d_empty = d_full + 1;
     uint64_t* w_full = d_empty + 1, *w_empty = w_full + TSTAGE;           // DWI ring (TMA mode)
-    uint32_t* s_ncand = (uint32_t*)(w_empty + TSTAGE);
-    uint32_t* tmem_ptr_s = s_ncand + 1;
+    uint32_t* s_ncand = (uint32_t*)(w_empty + TSTAGE);                    // [2]
+    uint32_t* tmem_ptr_s = s_ncand + 2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -359,7 +360,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 8 * VOX_CTA; i += TC_THREADS) keys[(size_t)Mk * VOX_CTA + i] = 0x8000;   // key 0
-    if (threadIdx.x == 0) *s_ncand = 0u;
+    if (threadIdx.x == 0) { s_ncand[0] = 0u; s_ncand[1] = 0u; }
     for (int i = threadIdx.x; i < Mk; i += TC_THREADS) s_nbr[i] = __ldg(reinterpret_cast<const uint4*>(p.nbr) + i);
     for (int i = threadIdx.x; i < 3 * Mk; i += TC_THREADS) s_vert[i] = __ldg(p.vert + i);
     tc_fence_before();
@@ -657,332 +658,284 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         const uint32_t obox0 = smem_u32(s_obox) + (uint32_t)(ew * p.obuf) * WBOX;
         const uint32_t obufm = (uint32_t)max(p.obuf, 1);
         uint32_t oc = 0;
+        // The epilogue of a tile is SPLIT across two loop iterations so that the L2 round trips of the settle step hide
+        // behind the next tile's accumulator drain:
+        //   iteration `it`:  [settle-issue(it-1): candidate list of the previous tile -> exact fp32 loads into registers]
+        //                    drain(it) (TMEM -> ODF stores + key tile)  -> TMEM released
+        //                    [settle-finish(it-1): compare, sorted-triple inserts]  [outputs(it-1)]
+        //                    scan(it) -> candidate list of tile `it`
+        // Candidate list, sorted triples, per-voxel minimum / mean are double-buffered (index it & 1); the key tile is not:
+        // the only reader outside the scan, the tie test of settle-issue, runs before the drain overwrites it.
         uint32_t it = 0;
-        for (int ti_ = cluster_id; ti_ < ntl; ti_ += ncluster, ++it) {
-            const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
-            const int64_t vox0 = (int64_t)tile * 256 + rank * VOX_CTA;   // first voxel of this CTA's half
-            const int64_t vox = vox0 + vl;
-            const bool vok = vox < p.nvox;
-            // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol], folded into the un-scale factor.
-            // A voxel whose q = 0 sample is <= 0 gets zeros: either it is skipped by the reference as well (all
-            // samples <= 0) or the reference divides by zero there (undefined; excluded from parity).
-            float scl = inv_scale;
-            if (p.cvol >= 0) {
-                const float sc = vok ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f;
-                scl = sc > 0.f ? inv_scale * (1.f / (p.dscale * sc)) : 0.f;     // inv_scale is a power of two: exact
+        bool have_prev = false;
+        int64_t vox0_prev = 0;
+        for (int i = et; i < 2 * 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
+        named_bar(1, EPI_THREADS);
+        auto insert_top = [&](unsigned long long* top, int cv, int cx, float c) {
+            // Insert (value, ~index) into the voxel's sorted triple: atomicMax returns what it displaced, and the
+            // smaller of the two moves down one level.  Larger value wins, equal values -> smaller index wins
+            // (the reference's stable order).  Every level ends up with the right key whatever the interleaving.
+            unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (0xFFFFFFFFu - (uint32_t)cv);
+#pragma unroll
+            for (int lvl = 0; lvl < 3; ++lvl) {
+                const unsigned long long old = atomicMax(&top[lvl * VOX_CTA + cx], key);
+                key = old < key ? old : key;
+                if (key == 0ull) break;
             }
-            for (int i = et; i < 3 * VOX_CTA; i += EPI_THREADS) s_top[i] = 0ull;
-            mbar_wait<50>(d_full, it & 1);
-            tc_fence_after();
-            if (warp == W_EPI0) TRACE(2);
-            // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + 16-bit key tile ----
-            // key(val) = ceil(32767 * clamp(val * ks, 0, 1)), ks = 1 / (KEY_WINDOW * mean): monotone in val, key >= 1
-            // <=> val > 0.  Stored as 0x8000 | key = the low mantissa bits of fma.rp(sat(val * ks), 32767, 2^23 + 2^15)
-            // (no conversion instruction); the always-set bit 15 lets one 32-bit subtraction compare two packed keys.
-            float mn = CUDART_INF_F, meanv = 0.f;
-            {
-                float ks = 0.f;
-                if (!p.plain) {
-                    meanv = __uint_as_float(tmem_ld1(lane_addr + M)) * scl;   // extra matrix row M: mean of the ODF rows
-                    tmem_wait_ld();
-                    ks = (meanv > 0.f && meanv < CUDART_INF_F) ? (1.f / KEY_WINDOW) / meanv : 1e-30f;
+        };
+        for (int ti_ = cluster_id; ; ti_ += ncluster, ++it) {
+            const bool have_cur = ti_ < ntl;
+            if (!have_cur && !have_prev) break;
+            const int buf = (int)(it & 1u), pbuf = buf ^ 1;
+            // ---- settle-issue (previous tile): thread e takes listed pair e.  A key that decided strictly needs the
+            //      value only; a key tie needs the neighbours' fp32 values as well.  All loads are L2 hits (this CTA
+            //      wrote the values one tile ago) and stay in flight during the drain below. ----
+            uint32_t ncand_raw = 0u; int ncand = 0;
+            bool act = false, tie = false;
+            int cv = 0, cx = 0;
+            float cval = 0.f, nv[8];
+            if (have_prev) {
+                if (kTma && p.obuf > 0 && lane == 0) {                      // staged ODF boxes of the previous tile have left
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
                 }
-                float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
-                uint16_t* kp = keys + c_begin * VOX_CTA + vl;
-                const int64_t pitch = p.out_pitch;
-                const bool plain = p.plain != 0;
-                // key = 0x8000 | ceil(32767 * sat(val * ks)): two instructions (FMUL.SAT, FFMA.RP), the low 16 bits of
-                // the second result are the stored key
-                // Row addresses: one 64-bit pointer advanced by an opaque add per row (IADD3 + IADD3.X).  Left to itself the
-                // compiler rebuilds every row address from the chunk base with IMAD.WIDE chains (3-4 instructions per store).
-                const int64_t pitch_b = pitch * 4;
-                auto next_row = [&](float*& g) { asm volatile("add.s64 %0, %0, %1;" : "+l"(g) : "l"(pitch_b)); };
-                auto st_row = [](float* g, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(g), "f"(v)); };   // (the opaque add hides the address space)
-                auto process = [&](const uint32_t (&r)[16], int c0) {
-                    const int nrow = min(16, M - c0);                   // warp-uniform
-                    float* g = gp;
-                    if (plain) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (j < nrow && vok) st_row(g, __uint_as_float(r[j]) * scl);
-                            next_row(g);
-                        }
-                    } else if (nrow == 16) {
-                        float prev = CUDART_INF_F;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float val = __uint_as_float(r[j]) * scl;
-                            if (vok) st_row(g, val);
-                            next_row(g);
-                            const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
-                            kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                            if (j & 1) asm("min.f32 %0, %0, %1, %2;" : "+f"(mn) : "f"(prev), "f"(val));   // FMNMX3: one instruction per two values
-                            else prev = val;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (j < nrow) {
-                                const float val = __uint_as_float(r[j]) * scl;
-                                if (vok) st_row(g, val);
-                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
-                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                                mn = fminf(mn, val);
-                            }
-                            next_row(g);
-                        }
-                    }
-                    gp = g; kp += 16 * VOX_CTA;
-                };
-                // TMA mode: the 16 x 32 values of a chunk go to this warp's staging box and leave with ONE bulk tensor store
-                // (rows >= M and voxels >= nvox are clipped by the tensor map); the box is reused two chunks later, once the
-                // TMA unit has read it.  The drain then runs at TMEM / issue speed instead of the store port's.
-                const int vcoord = (int)vox0 + q * 32;
-                long long box_wait = 0;                                // (trace only)
-                auto process_tma = [&](const uint32_t (&r)[16], int c0) {
-                    const int nrow = min(16, M - c0);                   // warp-uniform
-                    const uint32_t bx = obox0 + (oc % obufm) * WBOX + lane * 4;
-                    const long long tw0 = (kTrace && p.trace && warp == W_EPI0) ? clock64() : 0;
-                    if (lane == 0) {
-                        if (p.obuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    __syncwarp();
-                    if (kTrace && p.trace && warp == W_EPI0) { box_wait += clock64() - tw0; TRACE(17 + ((c0 - c_begin) >> 4)); }
-                    if (plain) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(__uint_as_float(r[j]) * scl) : "memory");
-                    } else if (nrow == 16) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float val = __uint_as_float(r[j]) * scl;
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
-                            const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
-                            kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                            mn = fminf(mn, val);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float val = __uint_as_float(r[j]) * scl;
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
-                            if (j < nrow) {
-                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
-                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
-                                mn = fminf(mn, val);
-                            }
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                                     ::"l"(&tmapO), "r"(vcoord), "r"(c0), "r"(bx) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    kp += 16 * VOX_CTA; ++oc;
-                };
-                const bool staged = kTma && p.obuf > 0;
-                auto step = [&](const uint32_t (&r)[16], int c0) { if (p.abl & 4) { mn = fminf(mn, __uint_as_float(r[0])); return; } if (staged) process_tma(r, c0); else process(r, c0); };
-                uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
-                if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
-                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                    tmem_wait_ld();
-                    if (c0 + 16 < c_end) tmem_ld16(lane_addr + c0 + 16, rb);
-                    step(ra, c0);
-                    if (c0 + 16 < c_end) {
-                        tmem_wait_ld();
-                        if (c0 + 32 < c_end) tmem_ld16(lane_addr + c0 + 32, ra);
-                        step(rb, c0 + 16);
-                    }
-                }
-                if (kTma && kTrace && p.trace && warp == W_EPI0) TRACE_ADD(24, box_wait);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
-            if (warp == W_EPI0) TRACE(3);
-            if (p.plain) continue;                                      // rows only (DSI pdf): nothing is staged
-            s_min[cpart * VOX_CTA + vl] = mn;
-            if (cpart == 0) s_mean[vl] = meanv;
-            named_bar(1, EPI_THREADS);                                  // key tile + this tile's ODF stores visible to the group
-            if (warp == W_EPI0) TRACE(4);
-            // ---- phase 2: scan.  A vertex can only be a local maximum (value > 0, > every mesh neighbour) if its
-            //      key is >= max(neighbour keys, 1); equality means "cannot tell from the keys".  Both kinds are
-            //      listed.  Two vertices per iteration; software-pipelined: the keys of pair i+1 and the offsets of
-            //      pair i+2 are in flight while pair i is tested.  (Prefetches past the warp's range touch rows
-            //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
-            if (!(p.abl & 2)) {
-                uint32_t kb = smem_u32(keys) + lane * 8;
-                asm volatile("mov.u32 %0, %0;" : "+r"(kb));             // pin: keeps the compiler from re-deriving the base in every iteration
-                const uint32_t ncand32 = smem_u32(s_ncand);
-                auto ld = [&](uint32_t off) {
-                    uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
-                };
-                // max of the six neighbour keys and of the threshold key 1 (two packed voxels): three 3-input packed max
-                auto max6 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
-                    return umax2(umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f)), 0x80018001u);
-                };
-                const bool wide = p.nbw > 6;                            // warp-uniform (meshes with degree 7-8)
-                // Vertex pairs are dealt round-robin to the warps (pair ew, ew + N_EPI, ...): ODF peaks are spatially
-                // compact, so contiguous ranges would give all the listing work of a tile to one or two warps.
-                const int npair = (M + 1) >> 1;
-                auto pair_vertex = [&](int pi) { return 2 * min(pi, npair); };      // past the end -> sentinel rows
-                int pi = ew;
-                int v = pair_vertex(pi), vn = pair_vertex(pi + N_EPI);
-                const uint32_t* op = c_nbr_off + v * NBR_W;
-                uint4 oA0 = *reinterpret_cast<const uint4*>(op), oB0 = *reinterpret_cast<const uint4*>(op + 8);
-                uint2 oA1 = *reinterpret_cast<const uint2*>(op + 4), oB1 = *reinterpret_cast<const uint2*>(op + 12);
-                uint2 cA = ld(v * KEY_ROW), cB = ld((v + 1) * KEY_ROW);
-                uint2 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
-                uint2 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
-                op = c_nbr_off + vn * NBR_W;
-                oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
-                oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
-                uint32_t fw0 = 0u, fw1 = 0u, fw2 = 0u, fw3 = 0u;       // result bits: one byte per iteration (<= 16 iterations: M <= 383)
-                int iter = 0;
-                for (; pi < npair; pi += N_EPI) {
-                    // reduce pair i
-                    uint32_t mAx = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x), mAy = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
-                    uint32_t mBx = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x), mBy = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
-                    if (wide) {
-                        const uint2 wA = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 6), wB = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 14);
-                        const uint2 a6 = ld(wA.x), a7 = ld(wA.y), b6 = ld(wB.x), b7 = ld(wB.y);
-                        mAx = umax2(mAx, umax2(a6.x, a7.x)); mAy = umax2(mAy, umax2(a6.y, a7.y));
-                        mBx = umax2(mBx, umax2(b6.x, b7.x)); mBy = umax2(mBy, umax2(b6.y, b7.y));
-                    }
-                    const uint2 kA = cA, kB = cB;
-                    // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
-                    v = vn; vn = pair_vertex(pi + 2 * N_EPI);
-                    cA = ld(v * KEY_ROW); cB = ld((v + 1) * KEY_ROW);
-                    a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z);
-                    b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z);
-                    if (p.abl & 16) { a3 = a0; a4 = a1; a5 = a2; b3 = b0; b4 = b1; b5 = b2; }      // (timing ablation: 10 instead of 16 row loads per pair)
-                    else { a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y); }
-                    op = c_nbr_off + vn * NBR_W;
-                    oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
-                    oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
-                    // stored keys have bit 15 set, so per 16-bit half  (k - t + 0x8000) has bit 15 set  <=>  k >= t,
-                    // and the two halves cannot borrow from each other: one 32-bit subtraction tests two voxels.
-                    // threshold t = max(neighbour keys, 1)
-                    const uint32_t hAx = kA.x - mAx + 0x80008000u, hAy = kA.y - mAy + 0x80008000u;
-                    const uint32_t hBx = kB.x - mBx + 0x80008000u, hBy = kB.y - mBy + 0x80008000u;
-                    // No branch in the loop: the result bits of the pair are bit 15 / 31 of the four words.  Two byte
-                    // permutes collect the bytes that hold them (byte b of pA = vertex v, voxel 4*lane + b; same for pB and
-                    // vertex v + 1), one mask + shift + or interleaves them (A at bit 7, B at bit 6 of every byte) and the
-                    // pair of iteration j lands 2 j bits lower: four iterations fill a 32-bit word.
-                    uint32_t pA, pB;
-                    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pA) : "r"(hAx), "r"(hAy));
-                    asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pB) : "r"(hBx), "r"(hBy));
-                    const uint32_t fl = (pA & 0x80808080u) | ((pB >> 1) & 0x40404040u);
-                    const uint32_t sh = (uint32_t)(iter & 3) * 2u;
-                    switch (iter >> 2) {                                // (warp-uniform)
-                        case 0: fw0 |= fl >> sh; break;
-                        case 1: fw1 |= fl >> sh; break;
-                        case 2: fw2 |= fl >> sh; break;
-                        default: fw3 |= fl >> sh; break;
-                    }
-                    ++iter;
-                }
-                // List the hits (typically a dozen lanes per warp and tile have one or two).  The slots come from ONE shared-memory
-                // atomic per warp (warp prefix sum of the per-lane counts): per-lane atomics on the single counter serialise.
-                const uint32_t nhit = (p.abl & 48) ? 0u : __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);   // (ablations 16 / 32: nothing is listed)
-                if (__any_sync(0xffffffffu, nhit != 0u)) {
-                    uint32_t incl = nhit;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                    uint32_t base = 0u;
-                    if (lane == 31) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(ncand32), "r"(incl) : "memory");
-                    base = __shfl_sync(0xffffffffu, base, 31);
-                    uint32_t slot = base + incl - nhit;
-                    const uint32_t fws[4] = {fw0, fw1, fw2, fw3};
-#pragma unroll
-                    for (int wi = 0; wi < 4; ++wi) {
-                        uint32_t bits = fws[wi];
-                        while (bits) {
-                            const int h = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const int r = 7 - (h & 7);                  // 2 * (iteration within the word) + (vertex v + 1 ?)
-                            const int vv = pair_vertex(ew + (wi * 4 + (r >> 1)) * N_EPI) + (r & 1);
-                            if (slot < (uint32_t)p.cand_cap) s_cand[slot] = ((uint32_t)vv << 8) | (uint32_t)(4 * lane + (h >> 3));
-                            ++slot;
-                        }
-                    }
-                }
-            }
-            if (kTma && lane == 0) {                                    // the settle step re-reads this tile's ODF values (L2)
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            named_bar(1, EPI_THREADS);
-            if (warp == W_EPI0) TRACE(5);
-            // ---- phase 3: settle the listed pairs on the exact fp32 values (this CTA wrote them a moment ago: L2 hits).
-            //      Keys that decided strictly need the value only; ties re-run the neighbour test in fp32. ----
-            const uint32_t ncand_raw = *s_ncand;
-            const int ncand = (int)min(ncand_raw, (uint32_t)p.cand_cap);
-            for (int e = et; e < ncand; e += EPI_THREADS) {
-                const uint32_t ent = s_cand[e];
-                const int cv = (int)(ent >> 8), cx = (int)(ent & 0xFFu);
-                const float* col = p.odf + vox0 + cx;
-                const float c = __ldcg(col + (int64_t)cv * p.out_pitch);       // in flight while the keys are compared
-                const uint4 n0 = s_nbr[cv];
-                const uint32_t nn[4] = {n0.x, n0.y, n0.z, n0.w};
-                const uint32_t kc = keys[cv * VOX_CTA + cx];
-                uint32_t kn = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-                    kn = max(kn, (uint32_t)keys[(n != NBR_NONE ? n : (uint32_t)M) * VOX_CTA + cx]);
-                }
-                bool ok = c > 0.f;
-                if (kc <= kn) {                                          // keys tie: repeat the neighbour test in fp32
-                    float nv[8];
+                ncand_raw = s_ncand[pbuf];
+                ncand = (int)min(ncand_raw, (uint32_t)p.cand_cap);
+                if (et < ncand) {
+                    act = true;
+                    const uint32_t ent = s_cand[pbuf * CAND_CAP + et];
+                    cv = (int)(ent >> 8); cx = (int)(ent & 0xFFu);
+                    const float* col = p.odf + vox0_prev + cx;
+                    cval = __ldcg(col + (int64_t)cv * p.out_pitch);
+                    const uint4 n0 = s_nbr[cv];
+                    const uint32_t nn[4] = {n0.x, n0.y, n0.z, n0.w};
+                    const uint32_t kc = keys[cv * VOX_CTA + cx];
+                    uint32_t kn = 0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-                        nv[k] = (n != NBR_NONE) ? __ldcg(col + (int64_t)n * p.out_pitch) : -CUDART_INF_F;
+                        kn = max(kn, (uint32_t)keys[(n != NBR_NONE ? n : (uint32_t)M) * VOX_CTA + cx]);
                     }
+                    tie = kc <= kn;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) ok = ok && (c > nv[k]);
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                        nv[k] = (tie && n != NBR_NONE) ? __ldcg(col + (int64_t)n * p.out_pitch) : -CUDART_INF_F;
+                    }
                 }
-                if (ok) {
-                    // Insert (value, ~index) into the voxel's sorted triple: atomicMax returns what it displaced, and the
-                    // smaller of the two moves down one level.  Larger value wins, equal values -> smaller index wins
-                    // (the reference's stable order).  Every level ends up with the right key whatever the interleaving.
-                    unsigned long long key = ((unsigned long long)__float_as_uint(c) << 32) | (0xFFFFFFFFu - (uint32_t)cv);
-#pragma unroll
-                    for (int lvl = 0; lvl < 3; ++lvl) {
-                        const unsigned long long old = atomicMax(&s_top[lvl * VOX_CTA + cx], key);
-                        key = old < key ? old : key;
-                        if (key == 0ull) break;
+                named_bar(1, EPI_THREADS);                                  // every warp has read the key tile / list size
+                if (et == 0) s_ncand[pbuf] = 0u;
+            }
+            int64_t vox0 = 0;
+            if (have_cur) {
+                const int tile = ident ? ti_ : __ldg(p.tile_list + ti_);
+                vox0 = (int64_t)tile * 256 + rank * VOX_CTA;               // first voxel of this CTA's half
+                const int64_t vox = vox0 + vl;
+                const bool vok = vox < p.nvox;
+                // DSI: p = Re(FFT)/sum(p) with sum(p) = dscale * s+[cvol], folded into the un-scale factor.
+                // A voxel whose q = 0 sample is <= 0 gets zeros: either it is skipped by the reference as well (all
+                // samples <= 0) or the reference divides by zero there (undefined; excluded from parity).
+                float scl = inv_scale;
+                if (p.cvol >= 0) {
+                    const float sc = vok ? __ldg(p.dwi + (int64_t)p.cvol * p.dwi_pitch + vox) : 0.f;
+                    scl = sc > 0.f ? inv_scale * (1.f / (p.dscale * sc)) : 0.f;     // inv_scale is a power of two: exact
+                }
+                mbar_wait<50>(d_full, it & 1);
+                tc_fence_after();
+                if (warp == W_EPI0) TRACE(2);
+                // ---- phase 1: TMEM -> registers -> un-scale -> global ODF (coalesced) + 16-bit key tile ----
+                // key(val) = ceil(32767 * clamp(val * ks, 0, 1)), ks = 1 / (KEY_WINDOW * mean): monotone in val, key >= 1
+                // <=> val > 0.  Stored as 0x8000 | key = the low mantissa bits of fma.rp(sat(val * ks), 32767, 2^23 + 2^15)
+                // (no conversion instruction); the always-set bit 15 lets one 32-bit subtraction compare two packed keys.
+                float mn = CUDART_INF_F, meanv = 0.f;
+                {
+                    float ks = 0.f;
+                    if (!p.plain) {
+                        meanv = __uint_as_float(tmem_ld1(lane_addr + M)) * scl;   // extra matrix row M: mean of the ODF rows
+                        tmem_wait_ld();
+                        ks = (meanv > 0.f && meanv < CUDART_INF_F) ? (1.f / KEY_WINDOW) / meanv : 1e-30f;
                     }
+                    float* gp = p.odf + (int64_t)c_begin * p.out_pitch + (vok ? vox : 0);
+                    uint16_t* kp = keys + c_begin * VOX_CTA + vl;
+                    const int64_t pitch = p.out_pitch;
+                    const bool plain = p.plain != 0;
+                    // key = 0x8000 | ceil(32767 * sat(val * ks)): two instructions (FMUL.SAT, FFMA.RP), the low 16 bits of
+                    // the second result are the stored key
+                    // Row addresses: one 64-bit pointer advanced by an opaque add per row (IADD3 + IADD3.X).  Left to itself the
+                    // compiler rebuilds every row address from the chunk base with IMAD.WIDE chains (3-4 instructions per store).
+                    const int64_t pitch_b = pitch * 4;
+                    auto next_row = [&](float*& g) { asm volatile("add.s64 %0, %0, %1;" : "+l"(g) : "l"(pitch_b)); };
+                    auto st_row = [](float* g, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(g), "f"(v)); };   // (the opaque add hides the address space)
+                    auto process = [&](const uint32_t (&r)[16], int c0) {
+                        const int nrow = min(16, M - c0);                   // warp-uniform
+                        float* g = gp;
+                        if (plain) {
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < nrow && vok) st_row(g, __uint_as_float(r[j]) * scl);
+                                next_row(g);
+                            }
+                        } else if (nrow == 16) {
+                            float prev = CUDART_INF_F;
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float val = __uint_as_float(r[j]) * scl;
+                                if (vok) st_row(g, val);
+                                next_row(g);
+                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                                if (j & 1) asm("min.f32 %0, %0, %1, %2;" : "+f"(mn) : "f"(prev), "f"(val));   // FMNMX3: one instruction per two values
+                                else prev = val;
+                            }
+                        } else {
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (j < nrow) {
+                                    const float val = __uint_as_float(r[j]) * scl;
+                                    if (vok) st_row(g, val);
+                                    const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                                    kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                                    mn = fminf(mn, val);
+                                }
+                                next_row(g);
+                            }
+                        }
+                        gp = g; kp += 16 * VOX_CTA;
+                    };
+                    // TMA mode: the 16 x 32 values of a chunk go to this warp's staging box and leave with ONE bulk tensor store
+                    // (rows >= M and voxels >= nvox are clipped by the tensor map); the box is reused two chunks later, once the
+                    // TMA unit has read it.  The drain then runs at TMEM / issue speed instead of the store port's.
+                    const int vcoord = (int)vox0 + q * 32;
+                    long long box_wait = 0;                                // (trace only)
+                    auto process_tma = [&](const uint32_t (&r)[16], int c0) {
+                        const int nrow = min(16, M - c0);                   // warp-uniform
+                        const uint32_t bx = obox0 + (oc % obufm) * WBOX + lane * 4;
+                        const long long tw0 = (kTrace && p.trace && warp == W_EPI0) ? clock64() : 0;
+                        if (lane == 0) {
+                            if (p.obuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                        __syncwarp();
+                        if (kTrace && p.trace && warp == W_EPI0) { box_wait += clock64() - tw0; TRACE(17 + ((c0 - c_begin) >> 4)); }
+                        if (plain) {
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(__uint_as_float(r[j]) * scl) : "memory");
+                        } else if (nrow == 16) {
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float val = __uint_as_float(r[j]) * scl;
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
+                                const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                                kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                                mn = fminf(mn, val);
+                            }
+                        } else {
+    #pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float val = __uint_as_float(r[j]) * scl;
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bx + j * 128), "f"(val) : "memory");
+                                if (j < nrow) {
+                                    const float y = __fmaf_ru(__saturatef(val * ks), 32767.f, 8421376.f);
+                                    kp[j * VOX_CTA] = (uint16_t)__float_as_uint(y);
+                                    mn = fminf(mn, val);
+                                }
+                            }
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                                         ::"l"(&tmapO), "r"(vcoord), "r"(c0), "r"(bx) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        kp += 16 * VOX_CTA; ++oc;
+                    };
+                    const bool staged = kTma && p.obuf > 0;
+                    auto step = [&](const uint32_t (&r)[16], int c0) { if (p.abl & 4) { mn = fminf(mn, __uint_as_float(r[0])); return; } if (staged) process_tma(r, c0); else process(r, c0); };
+                    uint32_t ra[16], rb[16];                               // double buffer: the next chunk's load is in flight
+                    if (c_begin < c_end) tmem_ld16(lane_addr + c_begin, ra);
+                    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                        tmem_wait_ld();
+                        if (c0 + 16 < c_end) tmem_ld16(lane_addr + c0 + 16, rb);
+                        step(ra, c0);
+                        if (c0 + 16 < c_end) {
+                            tmem_wait_ld();
+                            if (c0 + 32 < c_end) tmem_ld16(lane_addr + c0 + 32, ra);
+                            step(rb, c0 + 16);
+                        }
+                    }
+                    if (kTma && kTrace && p.trace && warp == W_EPI0) TRACE_ADD(24, box_wait);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(dempty0);               // TMEM may be overwritten by the next tile
+                if (warp == W_EPI0) TRACE(3);
+                if (!p.plain) {
+                    s_min[(buf * N_CPART + cpart) * VOX_CTA + vl] = mn;
+                    if (cpart == 0) s_mean[buf * VOX_CTA + vl] = meanv;
                 }
             }
-            named_bar(1, EPI_THREADS);
-            if (warp == W_EPI0) TRACE(6);
-            // ---- outputs: warp group k (4 warps = 128 voxels) writes peak k; group 0 also owns the statistics ----
-            {
+            if (p.plain) continue;                                          // rows only (DSI pdf): nothing is staged
+            // ---- settle-finish (previous tile) ----
+            if (have_prev) {
+                unsigned long long* top = s_top + pbuf * 3 * VOX_CTA;
+                if (act) {
+                    bool ok = cval > 0.f;
+                    if (tie) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) ok = ok && (cval > nv[k]);
+                    }
+                    if (ok) insert_top(top, cv, cx, cval);
+                }
+                // more listed pairs than threads (rare): the rest is settled on fp32 values alone (the key tile is gone)
+                for (int e = et + EPI_THREADS; e < ncand; e += EPI_THREADS) {
+                    const uint32_t ent = s_cand[pbuf * CAND_CAP + e];
+                    const int ev = (int)(ent >> 8), ex = (int)(ent & 0xFFu);
+                    const float* col = p.odf + vox0_prev + ex;
+                    const float c = __ldcg(col + (int64_t)ev * p.out_pitch);
+                    const uint4 n0 = s_nbr[ev];
+                    const uint32_t nn[4] = {n0.x, n0.y, n0.z, n0.w};
+                    float w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t n = (nn[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+                        w[k] = (n != NBR_NONE) ? __ldcg(col + (int64_t)n * p.out_pitch) : -CUDART_INF_F;
+                    }
+                    bool ok = c > 0.f;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ok = ok && (c > w[k]);
+                    if (ok) insert_top(top, ev, ex, c);
+                }
+            }
+            named_bar(1, EPI_THREADS);          // sorted triples of the previous tile complete; key tile + ODF stores of this tile visible to the group
+            if (warp == W_EPI0) TRACE(4);
+            // ---- outputs (previous tile): warp group k (4 warps = 128 voxels) writes peak k; group 0 also owns the statistics ----
+            if (have_prev) {
+                unsigned long long* top = s_top + pbuf * 3 * VOX_CTA;
                 const int k = ew >> 2;                                  // 0..2 (N_EPI == 12)
                 const int ov = (ew & 3) * 32 + lane;                    // voxel within the CTA
-                const int64_t ovox = vox0 + ov;
+                const int64_t ovox = vox0_prev + ov;
                 const bool ook = ovox < p.nvox;
-                float omin = s_min[ov];
+                float omin = s_min[pbuf * N_CPART * VOX_CTA + ov];
 #pragma unroll
-                for (int cp = 1; cp < N_CPART; ++cp) omin = fminf(omin, s_min[cp * VOX_CTA + ov]);
-                if (ook && k < 3) {
-                    const unsigned long long key = s_top[k * VOX_CTA + ov];
-                    const bool ok = key != 0ull;
-                    const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
-                    const float val = __uint_as_float((uint32_t)(key >> 32));
-                    p.peak[k][ovox]                   = ok ? s_vert[id * 3 + 0] : 0.f;
-                    p.peak[k][ovox + p.out_pitch]     = ok ? s_vert[id * 3 + 1] : 0.f;
-                    p.peak[k][ovox + 2 * p.out_pitch] = ok ? s_vert[id * 3 + 2] : 0.f;
-                    p.qa[k][ovox] = ok ? val - omin : 0.f;
-                    if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
+                for (int cp = 1; cp < N_CPART; ++cp) omin = fminf(omin, s_min[(pbuf * N_CPART + cp) * VOX_CTA + ov]);
+                {
+                    const unsigned long long key = top[k * VOX_CTA + ov];
+                    top[k * VOX_CTA + ov] = 0ull;                       // (this thread is the entry's only reader) ready for the tile after next
+                    if (ook) {
+                        const bool ok = key != 0ull;
+                        const int id = ok ? (int)(0xFFFFFFFFu - (uint32_t)key) : 0;
+                        const float val = __uint_as_float((uint32_t)(key >> 32));
+                        p.peak[k][ovox]                   = ok ? s_vert[id * 3 + 0] : 0.f;
+                        p.peak[k][ovox + p.out_pitch]     = ok ? s_vert[id * 3 + 1] : 0.f;
+                        p.peak[k][ovox + 2 * p.out_pitch] = ok ? s_vert[id * 3 + 2] : 0.f;
+                        p.qa[k][ovox] = ok ? val - omin : 0.f;
+                        if (p.peak_idx) p.peak_idx[ovox + k * p.out_pitch] = ok ? (int16_t)id : (int16_t)-1;
+                    }
                 }
                 if (k == 0) {
-                    float mean = s_mean[ov];
+                    float mean = s_mean[pbuf * VOX_CTA + ov];
                     // fp16 overflow of the scaled signal (every accumulator column of the voxel, the mean row included, is
                     // then non-finite), or more listed pairs than the list holds
                     const bool bad = ook && (!(fabsf(mean) < CUDART_INF_F) || ncand_raw > (uint32_t)p.cand_cap);
@@ -994,15 +947,121 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                         if (mean > -CUDART_INF_F) atomicMax(p.stats, f2ord(mean));
                         if (anybad) {                                   // recompute this 64-voxel tile with the SIMT kernel
                             const int slot = atomicAdd(p.fix_count, 1);
-                            if (slot < p.fix_cap) p.fix_list[slot] = (int)((vox0 + (ew & 3) * 32) >> 6);
+                            if (slot < p.fix_cap) p.fix_list[slot] = (int)((vox0_prev + (ew & 3) * 32) >> 6);
                         }
                     }
                 }
+                if (warp == W_EPI0) TRACE(7);
             }
-            if (et == 0) *s_ncand = 0u;
-            if (warp == W_EPI0) TRACE(7);
-            named_bar(1, EPI_THREADS);                                  // key tile / lists free for the next tile
-            if (warp == W_EPI0) TRACE(8);
+            if (have_cur) {
+                // ---- phase 2: scan.  A vertex can only be a local maximum (value > 0, > every mesh neighbour) if its
+                //      key is >= max(neighbour keys, 1); equality means "cannot tell from the keys".  Both kinds are
+                //      listed.  Two vertices per iteration; software-pipelined: the keys of pair i+1 and the offsets of
+                //      pair i+2 are in flight while pair i is tested.  (Prefetches past the warp's range touch rows
+                //      < M + 8 of the offset table / key tile, which exist; their values are never tested.) ----
+                if (!(p.abl & 2)) {
+                    uint32_t kb = smem_u32(keys) + lane * 8;
+                    asm volatile("mov.u32 %0, %0;" : "+r"(kb));             // pin: keeps the compiler from re-deriving the base in every iteration
+                    const uint32_t ncand32 = smem_u32(s_ncand + buf);
+                    auto ld = [&](uint32_t off) {
+                        uint2 r; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(kb + off)); return r;
+                    };
+                    // max of the six neighbour keys and of the threshold key 1 (two packed voxels): three 3-input packed max
+                    auto max6 = [](uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+                        return umax2(umax2(umax2(umax2(a, b), c), umax2(umax2(d, e), f)), 0x80018001u);
+                    };
+                    const bool wide = p.nbw > 6;                            // warp-uniform (meshes with degree 7-8)
+                    // Vertex pairs are dealt round-robin to the warps (pair ew, ew + N_EPI, ...): ODF peaks are spatially
+                    // compact, so contiguous ranges would give all the listing work of a tile to one or two warps.
+                    const int npair = (M + 1) >> 1;
+                    auto pair_vertex = [&](int pi) { return 2 * min(pi, npair); };      // past the end -> sentinel rows
+                    int pi = ew;
+                    int v = pair_vertex(pi), vn = pair_vertex(pi + N_EPI);
+                    const uint32_t* op = c_nbr_off + v * NBR_W;
+                    uint4 oA0 = *reinterpret_cast<const uint4*>(op), oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                    uint2 oA1 = *reinterpret_cast<const uint2*>(op + 4), oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                    uint2 cA = ld(v * KEY_ROW), cB = ld((v + 1) * KEY_ROW);
+                    uint2 a0 = ld(oA0.x), a1 = ld(oA0.y), a2 = ld(oA0.z), a3 = ld(oA0.w), a4 = ld(oA1.x), a5 = ld(oA1.y);
+                    uint2 b0 = ld(oB0.x), b1 = ld(oB0.y), b2 = ld(oB0.z), b3 = ld(oB0.w), b4 = ld(oB1.x), b5 = ld(oB1.y);
+                    op = c_nbr_off + vn * NBR_W;
+                    oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                    oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                    uint32_t fw0 = 0u, fw1 = 0u, fw2 = 0u, fw3 = 0u;       // result bits: one byte per iteration (<= 16 iterations: M <= 383)
+                    int iter = 0;
+                    for (; pi < npair; pi += N_EPI) {
+                        // reduce pair i
+                        uint32_t mAx = max6(a0.x, a1.x, a2.x, a3.x, a4.x, a5.x), mAy = max6(a0.y, a1.y, a2.y, a3.y, a4.y, a5.y);
+                        uint32_t mBx = max6(b0.x, b1.x, b2.x, b3.x, b4.x, b5.x), mBy = max6(b0.y, b1.y, b2.y, b3.y, b4.y, b5.y);
+                        if (wide) {
+                            const uint2 wA = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 6), wB = *reinterpret_cast<const uint2*>(c_nbr_off + v * NBR_W + 14);
+                            const uint2 a6 = ld(wA.x), a7 = ld(wA.y), b6 = ld(wB.x), b7 = ld(wB.y);
+                            mAx = umax2(mAx, umax2(a6.x, a7.x)); mAy = umax2(mAy, umax2(a6.y, a7.y));
+                            mBx = umax2(mBx, umax2(b6.x, b7.x)); mBy = umax2(mBy, umax2(b6.y, b7.y));
+                        }
+                        const uint2 kA = cA, kB = cB;
+                        // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
+                        v = vn; vn = pair_vertex(pi + 2 * N_EPI);
+                        cA = ld(v * KEY_ROW); cB = ld((v + 1) * KEY_ROW);
+                        a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z);
+                        b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z);
+                        if (p.abl & 16) { a3 = a0; a4 = a1; a5 = a2; b3 = b0; b4 = b1; b5 = b2; }      // (timing ablation: 10 instead of 16 row loads per pair)
+                        else { a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y); }
+                        op = c_nbr_off + vn * NBR_W;
+                        oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
+                        oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
+                        // stored keys have bit 15 set, so per 16-bit half  (k - t + 0x8000) has bit 15 set  <=>  k >= t,
+                        // and the two halves cannot borrow from each other: one 32-bit subtraction tests two voxels.
+                        // threshold t = max(neighbour keys, 1)
+                        const uint32_t hAx = kA.x - mAx + 0x80008000u, hAy = kA.y - mAy + 0x80008000u;
+                        const uint32_t hBx = kB.x - mBx + 0x80008000u, hBy = kB.y - mBy + 0x80008000u;
+                        // No branch in the loop: the result bits of the pair are bit 15 / 31 of the four words.  Two byte
+                        // permutes collect the bytes that hold them (byte b of pA = vertex v, voxel 4*lane + b; same for pB and
+                        // vertex v + 1), one mask + shift + or interleaves them (A at bit 7, B at bit 6 of every byte) and the
+                        // pair of iteration j lands 2 j bits lower: four iterations fill a 32-bit word.
+                        uint32_t pA, pB;
+                        asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pA) : "r"(hAx), "r"(hAy));
+                        asm("prmt.b32 %0, %1, %2, 0x7531;" : "=r"(pB) : "r"(hBx), "r"(hBy));
+                        const uint32_t fl = (pA & 0x80808080u) | ((pB >> 1) & 0x40404040u);
+                        const uint32_t sh = (uint32_t)(iter & 3) * 2u;
+                        switch (iter >> 2) {                                // (warp-uniform)
+                            case 0: fw0 |= fl >> sh; break;
+                            case 1: fw1 |= fl >> sh; break;
+                            case 2: fw2 |= fl >> sh; break;
+                            default: fw3 |= fl >> sh; break;
+                        }
+                        ++iter;
+                    }
+                    // List the hits (typically a dozen lanes per warp and tile have one or two).  The slots come from ONE shared-memory
+                    // atomic per warp (warp prefix sum of the per-lane counts): per-lane atomics on the single counter serialise.
+                    const uint32_t nhit = (p.abl & 48) ? 0u : __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);   // (ablations 16 / 32: nothing is listed)
+                    if (__any_sync(0xffffffffu, nhit != 0u)) {
+                        uint32_t incl = nhit;
+    #pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                        uint32_t base = 0u;
+                        if (lane == 31) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(ncand32), "r"(incl) : "memory");
+                        base = __shfl_sync(0xffffffffu, base, 31);
+                        uint32_t slot = base + incl - nhit;
+                        const uint32_t fws[4] = {fw0, fw1, fw2, fw3};
+    #pragma unroll
+                        for (int wi = 0; wi < 4; ++wi) {
+                            uint32_t bits = fws[wi];
+                            while (bits) {
+                                const int h = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                const int r = 7 - (h & 7);                  // 2 * (iteration within the word) + (vertex v + 1 ?)
+                                const int vv = pair_vertex(ew + (wi * 4 + (r >> 1)) * N_EPI) + (r & 1);
+                                if (slot < (uint32_t)p.cand_cap) s_cand[buf * CAND_CAP + slot] = ((uint32_t)vv << 8) | (uint32_t)(4 * lane + (h >> 3));
+                                ++slot;
+                            }
+                        }
+                    }
+                }
+                named_bar(1, EPI_THREADS);                                  // candidate list of this tile complete
+                if (warp == W_EPI0) TRACE(5);
+            }
+            have_prev = have_cur;
+            vox0_prev = vox0;
         }
     }
 
@@ -1023,7 +1082,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 
 // dynamic shared memory of one instantiation (carve-up of recon_tc_kernel; M = 0 for plain passes)
 size_t tc_smem_bytes(bool tma, int M, int Nh, int nstage, int tstage, int obuf) {
-    size_t b = (size_t)nstage * 2 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + 3 * VOX_CTA * 8 + (size_t)CAND_CAP * 4 + (N_CPART + 1) * VOX_CTA * 4;
+    size_t b = (size_t)nstage * 2 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + 2 * (3 * VOX_CTA * 8 + (size_t)CAND_CAP * 4 + (N_CPART + 1) * VOX_CTA * 4);
     b = (b + 127) & ~(size_t)127;
     b += tma ? (size_t)tstage * 16 * VOX_CTA * 4 + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
     b += (size_t)M * 16 + (size_t)((3 * M + 3) & ~3) * 4 + (2 * NSTAGE + 2 * ASLOT + 2 + 2 * TSTAGE) * 8 + 16;

@@ -1,0 +1,278 @@
+// Deterministic streamline tractography on the GPU (`stream`, the downstream consumer of
+// the GQI / DSI / DTI peaks).  Replaces the `Threads.@threads` seed loop of the reference (src/stream.jl:730-790) and the
+// per-seed propagation it calls (stream_new_line :621-690, stream_new_point! :497-541, stream_pick_by_angle! :355-387)
+// for the regime that has a deterministic answer: orientation VECTORS, no local connection matrices (that branch draws
+// from rand(Categorical(...))), macroscopic voxels (voxel size > 50 um).
+//
+//   stream_pack_kernel   the StreamWork constructor (:72-147): voxel mask (given, or "any vector component non-zero"),
+//                        intersected with fa >= fa_thresh; vectors zeroed outside the mask / where f[ivec] < f_thresh;
+//                        packed as [voxel][ivec][3] (= W.ovecs[3, nvec, nx, ny, nz]), so that one propagation step reads
+//                        12 nvec contiguous bytes.
+//   stream_track_kernel  one thread per (seed voxel, sub-voxel sample), seeds in column-major order, samples innermost
+//                        (the reference's output order).  Run twice: a counting pass (points forward / backward), an
+//                        exclusive scan over the lines that reach len_min, and a writing pass that puts every point at
+//                        its final place -- forward points are PREPENDED by the reference (:660), so forward point i of nf
+//                        lands at nf - 1 - i and backward point j at nf + j.  Nothing is compacted on the host.
+// The reference's quirks are kept: the seed position is stored once per direction, the point counter runs on across
+// the two directions (:681), and the backward pass starts along vector `ivec_next` of the SEED voxel where `ivec_next`
+// is whatever the forward pass chose last (:646, :653).
+//
+// Arithmetic follows the reference's fp32 operation order (this file is compiled with -fmad=false): positions and
+// vectors in fp32, dot products as (a1 b1 + a2 b2) + a3 b3, `norm` = squares in fp32, sum and square root in fp64
+// (LinearAlgebra.generic_norm2), IEEE division, round-half-even for round(Int, x).
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+
+namespace fibers {
+namespace {
+
+constexpr int MAX_NVEC = 8;
+
+struct PackIn { const float* ovec[MAX_NVEC]; const float* f[MAX_NVEC]; };
+
+// mask_out[v] (u8), ovec_out[v][i][3]; inputs are the reference's volumes: component c of vector volume i at ovec[i][c * nvox + v]
+__global__ void stream_pack_kernel(PackIn in, int nvec, int has_f, float f_thresh, const float* __restrict__ fa, float fa_thresh,
+                                   const uint8_t* __restrict__ mask, int64_t nvox, uint8_t* __restrict__ mask_out, float* __restrict__ ovec_out) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    float x[MAX_NVEC][3];
+    bool m;
+    if (mask) m = mask[v] != 0;
+    else m = false;
+    for (int i = 0; i < nvec; ++i)
+        for (int c = 0; c < 3; ++c) {
+            x[i][c] = in.ovec[i][(int64_t)c * nvox + v];
+            if (!mask && x[i][c] != 0.f) m = true;                    // (:107-112) NaN != 0 counts, as in Julia
+        }
+    if (fa) m = m && (fa[v] >= fa_thresh);                            // (:128)
+    mask_out[v] = m ? 1 : 0;
+    for (int i = 0; i < nvec; ++i) {
+        const bool om = has_f ? (m && in.f[i][v] >= f_thresh) : m;    // (:136-138)
+        for (int c = 0; c < 3; ++c) ovec_out[(v * nvec + i) * 3 + c] = om ? x[i][c] : 0.f;
+    }
+}
+
+struct TrackParams {
+    const float* ovec; const uint8_t* mask; const int32_t* seeds; int64_t nseed; const float* sub; int nsub;
+    int nx, ny, nz, nvec, len_min, len_max; float cos_thresh, step, smooth;
+};
+
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) { return (a0 * b0 + a1 * b1) + a2 * b2; }
+
+// kWrite == false: counts -> nfb[line] = (points forward, points backward).
+// kWrite == true : points -> xyz + 3 * off[line] for the lines with kept[line] != 0 (nfb gives nf).
+template <bool kWrite>
+__global__ void __launch_bounds__(128) stream_track_kernel(TrackParams P, int2* __restrict__ nfb, const int64_t* __restrict__ off,
+                                                            const int32_t* __restrict__ sidx, const uint8_t* __restrict__ kept,
+                                                            float* __restrict__ xyz, int32_t* __restrict__ npts_out) {
+    const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= P.nseed * P.nsub) return;
+    int nf_known = 0;
+    float* out = nullptr;
+    if (kWrite) {
+        if (!kept[line]) return;
+        const int2 c = nfb[line];
+        nf_known = c.x;
+        out = xyz + 3 * off[line];
+        npts_out[sidx[line]] = c.x + c.y;
+    }
+    const int64_t si = line / P.nsub; const int isub = (int)(line - si * P.nsub);
+    const int lin = P.seeds[si];
+    const int sx = lin % P.nx, sy = (lin / P.nx) % P.ny, sz = lin / (P.nx * P.ny);      // 0-based seed voxel
+    const float s0 = P.sub[isub * 3 + 0], s1 = P.sub[isub * 3 + 1], s2 = P.sub[isub * 3 + 2];
+    int ivec = 0;                                          // W.ivec_next[tid] - 1 (:646): NOT reset between the directions
+    int npts = 0, nf = 0, nb = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        const float fwd = dir == 0 ? 1.f : -1.f;
+        float px = (float)(sx + 1) + s0, py = (float)(sy + 1) + s1, pz = (float)(sz + 1) + s2;     // 1-based coordinates (:652)
+        const float* sv = P.ovec + ((int64_t)lin * P.nvec + ivec) * 3;
+        float vx = sv[0] * fwd, vy = sv[1] * fwd, vz = sv[2] * fwd;                                 // (:653)
+        while (true) {
+            // ---- stream_new_point! (:497-541) ----
+            const float qx = px + vx * P.step, qy = py + vy * P.step, qz = pz + vz * P.step;
+            const int ix = __float2int_rn(qx), iy = __float2int_rn(qy), iz = __float2int_rn(qz);
+            if (ix < 1 || ix > P.nx || iy < 1 || iy > P.ny || iz < 1 || iz > P.nz) break;
+            const int64_t nl = (int64_t)(ix - 1) + (int64_t)P.nx * ((iy - 1) + (int64_t)P.ny * (iz - 1));
+            if (!P.mask[nl]) break;
+            // ---- stream_pick_by_angle! (:355-387): argmax of |cos|, first maximum, NaN first ----
+            const float* ov = P.ovec + nl * P.nvec * 3;
+            int best = 0; float bcos = 0.f, babs = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+            for (int i = 0; i < P.nvec; ++i) {
+                const float wx = ov[3 * i], wy = ov[3 * i + 1], wz = ov[3 * i + 2];
+                float c, a;
+                if (wx == 0.f && wy == 0.f && wz == 0.f) c = a = -INFINITY;
+                else { c = dot3(vx, vy, vz, wx, wy, wz); a = fabsf(c); }
+                if (i == 0 || (!isnan(babs) && (isnan(a) || a > babs))) { best = i; bcos = c; babs = a; bx = wx; by = wy; bz = wz; }
+            }
+            if (!isfinite(bcos)) break;
+            float nxv, nyv, nzv;
+            if (bcos > 0.f) { nxv = bx; nyv = by; nzv = bz; } else { nxv = -bx; nyv = -by; nzv = -bz; }
+            ivec = best;
+            // ---- stream_new_line: save the CURRENT position (:660 / :666) ----
+            if (kWrite) {
+                float* o = out + 3 * (int64_t)(dir == 0 ? nf_known - 1 - nf : nf_known + nb);
+                o[0] = px; o[1] = py; o[2] = pz;
+            }
+            if (dir == 0) ++nf; else ++nb;
+            ++npts;
+            if (dot3(vx, vy, vz, nxv, nyv, nzv) < P.cos_thresh) break;                              // (:677)
+            if (npts > P.len_max) break;                                                            // (:681)
+            if (P.smooth != 0.f) {                                                                  // (:684-688)
+                const float om = 1.f - P.smooth;
+                const float tx = P.smooth * vx + om * nxv, ty = P.smooth * vy + om * nyv, tz = P.smooth * vz + om * nzv;
+                const float nrm = (float)sqrt(((double)(tx * tx) + (double)(ty * ty)) + (double)(tz * tz));
+                nxv = tx / nrm; nyv = ty / nrm; nzv = tz / nrm;
+            }
+            px = qx; py = qy; pz = qz; vx = nxv; vy = nyv; vz = nzv;
+        }
+    }
+    if (!kWrite) nfb[line] = make_int2(nf, nb);
+}
+
+__global__ void stream_len_kernel(const int2* __restrict__ nfb, int64_t n, int len_min, int64_t* __restrict__ len, int32_t* __restrict__ keep32, uint8_t* __restrict__ kept) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = nfb[i].x + nfb[i].y;
+    const bool k = t >= len_min;                                       // (:768)
+    len[i] = k ? t : 0; keep32[i] = k ? 1 : 0; kept[i] = k ? 1 : 0;
+}
+
+struct DevBuf { std::vector<void*> p; ~DevBuf() { for (void* q : p) cudaFree(q); }
+                template <class T> cudaError_t alloc(T** o, size_t n) { void* q = nullptr; cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) p.push_back(q); *o = (T*)q; return e; } };
+
+struct StreamResult { int device; int64_t nstr, npts; int32_t* d_npts; float* d_xyz; };
+
+}  // namespace
+}  // namespace fibers
+
+using namespace fibers;
+#define T_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? FIBERS_ERR_NOMEM : FIBERS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+// Device-resident core: every volume pointer is a DEVICE pointer (e.g. the peak / qa planes a reconstruction just wrote).
+extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
+                                    const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
+                                    const float* sublist /*host [nsub][3]*/, int nsub, int len_min, int len_max, float cosang_thresh,
+                                    float step_size, float smooth_coeff, void** result, int64_t* nstr, int64_t* npts_total) {
+    if (!d_ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
+    if (nx <= 0 || ny <= 0 || nz <= 0 || nsub <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions and the number of sub-voxel samples must be positive");
+    const int64_t nvox = (int64_t)nx * ny * nz;
+    if (nvox >= (1ll << 31)) return fail(FIBERS_ERR_ARG, "volume too large");
+    *result = nullptr; *nstr = 0; *npts_total = 0;
+    int device = 0;
+    T_CUDA(cudaGetDevice(&device));
+    DevBuf D;
+    uint8_t* mask_arr; float* ovec_arr;
+    T_CUDA(D.alloc(&mask_arr, (size_t)nvox)); T_CUDA(D.alloc(&ovec_arr, (size_t)nvox * nvec * 3));
+    PackIn in{};
+    for (int i = 0; i < nvec; ++i) { in.ovec[i] = d_ovec[i]; in.f[i] = d_f ? d_f[i] : nullptr; if (!in.ovec[i] || (d_f && !in.f[i])) return fail(FIBERS_ERR_ARG, "NULL volume pointer"); }
+    const unsigned gv = (unsigned)((nvox + 255) / 256);
+    stream_pack_kernel<<<gv, 256>>>(in, nvec, d_f ? 1 : 0, f_thresh, d_fa, fa_thresh, d_mask, nvox, mask_arr, ovec_arr);
+    count_launch(1);
+    T_CUDA(cudaGetLastError());
+    // seed voxels in ascending (column-major) order: findall(W.mask .> 0) or findall(seed.vol .> 0)  (:744-754)
+    int32_t* seeds; int* d_nseed;
+    T_CUDA(D.alloc(&seeds, (size_t)nvox)); T_CUDA(D.alloc(&d_nseed, 1));
+    const uint8_t* flags = d_seed ? d_seed : mask_arr;
+    {
+        size_t tb = 0;
+        cub::CountingInputIterator<int32_t> cnt(0);
+        T_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cnt, flags, seeds, d_nseed, (int)nvox));
+        uint8_t* tmp; T_CUDA(D.alloc(&tmp, tb));
+        T_CUDA(cub::DeviceSelect::Flagged(tmp, tb, cnt, flags, seeds, d_nseed, (int)nvox));
+        count_launch(1);
+    }
+    int nseed = 0;
+    T_CUDA(cudaMemcpy(&nseed, d_nseed, sizeof(int), cudaMemcpyDeviceToHost));
+    const int64_t nline = (int64_t)nseed * nsub;
+    if (nline == 0) return 0;
+    float* d_sub; T_CUDA(D.alloc(&d_sub, (size_t)nsub * 3));
+    T_CUDA(cudaMemcpy(d_sub, sublist, sizeof(float) * 3 * nsub, cudaMemcpyHostToDevice));
+    int2* nfb; int64_t *len, *off; int32_t *keep32, *sidx; uint8_t* kept;
+    T_CUDA(D.alloc(&nfb, (size_t)nline)); T_CUDA(D.alloc(&len, (size_t)nline + 1)); T_CUDA(D.alloc(&off, (size_t)nline + 1));
+    T_CUDA(D.alloc(&keep32, (size_t)nline + 1)); T_CUDA(D.alloc(&sidx, (size_t)nline + 1)); T_CUDA(D.alloc(&kept, (size_t)nline));
+    TrackParams P{ovec_arr, mask_arr, seeds, nseed, d_sub, nsub, nx, ny, nz, nvec, len_min, len_max, cosang_thresh, step_size, smooth_coeff};
+    const unsigned gl = (unsigned)((nline + 127) / 128);
+    stream_track_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
+    stream_len_kernel<<<(unsigned)((nline + 255) / 256), 256>>>(nfb, nline, len_min, len, keep32, kept);
+    count_launch(2);
+    T_CUDA(cudaMemsetAsync(len + nline, 0, sizeof(int64_t))); T_CUDA(cudaMemsetAsync(keep32 + nline, 0, sizeof(int32_t)));
+    {
+        size_t t1 = 0, t2 = 0;
+        T_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t1, len, off, (int)(nline + 1)));
+        T_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, t2, keep32, sidx, (int)(nline + 1)));
+        uint8_t* tmp; T_CUDA(D.alloc(&tmp, std::max(t1, t2)));
+        T_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t1, len, off, (int)(nline + 1)));
+        T_CUDA(cub::DeviceScan::ExclusiveSum(tmp, t2, keep32, sidx, (int)(nline + 1)));
+        count_launch(2);
+    }
+    int64_t total = 0; int32_t nkeep = 0;
+    T_CUDA(cudaMemcpy(&total, off + nline, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    T_CUDA(cudaMemcpy(&nkeep, sidx + nline, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    StreamResult* R = new StreamResult{device, nkeep, total, nullptr, nullptr};
+    if (cudaMalloc(&R->d_npts, sizeof(int32_t) * std::max<int64_t>(nkeep, 1)) != cudaSuccess ||
+        cudaMalloc(&R->d_xyz, sizeof(float) * 3 * std::max<int64_t>(total, 1)) != cudaSuccess) {
+        cudaFree(R->d_npts); cudaFree(R->d_xyz); delete R; cudaGetLastError();
+        return fail(FIBERS_ERR_NOMEM, "stream: device allocation of the streamline buffers failed");
+    }
+    if (nkeep > 0) {
+        stream_track_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
+        count_launch(1);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaFree(R->d_npts); cudaFree(R->d_xyz); delete R; return fail(FIBERS_ERR_CUDA, std::string("stream: ") + cudaGetErrorString(e)); }
+    *result = R; *nstr = nkeep; *npts_total = total;
+    return 0;
+}
+
+extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
+                             const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
+                             int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff, int device,
+                             void** result, int64_t* nstr, int64_t* npts_total) {
+    if (!ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
+    if (nx <= 0 || ny <= 0 || nz <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions must be positive");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(FIBERS_ERR_NODEV, "no CUDA device available (libfibers_cuda has no CPU fallback)"); }
+    if (device < 0 || device >= n) return fail(FIBERS_ERR_ARG, "device ordinal out of range");
+    T_CUDA(cudaSetDevice(device));
+    const int64_t nvox = (int64_t)nx * ny * nz;
+    DevBuf D;
+    const float* d_ovec[MAX_NVEC]; const float* d_f[MAX_NVEC];
+    auto up = [&](const void* h, size_t bytes, const void** d) -> int {
+        uint8_t* q; T_CUDA(D.alloc(&q, bytes)); T_CUDA(cudaMemcpy(q, h, bytes, cudaMemcpyHostToDevice)); *d = q; return 0;
+    };
+    for (int i = 0; i < nvec; ++i) {
+        if (!ovec[i] || (f && !f[i])) return fail(FIBERS_ERR_ARG, "NULL volume pointer");
+        if (int rc = up(ovec[i], sizeof(float) * 3 * nvox, (const void**)&d_ovec[i])) return rc;
+        if (f) if (int rc = up(f[i], sizeof(float) * nvox, (const void**)&d_f[i])) return rc;
+    }
+    const float* d_fa = nullptr; const uint8_t *d_mask = nullptr, *d_seed = nullptr;
+    if (fa) if (int rc = up(fa, sizeof(float) * nvox, (const void**)&d_fa)) return rc;
+    if (mask) if (int rc = up(mask, (size_t)nvox, (const void**)&d_mask)) return rc;
+    if (seed) if (int rc = up(seed, (size_t)nvox, (const void**)&d_seed)) return rc;
+    return fibers_stream_device(d_ovec, nvec, nx, ny, nz, f ? d_f : nullptr, f_thresh, d_fa, fa_thresh, d_mask, d_seed, sublist, nsub,
+                                len_min, len_max, cosang_thresh, step_size, smooth_coeff, result, nstr, npts_total);
+}
+
+extern "C" int fibers_stream_fetch(void* result, int32_t* npts, float* xyz) {
+    StreamResult* R = (StreamResult*)result;
+    if (!R) return fail(FIBERS_ERR_ARG, "NULL result handle");
+    T_CUDA(cudaSetDevice(R->device));
+    if (npts && R->nstr > 0) T_CUDA(cudaMemcpy(npts, R->d_npts, sizeof(int32_t) * R->nstr, cudaMemcpyDeviceToHost));
+    if (xyz && R->npts > 0) T_CUDA(cudaMemcpy(xyz, R->d_xyz, sizeof(float) * 3 * R->npts, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" void fibers_stream_free(void* result) {
+    StreamResult* R = (StreamResult*)result;
+    if (!R) return;
+    cudaSetDevice(R->device);
+    cudaFree(R->d_npts); cudaFree(R->d_xyz);
+    delete R;
+}

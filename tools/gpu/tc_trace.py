@@ -43,8 +43,8 @@ if len(span):
     print(f"cluster 0: {cyc[1] - cyc[0]} SM cycles in {(span[0, 1] - span[0, 0]) / 1e3:.0f} us -> effective SM clock {(cyc[1] - cyc[0]) / (span[0, 1] - span[0, 0]) * 1e3:.0f} MHz")
     print("slowest clusters:", np.argsort(-dur)[:8].tolist(), " fastest:", np.argsort(dur)[:8].tolist())
 t0 = t[0, 0]
-names = {0: "mma:start", 1: "mma:done", 2: "epi:d_full", 3: "epi:tmem_read_done", 4: "epi:bar1", 5: "epi:peaks_done", 6: "epi:bar2",
-         7: "epi:merge_done", 8: "epi:bar3", 9: "conv:tile_start", 10: "conv:first_loads_issued", 11: "conv:a_empty_ok", 12: "conv:tile_end",
+names = {0: "mma:start", 1: "mma:done", 2: "epi:d_full", 3: "epi:tmem_read_done", 4: "epi:settle(prev)_done+bar", 7: "epi:outputs(prev)_done",
+         5: "epi:scan_done+bar", 9: "conv:tile_start", 10: "conv:first_loads_issued", 11: "conv:a_empty_ok", 12: "conv:tile_end",
          13: "tma:tile_start", 14: "tma:tile_end"}
 for it in range(8):
     ev = sorted((int(t[it, k] - t0), names[k]) for k in names if t[it, k])
