@@ -1002,10 +1002,8 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                         // issue pair i+1 (offsets arrived during the previous iteration) and fetch the offsets of pair i+2
                         v = vn; vn = pair_vertex(pi + 2 * N_EPI);
                         cA = ld(v * KEY_ROW); cB = ld((v + 1) * KEY_ROW);
-                        a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z);
-                        b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z);
-                        if (p.abl & 16) { a3 = a0; a4 = a1; a5 = a2; b3 = b0; b4 = b1; b5 = b2; }      // (timing ablation: 10 instead of 16 row loads per pair)
-                        else { a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y); }
+                        a0 = ld(oA0.x); a1 = ld(oA0.y); a2 = ld(oA0.z); a3 = ld(oA0.w); a4 = ld(oA1.x); a5 = ld(oA1.y);
+                        b0 = ld(oB0.x); b1 = ld(oB0.y); b2 = ld(oB0.z); b3 = ld(oB0.w); b4 = ld(oB1.x); b5 = ld(oB1.y);
                         op = c_nbr_off + vn * NBR_W;
                         oA0 = *reinterpret_cast<const uint4*>(op); oB0 = *reinterpret_cast<const uint4*>(op + 8);
                         oA1 = *reinterpret_cast<const uint2*>(op + 4); oB1 = *reinterpret_cast<const uint2*>(op + 12);
@@ -1033,7 +1031,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     }
                     // List the hits (typically a dozen lanes per warp and tile have one or two).  The slots come from ONE shared-memory
                     // atomic per warp (warp prefix sum of the per-lane counts): per-lane atomics on the single counter serialise.
-                    const uint32_t nhit = (p.abl & 48) ? 0u : __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);   // (ablations 16 / 32: nothing is listed)
+                    const uint32_t nhit = (p.abl & 32) ? 0u : __popc(fw0) + __popc(fw1) + __popc(fw2) + __popc(fw3);   // (ablation 32: nothing is listed)
                     if (__any_sync(0xffffffffu, nhit != 0u)) {
                         uint32_t incl = nhit;
     #pragma unroll

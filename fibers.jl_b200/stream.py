@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference's `stream` (src/stream.jl:730-790): same keyword arguments, same defaults,
+same output order; one blocking call into libfibers_cuda.so (fibers_stream) plus the fetch of the result.
+
+Covers the regime with a deterministic answer -- orientation vectors, no local connection matrices, macroscopic
+voxels.  `lcms` (random sampling from the connection matrix, src/stream.jl:394-492) and the microscopy regime
+(voxel size <= 50 um, :524-617) are not on the GPU path and raise.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .mri import MRI
+
+
+@dataclass
+class Tract:                       # the streamline fields of the reference's Tract (src/trk.jl:37-41) that stream() fills
+    xyz: list                      # [3, npts] float32 per streamline, 1-based voxel coordinates
+    npts: np.ndarray               # int32 [nstr]
+    sublist: np.ndarray = field(default=None, repr=False)   # the sub-voxel offsets that were used (the reference keeps them in StreamWork)
+
+    @property
+    def n_count(self):
+        return len(self.xyz)
+
+
+def _vol(m):
+    return m.vol if isinstance(m, MRI) else np.asarray(m)
+
+
+def draw_sublist(nsub: int, rng=None) -> np.ndarray:
+    """Sub-voxel sampling offsets, src/stream.jl:177-183: `T.(rand(Uniform(-.5+eps(), .5-eps()), 3))` per sample, or one
+    zero offset when nsub == 0."""
+    if nsub <= 0:
+        return np.zeros((1, 3), np.float32)
+    g = np.random.default_rng(rng)
+    e = np.finfo(np.float64).eps
+    return g.uniform(-0.5 + e, 0.5 - e, size=(nsub, 3)).astype(np.float32)
+
+
+def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=3, len_min=3,
+           len_max=None, ang_thresh=45, step_size=0.5, smooth_coeff=0.2, search_dist=15, search_ang=10, lcms=None,
+           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0) -> Tract:
+    """stream(ovec; odf, f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size,
+    smooth_coeff, search_dist, search_ang, lcms, lcm_thresh, verbose) -- reference: src/stream.jl:730.
+
+    `ovec`: MRI or list of MRI, each [nx,ny,nz,3]; `f`: MRI or list of MRI [nx,ny,nz].  Extra keywords: `sublist`
+    ([nsub,3] float32; drawn like the reference draws them when omitted, with `rng` as the seed) and `device`."""
+    ovecs = list(ovec) if isinstance(ovec, (list, tuple)) else [ovec]
+    fs = None if f is None else (list(f) if isinstance(f, (list, tuple)) else [f])
+    if lcms is not None:
+        raise _lib.FibersCudaError(1, "stream: local connection matrices (lcms) are not on the GPU path")
+    res = ovecs[0].header.get("volres") if isinstance(ovecs[0], MRI) else None
+    if res is not None and min(res) <= 0.05:
+        raise _lib.FibersCudaError(1, "stream: the microscopy regime (voxel size <= 50 um) is not on the GPU path")
+    vols = []
+    for o in ovecs:
+        v = np.asfortranarray(_vol(o), dtype=np.float32)
+        if v.ndim != 4 or v.shape[3] != 3:
+            raise _lib.FibersCudaError(1, "stream: orientation volumes must be [nx,ny,nz,3] vectors on the GPU path")
+        vols.append(v)
+    nx, ny, nz = vols[0].shape[:3]
+    if any(v.shape[:3] != (nx, ny, nz) for v in vols):
+        raise ValueError("stream: orientation volumes differ in size")
+    nvec = len(vols)
+    if fs is not None and len(fs) != nvec:
+        raise ValueError("stream: one amplitude volume per orientation volume is required")
+    fvols = None if fs is None else [np.asfortranarray(_vol(x), dtype=np.float32).reshape((nx, ny, nz), order="F") for x in fs]
+    fav = None if fa is None else np.asfortranarray(np.asarray(_vol(fa), dtype=np.float32).reshape((nx, ny, nz, -1), order="F")[..., 0])
+    mk = None
+    if mask is not None:
+        mv = _vol(mask)
+        mk = np.asfortranarray((mv.reshape((nx, ny, nz, -1), order="F")[..., 0] > 0).astype(np.uint8))
+    sd = None
+    if seed is not None:
+        sv = _vol(seed)
+        if mask is not None and tuple(sv.shape) != tuple(_vol(mask).shape):
+            raise ValueError(f"Dimension mismatch between seed mask {tuple(sv.shape)} and brain mask {tuple(_vol(mask).shape)}")
+        sd = np.asfortranarray((sv.reshape((nx, ny, nz, -1), order="F")[..., 0] > 0).astype(np.uint8))
+    if nsub is None:
+        nsub = 3
+    if sublist is None:
+        sublist = draw_sublist(int(nsub), rng)
+    sub = np.ascontiguousarray(sublist, dtype=np.float32).reshape(-1, 3)
+    if len_max is None:
+        len_max = max(nx, ny, nz)                                   # maximum(ovec.volsize)
+    ang = 45 if ang_thresh is None else ang_thresh
+    step = 0.5 if step_size is None else step_size
+    smooth = 0.2 if smooth_coeff is None else smooth_coeff
+    cos_thresh = np.float32(np.cos(np.deg2rad(np.float64(np.float32(ang)))))    # cosd(T(ang_thresh))
+
+    L = _lib.lib(); _lib.require_device()
+    PP = C.c_void_p * nvec
+    ov_ptrs = PP(*[v.ctypes.data for v in vols])
+    f_ptrs = None if fvols is None else PP(*[v.ctypes.data for v in fvols])
+    handle = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
+    _lib.check(L.fibers_stream(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
+                               _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(cos_thresh),
+                               float(step), float(smooth), int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
+    try:
+        npts = np.zeros(nstr.value, np.int32)
+        xyz = np.zeros((3, ntot.value), np.float32, order="F")
+        if handle.value:
+            _lib.check(L.fibers_stream_fetch(handle, _lib.ptr(npts), _lib.ptr(xyz)))
+    finally:
+        L.fibers_stream_free(handle)
+    ends = np.cumsum(npts, dtype=np.int64)
+    lines = [xyz[:, e - n:e] for e, n in zip(ends, npts)]
+    return Tract(lines, npts, sub)

@@ -1,0 +1,155 @@
+"""Streamline tractography: known-answer tests of the oracle (the reference's quirks spelled out by hand)
+and bit-exact parity of the CUDA path (fibers_stream through the C ABI) against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import stream_oracle as SO  # noqa: E402
+
+F = np.float32
+
+
+def straight_field(shape=(20, 5, 5)):
+    v = np.zeros(shape + (3,), F, order="F")
+    v[..., 0] = 1
+    return v
+
+
+def test_oracle_straight_line_quirks():
+    """All vectors along +x in a 20 x 5 x 5 volume, seed voxel (10, 3, 3), no sub-voxel offset, step 0.5, len_max = 20.
+    Forward: the positions 10, 10.5, ... are stored while the NEXT position is inside; round(10.5) = 10 and round(20.5) = 20
+    (half to even), so 10 ... 20.0 = 21 points are stored and the counter (21 > len_max) stops the pass.  Backward: the seed is
+    stored again (counter 22 > len_max) and the pass stops.  Forward points are prepended: 20.0, 19.5, ..., 10.0, then 10.0."""
+    v = straight_field()
+    m, arr = SO.stream_work([v])
+    assert m.all()
+    s = SO.new_line([10, 3, 3], np.zeros(3, F), m, arr, len_max=20, cosang_thresh=F(np.cos(np.pi / 4)), step=0.5, smooth=0.2)
+    assert s.shape == (3, 22)
+    np.testing.assert_array_equal(s[0], np.concatenate([np.arange(20.0, 9.75, -0.5), [10.0]]).astype(F))
+    np.testing.assert_array_equal(s[1], np.full(22, 3, F))
+
+
+def test_oracle_backward_pass_and_bounds():
+    """Same field, len_max large: forward runs to the +x face, backward to the -x face; the seed appears twice."""
+    v = straight_field()
+    m, arr = SO.stream_work([v])
+    s = SO.new_line([10, 3, 3], np.zeros(3, F), m, arr, len_max=1000, cosang_thresh=F(0.7071), step=0.5, smooth=0.0)
+    x = s[0]
+    # forward: 10 ... 20.0 stored (next of 20.5 is 21.0 -> outside); backward: 10, 9.5, ..., 1.0 stored? next of 1.0 is 0.5 -> round = 0 -> outside,
+    # so 1.0 is NOT stored; last stored is 1.5 (its next position 1.0 is inside)
+    np.testing.assert_array_equal(x, np.concatenate([np.arange(20.0, 9.75, -0.5), np.arange(10.0, 1.25, -0.5)]).astype(F))
+
+
+def test_oracle_pick_by_angle_sign_and_threshold():
+    """Two vector fields: e1 = -x (the propagation flips its sign), e2 = +y.  A line started along e1 keeps to x (|cos| = 1 beats 0).
+    A 60-degree kink between two half-volumes stops the line at the 45-degree threshold after the first point past the kink."""
+    shape = (12, 12, 3)
+    a = np.zeros(shape + (3,), F, order="F"); a[..., 0] = -1
+    b = np.zeros(shape + (3,), F, order="F"); b[..., 1] = 1
+    m, arr = SO.stream_work([a, b])
+    s = SO.new_line([6, 6, 2], np.zeros(3, F), m, arr, len_max=100, cosang_thresh=F(0.70710677), step=0.5, smooth=0.0)
+    assert np.all(s[1] == 6) and np.all(s[2] == 2) and s.shape[1] > 10
+    k = np.zeros(shape + (3,), F, order="F"); k[:6, :, :, 0] = 1
+    k[6:, :, :, 0] = F(np.cos(np.deg2rad(60.0))); k[6:, :, :, 1] = F(np.sin(np.deg2rad(60.0)))
+    m, arr = SO.stream_work([k])
+    s = SO.new_line([3, 6, 2], np.zeros(3, F), m, arr, len_max=100, cosang_thresh=F(0.70710677), step=0.5, smooth=0.0)
+    fwd = s[:, : np.argmax(s[0] == 3.0) + 1][:, ::-1]            # forward part in visiting order
+    # 6.0 -> 6.5 stays in voxel 6 (round(6.5) = 6); 6.5 -> 7.0 enters the kinked half: 6.5 is stored, cos 60 < cos 45 ends the pass
+    assert fwd[0, -1] == 6.5 and fwd[0, -2] == 6.0
+    assert s.shape[1] < 30
+
+
+def test_oracle_masks():
+    v = straight_field((8, 4, 4))
+    v[4:, :, :, :] = 0                                          # mask derived from "any component non-zero"
+    m, arr = SO.stream_work([v])
+    assert m[:4].all() and not m[4:].any()
+    fvol = np.ones((8, 4, 4), F, order="F"); fvol[2] = 0.01     # amplitude below f_thresh drops the vector, not the voxel
+    m2, arr2 = SO.stream_work([v], f=[fvol], f_thresh=0.03)
+    assert m2[2].all() and not arr2[:, 0, 2].any()
+    fa = np.full((8, 4, 4), 0.5, F, order="F"); fa[1] = 0.05
+    m3, _ = SO.stream_work([v], fa=fa, fa_thresh=0.1)
+    assert not m3[1].any() and m3[0].all()
+    out = SO.stream([v], [np.zeros(3, F)], len_min=3)
+    assert all(s.shape[1] >= 3 for s in out)
+
+
+def noisy_field(shape, nvec, seed):
+    """Smooth random orientation fields with holes (zero vectors) and per-vector amplitudes."""
+    g = np.random.default_rng(seed)
+    nx, ny, nz = shape
+    xs, ys, zs = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    vols, fs = [], []
+    for i in range(nvec):
+        ph = g.uniform(0, 2 * np.pi, 6)
+        th = 0.6 * np.sin(xs / 5.0 + ph[0]) + 0.5 * np.cos(ys / 4.0 + ph[1]) + 0.3 * np.sin(zs / 3.0 + ph[2]) + i * 1.1
+        el = 0.5 * np.sin(xs / 6.0 + ph[3]) * np.cos(ys / 7.0 + ph[4]) + 0.2 * np.sin(zs / 2.5 + ph[5])
+        v = np.stack([np.cos(th) * np.cos(el), np.sin(th) * np.cos(el), np.sin(el)], axis=-1)
+        v += 0.05 * g.standard_normal(v.shape)
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        hole = g.random(shape) < (0.03 + 0.1 * i)
+        v[hole] = 0
+        vols.append(np.asfortranarray(v.astype(F)))
+        fs.append(np.asfortranarray(g.uniform(0.0, 0.3, shape).astype(F)))
+    return vols, fs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["plain", "f_fa_mask_seed", "nosmooth_single"])
+def test_stream_gpu_parity_bit_exact(case):
+    import fibers_jl_b200 as Fb
+    shape = (26, 22, 12)
+    nvec = 1 if case == "nosmooth_single" else 3
+    vols, fs = noisy_field(shape, nvec, seed=7)
+    g = np.random.default_rng(11)
+    sub = Fb.draw_sublist(3, rng=5)
+    kw = dict(len_min=3, step_size=0.5, smooth_coeff=0.2, ang_thresh=45)
+    okw = dict(len_min=3, step_size=0.5, smooth_coeff=0.2, cosang_thresh=F(np.cos(np.deg2rad(45.0))))
+    if case == "f_fa_mask_seed":
+        fa = np.asfortranarray(g.uniform(0, 0.6, shape).astype(F))
+        mask = np.asfortranarray((g.random(shape) < 0.9).astype(np.uint8))
+        seed = np.asfortranarray((g.random(shape) < 0.3).astype(np.uint8))
+        kw.update(f=[Fb.MRI(x) for x in fs], f_thresh=0.05, fa=Fb.MRI(fa), fa_thresh=0.1, mask=Fb.MRI(mask), seed=Fb.MRI(seed))
+        okw.update(f=fs, f_thresh=0.05, fa=fa, fa_thresh=0.1, mask=mask, seed=seed)
+    if case == "nosmooth_single":
+        kw.update(smooth_coeff=0.0, step_size=0.75, ang_thresh=30, len_max=9)
+        okw.update(smooth_coeff=0.0, step_size=0.75, cosang_thresh=F(np.cos(np.deg2rad(np.float64(F(30))))), len_max=9)
+    got = Fb.stream([Fb.MRI(v) for v in vols], sublist=sub, **kw)
+    ref = SO.stream(vols, list(sub), **okw)
+    assert got.n_count == len(ref) and got.n_count > 200
+    assert np.array_equal(got.npts, np.array([s.shape[1] for s in ref], np.int32))
+    nbad = sum(0 if np.array_equal(a, b) else 1 for a, b in zip(got.xyz, ref))
+    print(f"[parity] stream {case}: {got.n_count} streamlines, {int(got.npts.sum())} points, mismatching lines {nbad}")
+    assert nbad == 0
+
+
+@pytest.mark.gpu
+def test_stream_gpu_consumes_gqi_peaks():
+    """gqi_rec peaks + qa feed stream() (the reference's downstream consumer, src/stream.jl:76-173 reads peaks / f / fa)."""
+    import fibers_jl_b200 as Fb
+    from fibers_jl_b200 import phantom
+    ph = phantom.gqi_phantom((16, 14, 8), seed=3, mask_fill=0.8)
+    r = Fb.gqi_rec(Fb.MRI(ph["dwi"], ph["bval"], ph["bvec"]), Fb.MRI(ph["mask"]))
+    sub = Fb.draw_sublist(2, rng=1)
+    got = Fb.stream(r.peak, f=r.qa, f_thresh=0.02, mask=Fb.MRI(ph["mask"]), sublist=sub)
+    ref = SO.stream([p.vol for p in r.peak], list(sub), f=[q.vol for q in r.qa], f_thresh=0.02, mask=ph["mask"])
+    assert got.n_count == len(ref) and got.n_count > 0
+    assert all(np.array_equal(a, b) for a, b in zip(got.xyz, ref))
+
+
+def test_stream_rejects_what_is_not_on_the_gpu_path():
+    import fibers_jl_b200 as Fb
+    v = straight_field((4, 4, 4))
+    with pytest.raises(Fb.FibersCudaError):
+        Fb.stream(Fb.MRI(v), lcms=Fb.MRI(np.zeros((4, 4, 4, 10), F)))
+    with pytest.raises(Fb.FibersCudaError):
+        Fb.stream(Fb.MRI(v, volres=(0.01, 0.01, 0.05)))
+    with pytest.raises(Fb.FibersCudaError):
+        Fb.stream(Fb.MRI(np.zeros((4, 4, 4), F)))
