@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfibers_cuda.so")
 
 F32, F64, I16, U16, I32, U8 = 0, 1, 2, 3, 4, 5
+I8, U32, I64 = 6, 7, 8              # volume I/O only
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
 _DTYPES = {np.dtype(np.float32): F32, np.dtype(np.float64): F64, np.dtype(np.int16): I16,
            np.dtype(np.uint16): U16, np.dtype(np.int32): I32, np.dtype(np.uint8): U8}
@@ -59,6 +60,9 @@ SIGNATURES = {
     "fibers_stream_device": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p]),
     "fibers_stream_fetch": (_i, [_p, _p, _p]),
     "fibers_stream_free": (None, [_p]),
+    "fibers_mri_read_info": (_i, [C.c_char_p, _p]),
+    "fibers_mri_read_data": (_i, [C.c_char_p, _p, _p, _i64]),
+    "fibers_mri_write": (_i, [C.c_char_p, _p, _i, _p, _p, _p, _f, _f, _f, _f, _f, _f, _i]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),

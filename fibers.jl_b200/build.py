@@ -23,9 +23,10 @@ EXTRA = {
     "structens.cu": ["-fmad=false"],
     "stream.cu": ["-fmad=false"],        # propagation follows the reference's unfused fp32 order
     "setup.cpp": ["-Xcompiler", "-ffp-contract=off"],
+    "mri_io.cpp": ["-Xcompiler", "-ffp-contract=off"],
     "recon_simt.cu": ["-diag-suppress", "128"],   # "loop is not reachable" in the plain-rows instantiation (early return)
 }
-SOURCES = ["api.cu", "host_pipeline.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu", "rumba.cu", "structens.cu", "stream.cu"]
+SOURCES = ["api.cu", "host_pipeline.cu", "setup.cpp", "dti.cu", "recon_simt.cu", "recon_tc.cu", "rumba.cu", "structens.cu", "stream.cu", "mri_io.cpp"]
 
 
 def _nvcc() -> str:
@@ -86,7 +87,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     link_digest = _digest(objs, "link")
     relinked = False
     if force or procs or _stale(LIB, LIB + ".sha256", link_digest):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda", "-ldl", "-Xcompiler", "-pthread"]
+        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda", "-ldl", "-lz", "-Xcompiler", "-pthread"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)

@@ -22,7 +22,7 @@
 // (LinearAlgebra.generic_norm2), IEEE division, round-half-even for round(Int, x).
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -181,7 +181,7 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
     const uint8_t* flags = d_seed ? d_seed : mask_arr;
     {
         size_t tb = 0;
-        cub::CountingInputIterator<int32_t> cnt(0);
+        thrust::counting_iterator<int32_t> cnt(0);
         T_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cnt, flags, seeds, d_nseed, (int)nvox));
         uint8_t* tmp; T_CUDA(D.alloc(&tmp, tb));
         T_CUDA(cub::DeviceSelect::Flagged(tmp, tb, cnt, flags, seeds, d_nseed, (int)nvox));

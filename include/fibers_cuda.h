@@ -65,6 +65,10 @@ extern "C" {
 #define FIBERS_U16 3
 #define FIBERS_I32 4
 #define FIBERS_U8  5
+/* further element types of the volume I/O entry points only (NIfTI Int8 / UInt32, MGH long) */
+#define FIBERS_I8  6
+#define FIBERS_U32 7
+#define FIBERS_I64 8
 
 /* Reconstruction kernel selection for GQI/DSI (all are CUDA paths). */
 #define FIBERS_KERNEL_AUTO  0   /* tensor-core path when the shape allows it, else SIMT */
@@ -202,6 +206,42 @@ int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, i
                          float step_size, float smooth_coeff, void** result, int64_t* nstr, int64_t* npts_total);
 int fibers_stream_fetch(void* result, int32_t* npts, float* xyz);
 void fibers_stream_free(void* result);
+
+/* ---- volume I/O either side of the path: NIfTI-1 (.nii, .nii.gz) and MGH (.mgh, .mgz) ----------
+ * fibers_mri_read_info   = load_nifti_hdr (src/mri.jl:1394-1551) / the header of load_mgh (:1217-1283) + what mri_read derives
+ *                          (:611-700): dims beyond the 4th folded into frames, units converted to mm / ms, vox2ras0 = sform if
+ *                          sform_code != 0, else qform if qform_code != 0, else diag(pixdim); volres from vox2ras0.
+ * fibers_mri_read_data   = the payload of load_nifti (:1640-1672) / load_mgh (:1305-1310): stored element type, byte order
+ *                          fixed, scl_slope / scl_inter applied by the reference's rule.  `dst` is column-major
+ *                          [dim0, dim1, dim2, dim3] of info->dtype; it may be pinned memory (fibers_cuda_host_register), so the
+ *                          reconstruction calls DMA straight from it.
+ * fibers_mri_write       = mri_write + save_nifti / save_mgh (:1695-1937, :2059-2176, :1939-2036): the format follows the
+ *                          extension; `out_dtype` (NIfTI only, < 0 = keep) is mri_write's `datatype` argument; `volres` may be NULL
+ *                          (derived from vox2ras0 as mri_write does :1719-1721).
+ * Compressed files are inflated / deflated in-process (zlib) straight into / from the caller's buffer; the reference pipes them
+ * through zcat / gzip and a temporary file (:1581-1592, :2160-2163).  Matrices are ROW-major 4 x 4 here. */
+#define FIBERS_FMT_NIFTI 1
+#define FIBERS_FMT_MGH   2
+typedef struct fibers_mri_info {
+    int32_t format;          /* FIBERS_FMT_* */
+    int32_t gz;              /* .nii.gz / .mgz */
+    int32_t ndim;            /* 3 or 4 */
+    int32_t dim[4];          /* volsize[3], nframes */
+    int32_t dtype;           /* FIBERS_* element type as stored */
+    int32_t bswap;           /* stored byte order differs from the host's (the reader fixes it) */
+    int32_t sform_code, qform_code;
+    int64_t data_offset;     /* round(vox_offset) (NIfTI) or 284 (MGH) */
+    float vox2ras0[16], sform[16], qform[16];
+    float pixdim[8];         /* NIfTI, in mm / ms */
+    float volres[3];
+    float tr, flip_angle, te, ti;
+    float scl_slope, scl_inter;
+} fibers_mri_info;
+int fibers_mri_read_info(const char* path, fibers_mri_info* info);
+int fibers_mri_read_data(const char* path, const fibers_mri_info* info, void* dst, int64_t dst_bytes);
+int fibers_mri_write(const char* path, const void* vol, int dtype, const int32_t* dim /*[4]*/, const float* vox2ras0 /*[16]*/,
+                     const float* volres /*[3] or NULL*/, float tr, float flip_angle, float te, float ti,
+                     float scl_slope, float scl_inter, int out_dtype);
 
 /* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
  * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
