@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 
@@ -285,13 +286,18 @@ int qform_of(const float* Mf, double q[7]) {
     return 0;
 }
 
-template <class S, class D> void convert_block(const S* s, D* d, size_t n) { for (size_t i = 0; i < n; ++i) d[i] = (D)s[i]; }
+// dtype.(vol) (src/mri.jl:2138): conversion to an integer type must be exact (Julia raises InexactError), to a float type it rounds
+template <class S, class D> bool convert_block(const S* s, D* d, size_t n) {
+    bool ok = true;
+    for (size_t i = 0; i < n; ++i) { d[i] = (D)s[i]; if (!std::is_floating_point<D>::value && (S)d[i] != s[i]) ok = false; }
+    return ok;
+}
 template <class S> bool convert_to(const S* s, void* d, int out, size_t n) {
     switch (out) {
-        case FIBERS_F32: convert_block(s, (float*)d, n); return true;   case FIBERS_F64: convert_block(s, (double*)d, n); return true;
-        case FIBERS_I16: convert_block(s, (int16_t*)d, n); return true; case FIBERS_U16: convert_block(s, (uint16_t*)d, n); return true;
-        case FIBERS_I32: convert_block(s, (int32_t*)d, n); return true; case FIBERS_U32: convert_block(s, (uint32_t*)d, n); return true;
-        case FIBERS_U8: convert_block(s, (uint8_t*)d, n); return true;  case FIBERS_I8: convert_block(s, (int8_t*)d, n); return true;
+        case FIBERS_F32: return convert_block(s, (float*)d, n);   case FIBERS_F64: return convert_block(s, (double*)d, n);
+        case FIBERS_I16: return convert_block(s, (int16_t*)d, n); case FIBERS_U16: return convert_block(s, (uint16_t*)d, n);
+        case FIBERS_I32: return convert_block(s, (int32_t*)d, n); case FIBERS_U32: return convert_block(s, (uint32_t*)d, n);
+        case FIBERS_U8: return convert_block(s, (uint8_t*)d, n);  case FIBERS_I8: return convert_block(s, (int8_t*)d, n);
         default: return false;
     }
 }
@@ -396,7 +402,7 @@ extern "C" int fibers_mri_write(const char* path, const void* vol, int dtype, co
         tmp.resize(std::min(n, CH) * os);
         for (size_t o = 0; o < n; o += CH) {
             const size_t c = std::min(CH, n - o);
-            if (!convert_any((const uint8_t*)vol + o * es, dtype, tmp.data(), out_dtype, c)) return fail(FIBERS_ERR_ARG, "element type not supported");
+            if (!convert_any((const uint8_t*)vol + o * es, dtype, tmp.data(), out_dtype, c)) return fail(FIBERS_ERR_ARG, "InexactError: the volume cannot be stored exactly in the requested integer type (or the type is not supported)");
             if (!out.write(tmp.data(), c * os)) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
         }
     }

@@ -1,0 +1,188 @@
+"""Volume I/O: the C-ABI readers / writers against an independent byte-level statement of the two formats
+(struct + gzip from the standard library), following src/mri.jl load_nifti_hdr / load_nifti / load_mgh / save_nifti / save_mgh /
+mri_write.  Host-only code: no GPU needed."""
+import gzip
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import fibers_jl_b200 as Fb  # noqa: E402
+from fibers_jl_b200 import io as fio  # noqa: E402
+
+NIFTI_DT = {2: np.uint8, 4: np.int16, 8: np.int32, 16: np.float32, 64: np.float64, 256: np.int8, 512: np.uint16, 768: np.uint32}
+
+
+def py_nifti_bytes(vol, *, endian="<", code=16, sform=None, sform_code=1, qform_code=0, quatern=(0, 0, 0), qoffset=(0, 0, 0),
+                   pixdim=(1, 1, 1, 1, 0, 0, 0, 0), units=2 | 16, slope=0.0, inter=0.0, dim=None, glmin=0, trailing=b""):
+    """A NIfTI-1 file image built field by field (nifti1.h layout)."""
+    e = endian
+    shape = list(vol.shape)
+    if dim is None:
+        dim = [len(shape)] + shape + [1] * (7 - len(shape))
+    h = bytearray(352)
+    struct.pack_into(e + "i", h, 0, 348)
+    struct.pack_into(e + "8h", h, 40, *dim)
+    struct.pack_into(e + "h", h, 70, code)
+    struct.pack_into(e + "h", h, 72, np.dtype(NIFTI_DT[code]).itemsize * 8)
+    struct.pack_into(e + "8f", h, 76, *pixdim)
+    struct.pack_into(e + "f", h, 108, 352.0)
+    struct.pack_into(e + "f", h, 112, slope)
+    struct.pack_into(e + "f", h, 116, inter)
+    struct.pack_into("b", h, 123, units)
+    struct.pack_into(e + "i", h, 144, glmin)
+    struct.pack_into(e + "h", h, 252, qform_code)
+    struct.pack_into(e + "h", h, 254, sform_code)
+    struct.pack_into(e + "3f", h, 256, *quatern)
+    struct.pack_into(e + "3f", h, 268, *qoffset)
+    S = np.eye(4, dtype=np.float32) if sform is None else np.asarray(sform, np.float32)
+    struct.pack_into(e + "12f", h, 280, *S[:3].reshape(-1))
+    h[344:348] = b"n+1\0"
+    data = np.asfortranarray(vol).astype(np.dtype(NIFTI_DT[code]).newbyteorder(e)).tobytes(order="F")
+    return bytes(h) + data + trailing
+
+
+def test_nifti_write_layout_and_roundtrip(tmp_path):
+    g = np.random.default_rng(0)
+    vol = np.asfortranarray(g.standard_normal((7, 5, 4, 3)).astype(np.float32))
+    M = np.array([[-1.25, 0, 0, 90], [0, 0, 1.5, -126], [0, -2.0, 0, 72], [0, 0, 0, 1]], np.float32)   # det(Mdc) > 0 after the sign flips? checked below
+    mri = Fb.MRI(vol, vox2ras0=M, tr=8800.0, niftihdr=dict(scl_slope=0.0, scl_inter=0.0))
+    for name, opener in (("a.nii", open), ("a.nii.gz", gzip.open)):
+        path = str(tmp_path / name)
+        assert fio.mri_write(mri, path) is False
+        raw = opener(path, "rb").read()
+        assert len(raw) == 352 + vol.nbytes
+        assert struct.unpack_from("<i", raw, 0)[0] == 348
+        assert struct.unpack_from("<8h", raw, 40) == (4, 7, 5, 4, 3, 1, 1, 1)
+        assert struct.unpack_from("<hh", raw, 70) == (16, 32)
+        pix = struct.unpack_from("<8f", raw, 76)
+        np.testing.assert_allclose(pix[1:5], [1.25, 2.0, 1.5, 8800.0], rtol=1e-6)
+        assert abs(pix[0]) == 1.0
+        assert struct.unpack_from("<f", raw, 108)[0] == 352.0
+        assert raw[123] == (2 | 16)
+        cal_max, cal_min = struct.unpack_from("<ff", raw, 124)
+        assert cal_max == vol.max() and cal_min == vol.min()
+        assert raw[148:228] == b"FreeSurfer julia".ljust(80)
+        assert struct.unpack_from("<hh", raw, 252) == (1, 1)
+        np.testing.assert_array_equal(np.array(struct.unpack_from("<12f", raw, 280), np.float32).reshape(3, 4), M[:3])
+        assert raw[328:332] == b"huh?" and raw[344:348] == b"n+1\0" and raw[348:352] == b"\0\0\0\0"
+        assert raw[352:] == vol.tobytes(order="F")
+        # the quaternion must reproduce the rotation part: rebuild the qform the way load_nifti_hdr does
+        back = fio.mri_read(path)
+        np.testing.assert_array_equal(back.vol, vol)
+        np.testing.assert_allclose(back.header["niftihdr"]["qform"], M, atol=2e-5)
+        np.testing.assert_array_equal(back.header["vox2ras0"], M)                  # sform wins
+        np.testing.assert_allclose(back.header["volres"], [1.25, 2.0, 1.5], rtol=1e-6)
+        assert back.header["tr"] == 8800.0 and back.header["nframes"] == 3 and back.header["volsize"] == [7, 5, 4]
+
+
+def test_nifti_read_big_endian_units_scaling_qform(tmp_path):
+    vol = (np.arange(6 * 4 * 3, dtype=np.int16).reshape(6, 4, 3, order="F") - 20)
+    b, c, d = 0.0, 0.0, np.sin(np.pi / 8)                         # 45 degrees about z
+    raw = py_nifti_bytes(vol, endian=">", code=4, sform_code=0, qform_code=1, quatern=(b, c, d), qoffset=(0.01, -0.02, 0.03),
+                         pixdim=(-1, 0.002, 0.003, 0.004, 2.5, 0, 0, 0), units=1 | 8, slope=2.0, inter=10.0)
+    p = tmp_path / "be.nii"
+    p.write_bytes(raw)
+    m = fio.mri_read(str(p))
+    assert m.vol.dtype == np.int16 and m.vol.shape == (6, 4, 3, 1)   # dim = (6, 4, 3, 1, 1, 1, 1): folded into a singleton 4th axis
+    np.testing.assert_array_equal(m.vol[..., 0], vol * 2 + 10)       # vol .= Int16.(vol .* slope .+ inter)
+    assert m.header["niftihdr"]["do_bswap"] is True
+    a = np.sqrt(1 - d * d)
+    R = np.array([[a * a - d * d, -2 * a * d, 0], [2 * a * d, a * a - d * d, 0], [0, 0, -(a * a + d * d)]])   # qfac = -1 flips the third column
+    Q = np.eye(4); Q[:3, :3] = R @ np.diag([2.0, 3.0, 4.0]); Q[:3, 3] = [0.01, -0.02, 0.03]   # metres -> mm for pixdim only (:1470-1473)
+    np.testing.assert_allclose(m.header["vox2ras0"], Q, atol=1e-5)
+    assert m.header["tr"] == 2500.0                                 # seconds -> ms
+
+
+def test_nifti_dims_beyond_four_fold_into_frames_and_errors(tmp_path):
+    vol = np.arange(2 * 3 * 2 * 2 * 3, dtype=np.float32).reshape((2, 3, 2, 2, 3), order="F")
+    raw = py_nifti_bytes(vol, dim=[5, 2, 3, 2, 2, 3, 1, 1])
+    p = tmp_path / "five.nii.gz"
+    p.write_bytes(gzip.compress(raw))
+    m = fio.mri_read(str(p))
+    assert m.vol.shape == (2, 3, 2, 6) and m.header["nframes"] == 6
+    np.testing.assert_array_equal(m.vol, vol.reshape((2, 3, 2, 6), order="F"))
+    bad = bytearray(raw); struct.pack_into("<i", bad, 0, 100)
+    (tmp_path / "bad.nii").write_bytes(bytes(bad))
+    with pytest.raises(Fb.FibersCudaError, match="Invalid header size"):
+        fio.mri_read(str(tmp_path / "bad.nii"))
+    bad = bytearray(raw); struct.pack_into("<h", bad, 70, 128)     # RGB24: not supported by the reference either
+    (tmp_path / "rgb.nii").write_bytes(bytes(bad))
+    with pytest.raises(Fb.FibersCudaError, match="Data type 128 not supported"):
+        fio.mri_read(str(tmp_path / "rgb.nii"))
+    (tmp_path / "long.nii").write_bytes(raw + b"xx")
+    with pytest.raises(Fb.FibersCudaError, match="did not reach end of file"):
+        fio.mri_read(str(tmp_path / "long.nii"))
+    with pytest.raises(ValueError, match="Cannot determine format"):
+        fio.mri_read(str(tmp_path / "volume.img"))
+
+
+def py_mgh_bytes(vol, M, parms, type_code):
+    nd = list(vol.shape) + [1] * (4 - vol.ndim)
+    M = np.asarray(M, np.float64)
+    delta = np.sqrt((M[:3, :3] ** 2).sum(0))
+    Mdc = M[:3, :3] / delta
+    pc = (M @ np.array([nd[0] / 2, nd[1] / 2, nd[2] / 2, 1.0]))[:3]
+    h = struct.pack(">7i", 1, nd[0], nd[1], nd[2], nd[3], type_code, 1) + struct.pack(">h", 1)
+    h += struct.pack(">3f", *delta) + struct.pack(">9f", *Mdc.reshape(-1, order="F")) + struct.pack(">3f", *pc)
+    h += b"\0" * (256 - 2 - 60)
+    dt = {3: ">f4", 0: "u1", 4: ">i2", 10: ">u2", 1: ">i4"}[type_code]
+    return h + np.asfortranarray(vol).astype(dt).tobytes(order="F") + struct.pack(">4f", *parms)
+
+
+def test_mgh_read_and_write(tmp_path):
+    g = np.random.default_rng(1)
+    vol = np.asfortranarray(g.integers(-500, 500, (5, 6, 4, 2)).astype(np.int16))
+    M = np.array([[-1, 0, 0, 64.5], [0, 0, 2, -40], [0, -1.5, 0, 33.25], [0, 0, 0, 1]], np.float32)
+    raw = py_mgh_bytes(vol, M, (2300.0, 0.1396, 2.9, 900.0), 4)
+    (tmp_path / "a.mgh").write_bytes(raw)
+    (tmp_path / "a.mgz").write_bytes(gzip.compress(raw))
+    for name in ("a.mgh", "a.mgz"):
+        m = fio.mri_read(str(tmp_path / name))
+        np.testing.assert_array_equal(m.vol, vol)
+        np.testing.assert_allclose(m.header["vox2ras0"], M, atol=1e-5)
+        np.testing.assert_allclose([m.header[k] for k in ("tr", "flip_angle", "te", "ti")], [2300.0, 0.1396, 2.9, 900.0], rtol=1e-6)
+    # writer: byte-identical to the independent statement of save_mgh
+    mri = Fb.MRI(vol, vox2ras0=M, tr=2300.0, flip_angle=np.float32(0.1396), te=np.float32(2.9), ti=900.0)
+    fio.mri_write(mri, str(tmp_path / "w.mgh"))
+    assert (tmp_path / "w.mgh").read_bytes() == raw
+    fio.mri_write(mri, str(tmp_path / "w.mgz"))
+    assert gzip.open(tmp_path / "w.mgz", "rb").read() == raw
+    fvol = np.asfortranarray(g.standard_normal((4, 3, 2)).astype(np.float32))
+    fio.mri_write(Fb.MRI(fvol, vox2ras0=np.eye(4, dtype=np.float32)), str(tmp_path / "f.mgh"))
+    assert (tmp_path / "f.mgh").read_bytes() == py_mgh_bytes(fvol, np.eye(4), (0, 0, 0, 0), 3)
+    np.testing.assert_array_equal(fio.mri_read(str(tmp_path / "f.mgh")).vol, fvol)
+
+
+def test_mri_read_tables_and_datatype_conversion(tmp_path):
+    g = np.random.default_rng(2)
+    vol = np.asfortranarray(np.round(g.uniform(0, 1000, (4, 4, 3, 5))).astype(np.float32))
+    bval = np.array([0, 1000, 1000, 2000, 2000], np.float32)
+    bvec = np.array([[0, 0, 0], [2, 0, 0], [0, 3, 4], [1, 1, 1], [0, 0, -0.5]], np.float32)
+    mri = Fb.MRI(vol, bval, bvec, vox2ras0=np.diag([2, 2, 2, 1]).astype(np.float32))
+    fio.mri_write(mri, str(tmp_path / "dwi.nii.gz"), datatype=np.int16)             # mri_write(mri, outfile, Int16): Int16.(vol)
+    back = fio.mri_read(str(tmp_path / "dwi.nii.gz"))
+    assert back.vol.dtype == np.int16
+    np.testing.assert_array_equal(back.vol, vol.astype(np.int16))
+    np.testing.assert_array_equal(back.bval, bval)
+    with np.errstate(invalid="ignore"):
+        want = bvec / np.sqrt((bvec ** 2).sum(1, keepdims=True))
+    want[0] = 0          # normalised rows, b0 row NaN -> 0 (:701-703)
+    np.testing.assert_allclose(back.bvec, want, rtol=1e-6)
+    with pytest.raises(Fb.FibersCudaError, match="InexactError"):                  # Int16.(vol) raises for non-integers
+        fio.mri_write(Fb.MRI(vol + np.float32(0.5), vox2ras0=np.eye(4, dtype=np.float32)), str(tmp_path / "x.nii"), datatype=np.int16)
+    # tables given as rows / in the other order
+    (tmp_path / "r.bvals").write_text(" ".join(str(x) for x in bval) + "\n")
+    (tmp_path / "r.bvecs").write_text("\n".join(" ".join(str(x) for x in bvec[:, c]) for c in range(3)) + "\n")
+    b, gtab = fio.mri_read_bfiles(str(tmp_path / "r.bvecs"), str(tmp_path / "r.bvals"))
+    np.testing.assert_array_equal(b, bval); np.testing.assert_array_equal(gtab, bvec)
+    # file stem without extension; permutedata
+    m2 = fio.mri_read(str(tmp_path / "dwi"), permutedata=True)
+    assert m2.vol.shape == (4, 4, 3, 5) and m2.header["ispermuted"]
+    np.testing.assert_array_equal(m2.vol, np.swapaxes(back.vol, 0, 1))
