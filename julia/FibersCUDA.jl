@@ -17,7 +17,8 @@
 =#
 module FibersCUDA
 
-using ..Fibers: MRI, ODF, DTI, GQI, DSI, sphere_642
+using ..Fibers: MRI, ODF, DTI, GQI, DSI, sphere_642, Tract, str_add!
+using Distributions: Uniform
 
 export adc_fit, dti_fit, gqi_rec, dsi_rec, dti_gqi_fit, dti_gqi_fit_batch, device_count
 
@@ -258,6 +259,103 @@ function dti_gqi_fit_batch(dwis::Vector{MRI}, masks::Vector{MRI}, odf_dirs::ODF=
                 dti_tab, odf_dirs.vertices, size(odf_dirs.vertices, 1), faces, size(faces, 1), σ, gqi_tab, NGPU[]))
   end
   return res
+end
+
+"""
+    stream(ovec; f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size, smooth_coeff)
+
+GPU version of `Fibers.stream` (src/stream.jl:730-790) for orientation VECTORS without local connection matrices in
+the macroscopic regime.  The StreamWork constructor's masking, the seed loop and the propagation run in
+`fibers_stream`; this wrapper keeps the reference's defaults, draws the sub-voxel offsets exactly like StreamWork
+does (src/stream.jl:177-183) and assembles the `Tract`.
+"""
+function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=nothing, f_thresh::Real=.03,
+                fa::Union{MRI,Nothing}=nothing, fa_thresh::Real=.1, mask::Union{MRI,Nothing}=nothing,
+                seed::Union{MRI,Nothing}=nothing, nsub::Union{Integer,Nothing}=3, len_min::Integer=3,
+                len_max::Integer=(isa(ovec,MRI) ? maximum(ovec.volsize) : maximum(ovec[1].volsize)),
+                ang_thresh::Union{Real,Nothing}=45, step_size::Union{Real,Nothing}=.5,
+                smooth_coeff::Union{Real,Nothing}=.2, lcms::Union{MRI,Nothing}=nothing)
+  isnothing(lcms) || error("stream: local connection matrices are not on the GPU path")
+  ovecs = isa(ovec, MRI) ? MRI[ovec] : ovec
+  fs    = isa(f, MRI) ? MRI[f] : f
+  minimum(ovecs[1].volres) <= 0.05 && error("stream: the microscopy regime is not on the GPU path")
+  all(o -> size(o.vol, 4) == 3, ovecs) || error("stream: orientation volumes must be [nx,ny,nz,3] vectors on the GPU path")
+  nx, ny, nz = size(ovecs[1].vol)[1:3]
+  isnothing(nsub) && (nsub = 3); isnothing(ang_thresh) && (ang_thresh = 45)
+  isnothing(step_size) && (step_size = .5); isnothing(smooth_coeff) && (smooth_coeff = .2)
+  if !isnothing(seed) && !isnothing(mask) && size(seed.vol) != size(mask.vol)
+    error("Dimension mismatch between seed mask " * string(size(seed.vol)) * " and brain mask " * string(size(mask.vol)))
+  end
+  sublist = nsub > 0 ? [Float32.(rand(Uniform(-.5+eps(), .5-eps()), 3)) for isub in 1:nsub] : [zeros(Float32, 3)]
+  sub  = reduce(hcat, sublist)                                   # [3, nsub] column-major = [nsub][3] for the C side
+  vols = [Array{Float32,4}(o.vol) for o in ovecs]
+  fvol = isnothing(fs) ? nothing : [Array{Float32,3}(x.vol[:,:,:,1]) for x in fs]
+  favol = isnothing(fa) ? nothing : Array{Float32,3}(fa.vol[:,:,:,1])
+  m  = isnothing(mask) ? nothing : UInt8.(mask.vol[:,:,:,1] .> 0)
+  sd = isnothing(seed) ? nothing : UInt8.(seed.vol[:,:,:,1] .> 0)
+  handle = Ref{Ptr{Cvoid}}(C_NULL); nstr = Ref{Int64}(0); ntot = Ref{Int64}(0)
+  GC.@preserve vols fvol begin
+    check(ccall((:fibers_stream, libfibers), Cint,
+                (Ptr{Ptr{Float32}}, Cint, Cint, Cint, Cint, Ptr{Ptr{Float32}}, Cfloat, Ptr{Float32}, Cfloat, Ptr{UInt8}, Ptr{UInt8},
+                 Ptr{Float32}, Cint, Cint, Cint, Cfloat, Cfloat, Cfloat, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}),
+                pointer.(vols), length(vols), nx, ny, nz, isnothing(fvol) ? C_NULL : pointer.(fvol), Float32(f_thresh),
+                isnothing(favol) ? C_NULL : favol, Float32(fa_thresh), isnothing(m) ? C_NULL : m, isnothing(sd) ? C_NULL : sd,
+                sub, size(sub, 2), len_min, len_max, cosd(Float32(ang_thresh)), Float32(step_size), Float32(smooth_coeff),
+                0, handle, nstr, ntot))
+  end
+  npts = Vector{Int32}(undef, nstr[]); xyz = Matrix{Float32}(undef, 3, ntot[])
+  try
+    check(ccall((:fibers_stream_fetch, libfibers), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float32}), handle[], npts, xyz))
+  finally
+    ccall((:fibers_stream_free, libfibers), Cvoid, (Ptr{Cvoid},), handle[])
+  end
+  ends = cumsum(Int.(npts))
+  str = [xyz[:, (ends[i]-npts[i]+1):ends[i]] for i in eachindex(npts)]
+  tr = Tract{Float32}(isnothing(mask) ? ovecs[1] : mask)
+  str_add!(tr, str)                                               # src/stream.jl:785-787
+  return tr
+end
+
+# fibers_mri_info (include/fibers_cuda.h); matrices are row-major on the C side
+struct MriInfo
+  format::Int32; gz::Int32; ndim::Int32; dim::NTuple{4,Int32}; dtype::Int32; bswap::Int32; sform_code::Int32; qform_code::Int32
+  data_offset::Int64
+  vox2ras0::NTuple{16,Float32}; sform::NTuple{16,Float32}; qform::NTuple{16,Float32}; pixdim::NTuple{8,Float32}
+  volres::NTuple{3,Float32}; tr::Float32; flip_angle::Float32; te::Float32; ti::Float32; scl_slope::Float32; scl_inter::Float32
+end
+const IO_TYPES = (Float32, Float64, Int16, UInt16, Int32, UInt8, Int8, UInt32, Int64)      # FIBERS_F32 ... FIBERS_I64
+
+"""
+    load_volume(fname) -> (info::MriInfo, vol)
+
+Header + payload of a NIfTI-1 / MGH file through the library (replaces `load_nifti` / `load_mgh`, src/mri.jl:1576, :1217,
+inside `mri_read`): no temporary file for .nii.gz / .mgz, byte order and scl_slope / scl_inter handled as in the reference.
+"""
+function load_volume(fname::String)
+  info = Ref{MriInfo}()
+  check(ccall((:fibers_mri_read_info, libfibers), Cint, (Cstring, Ptr{MriInfo}), fname, info))
+  h = info[]
+  T = IO_TYPES[h.dtype + 1]
+  vol = Array{T}(undef, Int.(h.ndim >= 4 ? h.dim : h.dim[1:3])...)
+  check(ccall((:fibers_mri_read_data, libfibers), Cint, (Cstring, Ptr{MriInfo}, Ptr{Cvoid}, Int64), fname, info, vol, sizeof(vol)))
+  return h, vol
+end
+
+"""
+    save_volume(fname, vol, vox2ras0, volres, mr_parms, scl_slope, scl_inter, datatype)
+
+`save_nifti` / `save_mgh` (src/mri.jl:2059, :1939) with the header `mri_write` builds (:1733-1885), format by extension.
+"""
+function save_volume(fname::String, vol::Array{T}, vox2ras0::Matrix, volres::Vector, mr_parms::Vector=zeros(4),
+                     scl_slope::Real=0, scl_inter::Real=0, datatype::DataType=T) where T<:Number
+  dim = Int32[size(vol, 1), size(vol, 2), size(vol, 3), size(vol, 4)]
+  M = Matrix{Float32}(permutedims(vox2ras0))                      # row-major for the C side
+  code(t) = Cint(findfirst(==(t), IO_TYPES) - 1)
+  check(ccall((:fibers_mri_write, libfibers), Cint,
+              (Cstring, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cint),
+              fname, vol, code(T), dim, M, Float32.(volres), mr_parms[1], mr_parms[2], mr_parms[3], mr_parms[4],
+              scl_slope, scl_inter, code(datatype)))
+  return false
 end
 
 end # module
