@@ -13,7 +13,9 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfibers_cuda.so")
+# FIBERS_CUDA_LIB: load another build of the library (A/B timing of kernel variants inside one GPU session; the Julia wrapper
+# honours the same variable)
+LIB_PATH = os.environ.get("FIBERS_CUDA_LIB") or os.path.join(HERE, "libfibers_cuda.so")
 
 F32, F64, I16, U16, I32, U8 = 0, 1, 2, 3, 4, 5
 I8, U32, I64 = 6, 7, 8              # volume I/O only
