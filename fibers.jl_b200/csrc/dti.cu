@@ -85,6 +85,10 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
     if (vox >= nvox) return;
     const bool inside = mask[vox] != 0;
     float d[NC];
+    // accumulators as fp32 PAIRS (d0 d1)(d2 d3)(d4 d5)(d6 -): one FFMA2 (two IEEE fma per instruction, sm_100) per pair and sample
+    unsigned long long dp[(NC + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < (NC + 1) / 2; ++k) dp[k] = 0ull;
 #pragma unroll
     for (int k = 0; k < NC; ++k) d[k] = 0.f;
     int nrem = 0, b0rem = 0;                           // removed (non-positive) samples, and how many of them are minimum-b volumes
@@ -98,12 +102,20 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
         // sent to the exact-log path -- no per-sample range test.
         float l2;
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(s > 0.f ? s : 1.f));
-        const float4 c0 = *reinterpret_cast<const float4*>(spa + j * CW);
-        d[0] = fmaf(c0.x, l2, d[0]); d[1] = fmaf(c0.y, l2, d[1]);
+        if (NC == 2) {                                  // ADC: two scalar FFMA (the packed form measured 0.9 % slower here, 1.3 % faster for DTI)
+            const float2 c = *reinterpret_cast<const float2*>(spa + j * CW);
+            d[0] = fmaf(c.x, l2, d[0]); d[1 % NC] = fmaf(c.y, l2, d[1 % NC]);
+            return;
+        }
+        unsigned long long l22;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(l22) : "f"(l2));
+        const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(spa + j * CW);
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dp[0]) : "l"(c0.x), "l"(l22));
         if (NC > 2) {
-            const float4 c1 = *reinterpret_cast<const float4*>(spa + j * CW + 4);
-            d[2 % NC] = fmaf(c0.z, l2, d[2 % NC]); d[3 % NC] = fmaf(c0.w, l2, d[3 % NC]);
-            d[4 % NC] = fmaf(c1.x, l2, d[4 % NC]); d[5 % NC] = fmaf(c1.y, l2, d[5 % NC]); d[6 % NC] = fmaf(c1.z, l2, d[6 % NC]);
+            const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(spa + j * CW + 4);
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dp[1 % ((NC + 1) / 2)]) : "l"(c0.y), "l"(l22));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dp[2 % ((NC + 1) / 2)]) : "l"(c1.x), "l"(l22));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dp[3 % ((NC + 1) / 2)]) : "l"(c1.y), "l"(l22));     // (second half: the zero pad)
         }
     };
     auto dropped = [&](int j) { if (nrem < RMAX) rem[nrem] = j; ++nrem; b0rem += ib0[j] ? 1 : 0; };
@@ -132,6 +144,15 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
             const float sv = __ldg(rb + (int64_t)u * pitch + vox32);
             sample(sv, j);
             if (!(sv > 0.f)) dropped(j);
+        }
+    }
+    if (NC > 2) {
+#pragma unroll
+        for (int k = 0; k < (NC + 1) / 2; ++k) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(dp[k]));
+            d[2 * k] = lo;
+            if (2 * k + 1 < NC) d[2 * k + 1] = hi;
         }
     }
     const int npos = nvol - nrem;

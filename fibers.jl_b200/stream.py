@@ -43,7 +43,7 @@ def draw_sublist(nsub: int, rng=None) -> np.ndarray:
 
 def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=3, len_min=3,
            len_max=None, ang_thresh=45, step_size=0.5, smooth_coeff=0.2, search_dist=15, search_ang=10, lcms=None,
-           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0) -> Tract:
+           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None) -> Tract:
     """stream(ovec; odf, f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size,
     smooth_coeff, search_dist, search_ang, lcms, lcm_thresh, verbose) -- reference: src/stream.jl:730.
 
@@ -96,10 +96,13 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     PP = C.c_void_p * nvec
     ov_ptrs = PP(*[v.ctypes.data for v in vols])
     f_ptrs = None if fvols is None else PP(*[v.ctypes.data for v in fvols])
+    import time
     handle = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
+    t0 = time.perf_counter()
     _lib.check(L.fibers_stream(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
                                _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(cos_thresh),
                                float(step), float(smooth), int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
+    t1 = time.perf_counter()
     try:
         npts = np.zeros(nstr.value, np.int32)
         xyz = np.zeros((3, ntot.value), np.float32, order="F")
@@ -107,6 +110,8 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
             _lib.check(L.fibers_stream_fetch(handle, _lib.ptr(npts), _lib.ptr(xyz)))
     finally:
         L.fibers_stream_free(handle)
+    if timing is not None:                     # (bench aid) seconds in the tracking call and in the fetch of the points
+        timing["call_s"] = t1 - t0; timing["fetch_s"] = time.perf_counter() - t1
     ends = np.cumsum(npts, dtype=np.int64)
     lines = [xyz[:, e - n:e] for e, n in zip(ends, npts)]
     return Tract(lines, npts, sub)

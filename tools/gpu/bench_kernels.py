@@ -79,10 +79,13 @@ def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642, align
         report(f"dsi_rec {tag} [{plan.kernel}]", nvox, ms, 8 * N + 4 * M + 49, 2 * N * (M + N), "tensor-bound in matrix form (3 kernel passes: odf rows, 2 x pdf rows)")
 
 
+ONLY = os.environ.get("BENCH_KERNELS_ONLY", "")          # "dti": the DTI / ADC rows only (A/B of kernel variants)
 b1, g1 = phantom.shells_table(1, [(1000.0, 30)])
 run_dti((64, 64, 40), b1, g1, "cfg1 64x64x40x31")
 b2, g2 = bench.make_tables()
 run_dti((145, 174, 145), b2, g2, "cfg4 145x174x145x288")
+if ONLY == "dti":
+    sys.exit(0)
 run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288")
 run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288, DWI pitch = nvox (rows not 16-byte aligned)", aligned=False)
 run_recon("gqi", (145, 174, 145), b2, g2, "simt", "cfg2 145x174x145x288")
