@@ -15,7 +15,14 @@ namespace fibers {
 namespace {
 
 constexpr int DTI_THREADS = 256;
-constexpr int UNROLL = 16;
+// Samples per batch of the software-pipelined hot loop (two batches of registers are live: one in flight, one being consumed).
+// Same-box A/B (profiles/r2_dti_ab.txt): DTI 8 -> 65.2 % of the HBM roof (16 spills at 64 registers: 49 %), ADC 16 -> 80.0 % (8: 68.6 %).
+#ifndef DTI_U
+#define DTI_U 8
+#endif
+#ifndef ADC_U
+#define ADC_U 16
+#endif
 
 struct DtiOut {
     float* p[10];   // s0, l1, l2, l3, v1, v2, v3, rd, md, fa
@@ -93,7 +100,7 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
     for (int k = 0; k < NC; ++k) d[k] = 0.f;
     int nrem = 0, b0rem = 0;                           // removed (non-positive) samples, and how many of them are minimum-b volumes
     int rem[RMAX];
-    // Hot loop, 13.5 instructions per sample: a non-positive sample is replaced by 1 (log = 0: it contributes nothing,
+    // Hot loop: a non-positive sample is replaced by 1 (log = 0: it contributes nothing,
     // src/dti.jl:297-298 drops its row) with one compare + select; WHICH samples were dropped is only looked at when the
     // minimum of a group of UNROLL samples is not positive (rare), so the loop carries no counters.
     auto sample = [&](float s, int j) {
@@ -125,21 +132,37 @@ fit_full_kernel(const float* __restrict__ dwi, int64_t pitch, const uint8_t* __r
         const uint32_t vox32 = (uint32_t)vox;
         const float* rb = dwi;
         int j = 0;
-        for (; j + UNROLL <= nvol; j += UNROLL) {
-            float s[UNROLL];
+        // Software-pipelined by one batch: the loads of batch b + 1 are issued BEFORE the arithmetic of batch b, so a warp keeps
+        // UNROLL loads in flight while it computes (two register sets, the loop is unrolled by two batches: no moves).
+        constexpr int UNROLL = NC == 7 ? DTI_U : ADC_U;
+        auto load = [&](float (&s)[UNROLL]) {
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) s[u] = __ldg(rb + (int64_t)u * pitch + vox32);
             rb += (int64_t)UNROLL * pitch;
+        };
+        auto process = [&](const float (&s)[UNROLL], int j0) {
             float mn = s[0];
 #pragma unroll
             for (int u = 1; u < UNROLL; ++u) asm("min.NaN.f32 %0, %0, %1;" : "+f"(mn) : "f"(s[u]));   // (a NaN sample counts as dropped, like `s > 0` in the reference)
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) sample(s[u], j + u);
+            for (int u = 0; u < UNROLL; ++u) sample(s[u], j0 + u);
             if (!(mn > 0.f)) {                                              // rare: remember which samples were dropped
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) dropped(j + u);
+                for (int u = 0; u < UNROLL; ++u) if (!(s[u] > 0.f)) dropped(j0 + u);
             }
+        };
+        const int nbatch = nvol / UNROLL;
+        float sa[UNROLL], sb[UNROLL];
+        if (nbatch > 0) load(sa);
+        int b = 0;
+        for (; b + 2 <= nbatch; b += 2) {
+            load(sb);
+            process(sa, b * UNROLL);
+            if (b + 2 < nbatch) load(sa);
+            process(sb, (b + 1) * UNROLL);
         }
+        if (b < nbatch) { process(sa, b * UNROLL); ++b; }
+        j = nbatch * UNROLL;
         for (int u = 0; j < nvol; ++j, ++u) {
             const float sv = __ldg(rb + (int64_t)u * pitch + vox32);
             sample(sv, j);

@@ -153,3 +153,32 @@ def test_stream_rejects_what_is_not_on_the_gpu_path():
         Fb.stream(Fb.MRI(v, volres=(0.01, 0.01, 0.05)))
     with pytest.raises(Fb.FibersCudaError):
         Fb.stream(Fb.MRI(np.zeros((4, 4, 4), F)))
+
+
+@pytest.mark.gpu
+def test_stream_device_resident_entry_point():
+    """fibers_stream_device on DEVICE volumes (peaks / amplitudes a reconstruction left on the GPU) equals the host-pointer call."""
+    import ctypes as C
+    import torch
+    import fibers_jl_b200 as Fb
+    shape = (20, 18, 10)
+    vols, fs = noisy_field(shape, 2, seed=4)
+    sub = Fb.draw_sublist(2, rng=8)
+    ref = Fb.stream([Fb.MRI(v) for v in vols], f=[Fb.MRI(x) for x in fs], f_thresh=0.1, sublist=sub)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    d_v = [torch.from_numpy(np.ascontiguousarray(np.moveaxis(v, 3, 0).reshape(3, -1, order="F"))).to(dev) for v in vols]   # [3][nvox], x fastest
+    d_f = [torch.from_numpy(np.ascontiguousarray(x.reshape(-1, order="F"))).to(dev) for x in fs]
+    L = Fb._lib.lib()
+    PP = C.c_void_p * 2
+    h = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
+    Fb._lib.check(L.fibers_stream_device(PP(*[t.data_ptr() for t in d_v]), 2, *shape, PP(*[t.data_ptr() for t in d_f]), 0.1, None, 0.0, None, None,
+                                          Fb._lib.ptr(sub), 2, 3, max(shape), float(np.float32(np.cos(np.deg2rad(45.0)))), 0.5, 0.2,
+                                          C.byref(h), C.byref(nstr), C.byref(ntot)))
+    try:
+        npts = np.zeros(nstr.value, np.int32); xyz = np.zeros((3, ntot.value), np.float32, order="F")
+        Fb._lib.check(L.fibers_stream_fetch(h, Fb._lib.ptr(npts), Fb._lib.ptr(xyz)))
+    finally:
+        L.fibers_stream_free(h)
+    assert nstr.value == ref.n_count > 0 and np.array_equal(npts, ref.npts)
+    assert np.array_equal(xyz, np.concatenate(ref.xyz, axis=1))
