@@ -449,7 +449,9 @@ def main():
         side = dist.new_group(backend="gloo")          # host-side barrier for the legs in which only rank 0 works (no kernel spinning on the idle GPUs)
     D.set_devices([local_rank])
 
-    pitch = (nvox + 63) // 64 * 64          # frame pitch of the DWI slab and of the outputs: 256-byte aligned rows
+    # frame pitch of the DWI slab and of the outputs: rows 16-byte aligned (TMA) -- BENCH_PITCH_ALIGN / BENCH_PITCH_EXTRA (voxels) for experiments
+    _pa = int(os.environ.get("BENCH_PITCH_ALIGN", "64")); _pe = int(os.environ.get("BENCH_PITCH_EXTRA", "0"))
+    pitch = (nvox + _pa - 1) // _pa * _pa + _pe
     dwi = synth_dwi_device(torch, nvox, bval, bvec, 1000 + rank, dev, pitch=pitch)
     if args.mask == "ones":
         mask = torch.ones(nvox, dtype=torch.uint8, device=dev)

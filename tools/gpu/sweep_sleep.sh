@@ -1,3 +1,5 @@
-for cs in 100 400 1000 0; do for ps in 200 1000 0; do
-echo "conv_sleep=$cs prod_sleep=$ps: $(FIBERS_TC_CONV_SLEEP=$cs FIBERS_TC_PROD_SLEEP=$ps python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["roofline"]["kernel_ms"], d["ms_per_step"])')"
-done; done
+# back-off (ns) of the converters' A-slot wait and of the two producers' ring waits: the polling loops are 15 % of the executed
+# instructions of recon_tc_kernel (ncu source page), so the poll period trades issue slots against wake-up latency
+for cfg in "100 200" "300 200" "1000 200" "100 1000" "300 1000" "1000 1000" "2000 2000" "0 0"; do set -- $cfg
+bash tools/gpu/quick_bench.sh FIBERS_TC_CONV_SLEEP=$1 FIBERS_TC_PROD_SLEEP=$2
+done
