@@ -482,6 +482,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the other half of BASELINE.json's metric ("GQI recon+peaks, DTI fit"): dti_fit and adc_fit on the SAME device-resident
+    #      volume (cfg4 runs both on every subject), timed apart from the headline step: extra keys of the line, not part of `value`
+    dti_legs = {}
+
+    def run_dti_legs():
+        nonlocal dti_legs
+        try:
+            pd = D.Plan("dti", local_rank, bval, bvec); pa = D.Plan("adc", local_rank, bval)
+            douts = [torch.empty((n, pitch), dtype=torch.float32, device=dev) for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)]
+            dptr = [o.data_ptr() for o in douts]
+            peak_gbs0 = measured_peaks()[0]
+            for name, fn, bpv_d in (("dti_fit", lambda: pd.dti_fit(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, pitch, dptr, stream=stream), 4 * nvol + 65),
+                                    ("adc_fit", lambda: pa.adc_fit(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, dptr[0], dptr[1], stream=stream), 4 * nvol + 9)):
+                for _ in range(3): fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(steps): fn()
+                b.record(); torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / steps
+                gbs = nvox * bpv_d / (ms * 1e-3) / 1e9
+                dti_legs[name] = {"value": nvox / (ms * 1e-3), "unit": "voxels/s", "ms_per_step": ms, "algorithmic_bytes_per_voxel": bpv_d,
+                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs0, "unit": "GB/s", "frac": gbs / peak_gbs0},
+                                  "api": f"fibers_{name}_device on the same {nvol}-volume slab (src/dti.jl:{'221' if name == 'dti_fit' else '164'})"}
+            del douts, pd, pa
+        except Exception as ex:                     # noqa: BLE001
+            dti_legs = {"dti_fit": {"error": f"{type(ex).__name__}: {ex}"[:200]}}
+
+    dti_first = os.environ.get("BENCH_DTI_FIRST", "1") != "0"      # before the tensor-heavy GQI loop (the board's clock governor lags after it)
+    if rank == 0 and world == 1 and not args.no_dti and dti_first:
+        run_dti_legs()
+        torch.cuda.synchronize()
     for _ in range(max(warmup, 3)):
         step()
     barrier()
@@ -524,31 +556,8 @@ def main():
             os.environ.pop("FIBERS_TC_TRACE", None)
             if os.path.exists(tf): os.remove(tf)
 
-    # ---- the other half of BASELINE.json's metric ("GQI recon+peaks, DTI fit"): dti_fit and adc_fit on the SAME device-resident
-    #      volume (cfg4 runs both on every subject), timed apart from the headline step: extra keys of the line, not part of `value`
-    dti_legs = {}
-    if rank == 0 and world == 1 and not args.no_dti:
-        try:
-            pd = D.Plan("dti", local_rank, bval, bvec); pa = D.Plan("adc", local_rank, bval)
-            douts = [torch.empty((n, pitch), dtype=torch.float32, device=dev) for n in (1, 1, 1, 1, 3, 3, 3, 1, 1, 1)]
-            dptr = [o.data_ptr() for o in douts]
-            peak_gbs0 = measured_peaks()[0]
-            for name, fn, bpv_d in (("dti_fit", lambda: pd.dti_fit(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, pitch, dptr, stream=stream), 4 * nvol + 65),
-                                    ("adc_fit", lambda: pa.adc_fit(dwi.data_ptr(), pitch, mask.data_ptr(), nvox, dptr[0], dptr[1], stream=stream), 4 * nvol + 9)):
-                for _ in range(3): fn()
-                torch.cuda.synchronize()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                for _ in range(steps): fn()
-                b.record(); torch.cuda.synchronize()
-                ms = a.elapsed_time(b) / steps
-                gbs = nvox * bpv_d / (ms * 1e-3) / 1e9
-                dti_legs[name] = {"value": nvox / (ms * 1e-3), "unit": "voxels/s", "ms_per_step": ms, "algorithmic_bytes_per_voxel": bpv_d,
-                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs0, "unit": "GB/s", "frac": gbs / peak_gbs0},
-                                  "api": f"fibers_{name}_device on the same {nvol}-volume slab (src/dti.jl:{'221' if name == 'dti_fit' else '164'})"}
-            del douts, pd, pa
-        except Exception as ex:                     # noqa: BLE001
-            dti_legs = {"dti_fit": {"error": f"{type(ex).__name__}: {ex}"[:200]}}
+    if rank == 0 and world == 1 and not args.no_dti and not dti_first:
+        run_dti_legs()
 
     # ---- end to end through the host-pointer C ABI (what the Julia wrapper ccalls) ----------
     e2e = None

@@ -71,7 +71,7 @@ __device__ void dti_zero(int64_t vox, const DtiOut& o) {
 // where P_r = pinv(A)[:, removed] (= G^-1 U for a full-column-rank design).  x0 falls out of the main
 // loop for free; the r x r system (r <= RMAX) is solved per thread in fp32.  Voxels with more
 // removed samples, or a singular downdate, go to the general per-voxel pinv kernel via a device list.
-constexpr int RMAX = 6;
+constexpr int RMAX = 8;     // (one voxel with 7 dropped samples on the per-voxel pinv path costs 0.27 ms of latency: fp64 Jacobi in ONE thread; with 8 the cfg4 phantom never leaves the inline path)
 constexpr int CW = 8;     // coefficient row width in shared memory: [nvol][CW] = pinv(A)' padded (2 x LDS.128 per sample)
 
 template <int NC>
@@ -250,12 +250,17 @@ __global__ void fit_partial_kernel(const float* __restrict__ dwi, int64_t pitch,
   // the counter of the NEXT launch of this plan is reset here (the two alternate), which saves a memset per call
   if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;
   const int total = *count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  // One WARP per listed voxel: the lanes split the samples (a single thread walking 288 dependent, uncoalesced loads took 0.27 ms
+  // for ONE voxel: the latency of the whole call), the normal matrix is reduced with shuffles, every lane then runs the small
+  // eigen-solve redundantly and lane 0 stores.
+  const int lane = threadIdx.x & 31;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += nwarp) {
     const int64_t vox = list[i];
     double G[NC][NC], V[NC][NC], rhs[NC];
     for (int a = 0; a < NC; ++a) { rhs[a] = 0; for (int b = 0; b < NC; ++b) { G[a][b] = 0; V[a][b] = (a == b); } }
     int npos = 0;
-    for (int j = 0; j < nvol; ++j) {
+    for (int j = lane; j < nvol; j += 32) {
         float s = dwi[vox + (int64_t)j * pitch];
         if (!(s > 0.f)) continue;
         ++npos;
@@ -265,6 +270,14 @@ __global__ void fit_partial_kernel(const float* __restrict__ dwi, int64_t pitch,
         for (int a = 0; a < NC; ++a) {
             rhs[a] += row[a] * lg;
             for (int b = a; b < NC; ++b) G[a][b] += row[a] * row[b];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        npos += __shfl_xor_sync(0xffffffffu, npos, o);
+        for (int a = 0; a < NC; ++a) {
+            rhs[a] += __shfl_xor_sync(0xffffffffu, rhs[a], o);
+            for (int b = a; b < NC; ++b) G[a][b] += __shfl_xor_sync(0xffffffffu, G[a][b], o);
         }
     }
     for (int a = 0; a < NC; ++a) for (int b = 0; b < a; ++b) G[a][b] = G[b][a];
@@ -311,8 +324,10 @@ __global__ void fit_partial_kernel(const float* __restrict__ dwi, int64_t pitch,
         for (int a = 0; a < NC; ++a) acc[a] += V[a][k] * proj;
     }
     for (int a = 0; a < NC; ++a) d[a] = (float)acc[a];
-    if (NC == 7) dti_finish(d, vox, out);
-    else { adc[vox] = d[0]; adc_s0[vox] = expf(d[1]); }
+    if (lane == 0) {
+        if (NC == 7) dti_finish(d, vox, out);
+        else { adc[vox] = d[0]; adc_s0[vox] = expf(d[1]); }
+    }
   }
 }
 
@@ -344,7 +359,7 @@ int launch_fit(Plan* p, const float* d_dwi, int64_t dwi_pitch, const uint8_t* d_
                                                            p->d_ib0, out, adc, adc_s0, p->d_list, cnt);
     // The partial path is rare: a fixed 4-CTA-per-SM grid strides over the device-side list
     // (no host sync needed to learn the count).  64-thread blocks: heavy per-thread state.
-    unsigned pblocks = (unsigned)std::min<int64_t>((nvox + 63) / 64, 148 * 4);
+    unsigned pblocks = (unsigned)std::min<int64_t>((nvox + 1) / 2, 148 * 4);        // two warps (= two listed voxels at a time) per block
     fit_partial_kernel<NC><<<pblocks, 64, 0, st>>>(d_dwi, dwi_pitch, p->nvol, p->d_design, out, adc, adc_s0,
                                                    p->d_list, cnt, cnt_next);
     count_launch(2);
