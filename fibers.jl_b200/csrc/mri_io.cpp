@@ -409,3 +409,47 @@ extern "C" int fibers_mri_write(const char* path, const void* vol, int dtype, co
     if (!out.close()) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
     return 0;
 }
+
+// ---- TrackVis .trk (version 2) writer: trk_write (src/trk.jl:433-495) with the header Tract{T}(ref::MRI) builds (:88-145) ----
+extern "C" int fibers_trk_write(const char* path, const int32_t* volsize, const float* volres, const float* vox2ras,
+                                int64_t nstr, const int32_t* npts, const float* xyz) {
+    if (!path || !volsize || !volres || !vox2ras || (nstr > 0 && (!npts || !xyz))) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    uint8_t h[1000]; memset(h, 0, sizeof(h));
+    memcpy(h, "TRACK", 6);
+    for (int i = 0; i < 3; ++i) { const int16_t d = (int16_t)volsize[i]; memcpy(h + 6 + 2 * i, &d, 2); }
+    memcpy(h + 12, volres, 12);                                   // voxel_size; origin (24..35) = 0; n_scalars (36) = 0; n_properties (238) = 0
+    memcpy(h + 440, vox2ras, 64);                                 // vox_to_ras, row by row (permutedims before the write, :452)
+    // voxel_order from vox2ras_to_orient (src/mri.jl:471-500): the dominant axis of every column and its sign
+    for (int c = 0; c < 3; ++c) {
+        int im = 0; float am = std::fabs(vox2ras[c]);
+        for (int r = 1; r < 3; ++r) if (std::fabs(vox2ras[4 * r + c]) > am) { am = std::fabs(vox2ras[4 * r + c]); im = r; }
+        const bool pos = vox2ras[4 * im + c] > 0;
+        const char o = im == 0 ? (pos ? 'R' : 'L') : im == 1 ? (pos ? 'A' : 'P') : (pos ? 'S' : 'I');
+        h[948 + c] = (uint8_t)o; h[952 + c] = (uint8_t)o;         // voxel_order, voxel_order_original (4 bytes each, NUL-terminated)
+    }
+    // image_orientation_patient = ([-1 0 0; 0 -1 0; 0 0 1] * vox2ras[1:3, 1:2] * Diagonal(1 ./ volres[1:2]))[:]   (:105-110)
+    for (int c = 0; c < 2; ++c)
+        for (int r = 0; r < 3; ++r) {
+            const float v = (float)((r < 2 ? -1.0 : 1.0) * (double)vox2ras[4 * r + c] * (1.0 / (double)volres[c]));
+            memcpy(h + 956 + 4 * (3 * c + r), &v, 4);
+        }
+    const int32_t n32 = (int32_t)nstr, ver = 2, hs = 1000;
+    memcpy(h + 988, &n32, 4); memcpy(h + 992, &ver, 4); memcpy(h + 996, &hs, 4);
+    Out out;
+    if (!out.open(path, false)) return fail(FIBERS_ERR_ARG, std::string("Could not open ") + path + " for writing");
+    if (!out.write(h, 1000)) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
+    std::vector<float> buf;
+    int64_t p0 = 0;
+    for (int64_t i = 0; i < nstr; ++i) {
+        const int32_t n = npts[i];
+        buf.resize((size_t)3 * n + 1);
+        memcpy(buf.data(), &n, 4);
+        for (int32_t k = 0; k < n; ++k)
+            for (int c = 0; c < 3; ++c)                            // T.((xyz .+ .5) .* voxel_size): Float64 arithmetic, rounded once (:477)
+                buf[1 + 3 * k + c] = (float)(((double)xyz[3 * (p0 + k) + c] + 0.5) * (double)volres[c]);
+        if (!out.write(buf.data(), buf.size() * 4)) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
+        p0 += n;
+    }
+    if (!out.close()) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
+    return 0;
+}

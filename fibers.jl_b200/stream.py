@@ -22,9 +22,24 @@ class Tract:                       # the streamline fields of the reference's Tr
     npts: np.ndarray               # int32 [nstr]
     sublist: np.ndarray = field(default=None, repr=False)   # the sub-voxel offsets that were used (the reference keeps them in StreamWork)
 
+    ref: dict = field(default=None, repr=False)             # volsize / volres / vox2ras of the volume the header is built from (Tract{T}(ref::MRI))
+
     @property
     def n_count(self):
         return len(self.xyz)
+
+
+def trk_write(tr: "Tract", outfile: str) -> bool:
+    """trk_write(tr, outfile) -- src/trk.jl:433-495; header as Tract{T}(ref::MRI) builds it (:88-145).  Returns True on error."""
+    ref = tr.ref or {}
+    xyz = np.concatenate(tr.xyz, axis=1) if len(tr.xyz) else np.zeros((3, 0), np.float32)
+    xyz = np.asfortranarray(xyz, dtype=np.float32)
+    vs = np.ascontiguousarray(ref.get("volsize", [1, 1, 1]), np.int32)
+    vr = np.ascontiguousarray(ref.get("volres", [1, 1, 1]), np.float32)
+    M = np.ascontiguousarray(ref.get("vox2ras0", np.eye(4)), np.float32)
+    npts = np.ascontiguousarray(tr.npts, np.int32)
+    _lib.check(_lib.lib().fibers_trk_write(outfile.encode(), _lib.ptr(vs), _lib.ptr(vr), _lib.ptr(M), int(len(npts)), _lib.ptr(npts), _lib.ptr(xyz)))
+    return False
 
 
 def _vol(m):
@@ -114,4 +129,10 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
         timing["call_s"] = t1 - t0; timing["fetch_s"] = time.perf_counter() - t1
     ends = np.cumsum(npts, dtype=np.int64)
     lines = [xyz[:, e - n:e] for e, n in zip(ends, npts)]
-    return Tract(lines, npts, sub)
+    href = mask if isinstance(mask, MRI) else (ovecs[0] if isinstance(ovecs[0], MRI) else None)      # Tract{Float32}(mask) (:783)
+    ref = None
+    if href is not None:
+        M0 = np.asarray(href.header.get("vox2ras0", np.eye(4)), np.float32)
+        ref = dict(volsize=[nx, ny, nz], vox2ras0=M0,
+                   volres=href.header.get("volres", np.sqrt((M0[:3, :3].astype(np.float64) ** 2).sum(0)).tolist()))
+    return Tract(lines, npts, sub, ref)

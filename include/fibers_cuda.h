@@ -243,6 +243,12 @@ int fibers_mri_write(const char* path, const void* vol, int dtype, const int32_t
                      const float* volres /*[3] or NULL*/, float tr, float flip_angle, float te, float ti,
                      float scl_slope, float scl_inter, int out_dtype);
 
+/* trk_write (src/trk.jl:433-495) for the Tract that stream() returns: TrackVis .trk version 2 with the header Tract{T}(ref::MRI)
+ * builds (:88-145) from the reference volume (volsize, volres, vox2ras row-major; voxel order from vox2ras_to_orient,
+ * src/mri.jl:471-500), no scalars / properties; points are stored as (xyz + .5) * voxel_size like the reference. */
+int fibers_trk_write(const char* path, const int32_t* volsize /*[3]*/, const float* volres /*[3]*/, const float* vox2ras /*[16]*/,
+                     int64_t nstr, const int32_t* npts, const float* xyz /*[3, sum(npts)]*/);
+
 /* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
  * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
 int fibers_cuda_host_register(void* ptr, size_t bytes);

@@ -186,3 +186,31 @@ def test_mri_read_tables_and_datatype_conversion(tmp_path):
     m2 = fio.mri_read(str(tmp_path / "dwi"), permutedata=True)
     assert m2.vol.shape == (4, 4, 3, 5) and m2.header["ispermuted"]
     np.testing.assert_array_equal(m2.vol, np.swapaxes(back.vol, 0, 1))
+
+
+def test_trk_write_layout(tmp_path):
+    """fibers_trk_write against the TrackVis v2 layout trk_write produces (src/trk.jl:433-495, header :88-145)."""
+    from fibers_jl_b200.stream import Tract, trk_write
+    M = np.array([[-1.25, 0, 0, 90], [0, 0, 1.5, -126], [0, -2.0, 0, 72], [0, 0, 0, 1]], np.float32)
+    lines = [np.asfortranarray(np.array([[1, 2, 3.5], [4, 5, 6.25], [7, 8, 9]], np.float32).T), np.asfortranarray(np.array([[10.5, 2, 3], [1, 1, 1]], np.float32).T)]
+    tr = Tract(lines, np.array([3, 2], np.int32), None, dict(volsize=[40, 50, 60], volres=[1.25, 2.0, 1.5], vox2ras0=M))
+    assert trk_write(tr, str(tmp_path / "a.trk")) is False
+    raw = (tmp_path / "a.trk").read_bytes()
+    assert len(raw) == 1000 + 4 * (2 + 3 * 5)
+    assert raw[:6] == b"TRACK\0"
+    assert struct.unpack_from("<3h", raw, 6) == (40, 50, 60)
+    assert struct.unpack_from("<3f", raw, 12) == (1.25, 2.0, 1.5)
+    assert struct.unpack_from("<3f", raw, 24) == (0.0, 0.0, 0.0)
+    assert struct.unpack_from("<h", raw, 36)[0] == 0 and struct.unpack_from("<h", raw, 238)[0] == 0
+    np.testing.assert_array_equal(np.array(struct.unpack_from("<16f", raw, 440), np.float32).reshape(4, 4), M)
+    assert raw[948:952] == b"LIA\0" and raw[952:956] == b"LIA\0"           # columns of M: -x, -z, +y
+    iop = np.array(struct.unpack_from("<6f", raw, 956))
+    want = (np.diag([-1.0, -1.0, 1.0]) @ M[:3, :2].astype(np.float64) @ np.diag([1 / 1.25, 1 / 2.0])).reshape(-1, order="F")
+    np.testing.assert_allclose(iop, want, rtol=1e-6)
+    assert struct.unpack_from("<3i", raw, 988) == (2, 2, 1000)
+    off = 1000
+    for ln in lines:
+        n = struct.unpack_from("<i", raw, off)[0]; off += 4
+        assert n == ln.shape[1]
+        pts = np.array(struct.unpack_from(f"<{3 * n}f", raw, off), np.float32).reshape(n, 3); off += 12 * n
+        np.testing.assert_array_equal(pts, ((ln.T.astype(np.float64) + 0.5) * np.array([1.25, 2.0, 1.5])).astype(np.float32))

@@ -42,3 +42,9 @@ def test_read_recon_write_stream(tmp_path):
     tr = Fb.stream(peaks, f=got.qa, f_thresh=0.02, mask=m, sublist=sub)
     want = SO.stream([p.vol for p in got.peak], list(sub), f=[q.vol for q in got.qa], f_thresh=0.02, mask=ph["mask"])
     assert tr.n_count == len(want) > 0 and all(np.array_equal(a, b) for a, b in zip(tr.xyz, want))
+    # ... and to disk (trk_write, src/trk.jl:433): header from the mask volume, points as (xyz + .5) * voxel_size
+    assert Fb.trk_write(tr, str(tmp_path / "tract.trk")) is False
+    raw = (tmp_path / "tract.trk").read_bytes()
+    import struct
+    assert len(raw) == 1000 + 4 * tr.n_count + 12 * int(tr.npts.sum()) and struct.unpack_from("<3h", raw, 6) == (14, 12, 8)
+    assert struct.unpack_from("<i", raw, 988)[0] == tr.n_count and raw[948:951] == b"LAS"
