@@ -58,8 +58,8 @@ SIGNATURES = {
     "fibers_st_eigen": (_i, [_p] * 6 + [_i, _i, _i, _p, _p, _i]),
     "fibers_st_recon": (_i, [_p, _i, _i, _i, _f, _f, _p, _p, _i]),
     "fibers_st_eigen_device": (_i, [_p] * 6 + [_i64, _p, _p, _p]),
-    "fibers_stream": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p]),
-    "fibers_stream_device": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p]),
+    "fibers_stream": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _f, _i, _p, _p, _p]),
+    "fibers_stream_device": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _f, _p, _p, _p]),
     "fibers_stream_fetch": (_i, [_p, _p, _p]),
     "fibers_stream_free": (None, [_p]),
     "fibers_mri_read_info": (_i, [C.c_char_p, _p]),

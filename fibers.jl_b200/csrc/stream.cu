@@ -1,8 +1,8 @@
 // Deterministic streamline tractography on the GPU (`stream`, the downstream consumer of
 // the GQI / DSI / DTI peaks).  Replaces the `Threads.@threads` seed loop of the reference (src/stream.jl:730-790) and the
 // per-seed propagation it calls (stream_new_line :621-690, stream_new_point! :497-541, stream_pick_by_angle! :355-387)
-// for the regime that has a deterministic answer: orientation VECTORS, no local connection matrices (that branch draws
-// from rand(Categorical(...))), macroscopic voxels (voxel size > 50 um).
+// for what has a deterministic answer: orientation VECTORS, no local connection matrices (that branch draws from
+// rand(Categorical(...))); macroscopic voxels and the microscopy regime (stream_micro_new_point! :547-617).
 //
 //   stream_pack_kernel   the StreamWork constructor (:72-147): voxel mask (given, or "any vector component non-zero"),
 //                        intersected with fa >= fa_thresh; vectors zeroed outside the mask / where f[ivec] < f_thresh;
@@ -60,6 +60,7 @@ __global__ void stream_pack_kernel(PackIn in, int nvec, int has_f, float f_thres
 struct TrackParams {
     const float* ovec; const uint8_t* mask; const int32_t* seeds; int64_t nseed; const float* sub; int nsub;
     int nx, ny, nz, nvec, len_min, len_max; float cos_thresh, step, smooth;
+    int sd[3]; float search_cos;       // microscopy regime: half widths of the search box, cosine of the search angle
 };
 
 __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) { return (a0 * b0 + a1 * b1) + a2 * b2; }
@@ -134,6 +135,106 @@ __global__ void __launch_bounds__(128) stream_track_kernel(TrackParams P, int2* 
     if (!kWrite) nfb[line] = make_int2(nf, nb);
 }
 
+// ---- microscopy regime (stream_micro_new_point!, src/stream.jl:547-617): one WARP per line.  After the tentative step the
+// next POSITION is the voxel of the (2 d1 + 1)(2 d2 + 1)(2 d3 + 1) search box -- inside the mask and inside the cone of the
+// search angle around the current direction -- whose first vector is most similar to the current one: `argmax` over the box
+// in column-major order (first maximum, NaN first; voxels outside the volume, the mask or the cone hold -Inf).  The unit vectors
+// of the search area (:268-292) are recomputed per candidate in the reference's fp32 order; its centre is 0 / 0 = NaN, which
+// fails every comparison, so the centre voxel always passes the cone test -- kept.
+struct Cand { float val, cos; int idx; };
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {       // does a come before b in Julia's argmax?
+    const bool an = isnan(a.val), bn = isnan(b.val);
+    if (an != bn) return an;
+    if (an) return a.idx < b.idx;
+    return a.val > b.val || (a.val == b.val && a.idx < b.idx);
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(128) stream_track_micro_kernel(TrackParams P, int2* __restrict__ nfb, const int64_t* __restrict__ off,
+                                                                  const int32_t* __restrict__ sidx, const uint8_t* __restrict__ kept,
+                                                                  float* __restrict__ xyz, int32_t* __restrict__ npts_out) {
+    const int64_t line = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (line >= P.nseed * P.nsub) return;
+    int nf_known = 0;
+    float* out = nullptr;
+    if (kWrite) {
+        if (!kept[line]) return;
+        const int2 c = nfb[line];
+        nf_known = c.x;
+        out = xyz + 3 * off[line];
+        if (lane == 0) npts_out[sidx[line]] = c.x + c.y;
+    }
+    const int64_t si = line / P.nsub; const int isub = (int)(line - si * P.nsub);
+    const int lin = P.seeds[si];
+    const int sx = lin % P.nx, sy = (lin / P.nx) % P.ny, sz = lin / (P.nx * P.ny);
+    const float s0 = P.sub[isub * 3 + 0], s1 = P.sub[isub * 3 + 1], s2 = P.sub[isub * 3 + 2];
+    const int d0 = P.sd[0], d1 = P.sd[1], d2 = P.sd[2];
+    const int w0 = 2 * d0 + 1, w1 = 2 * d1 + 1, nbox = w0 * w1 * (2 * d2 + 1);
+    const float h0 = (float)d0 + 0.5f, h1 = (float)d1 + 0.5f, h2 = (float)d2 + 0.5f;
+    int npts = 0, nf = 0, nb = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        const float fwd = dir == 0 ? 1.f : -1.f;
+        float px = (float)(sx + 1) + s0, py = (float)(sy + 1) + s1, pz = (float)(sz + 1) + s2;
+        const float* sv = P.ovec + (int64_t)lin * P.nvec * 3;          // first vector (W.ivec_next stays 1 in this regime)
+        float vx = sv[0] * fwd, vy = sv[1] * fwd, vz = sv[2] * fwd;
+        while (true) {
+            const float qx = px + vx * P.step, qy = py + vy * P.step, qz = pz + vz * P.step;
+            const int ix = __float2int_rn(qx), iy = __float2int_rn(qy), iz = __float2int_rn(qz);
+            if (ix < 1 || ix > P.nx || iy < 1 || iy > P.ny || iz < 1 || iz > P.nz) break;
+            if (!P.mask[(int64_t)(ix - 1) + (int64_t)P.nx * ((iy - 1) + (int64_t)P.ny * (iz - 1))]) break;
+            Cand best{-INFINITY, -INFINITY, 0x7fffffff};
+            for (int idx = lane; idx < nbox; idx += 32) {
+                const int kx = idx % w0 - d0, ky = (idx / w0) % w1 - d1, kz = idx / (w0 * w1) - d2;
+                const int x = ix + kx, y = iy + ky, z = iz + kz;
+                Cand c{-INFINITY, -INFINITY, idx};
+                if (x >= 1 && x <= P.nx && y >= 1 && y <= P.ny && z >= 1 && z <= P.nz) {
+                    const int64_t nl = (int64_t)(x - 1) + (int64_t)P.nx * ((y - 1) + (int64_t)P.ny * (z - 1));
+                    const float rx = (float)kx / h0, ry = (float)ky / h1, rz = (float)kz / h2;
+                    const float r = sqrtf((rx * rx + ry * ry) + rz * rz);
+                    float ax = 0.f, ay = 0.f, az = 0.f;
+                    if (r < 1.f) { ax = rx / r; ay = ry / r; az = rz / r; }
+                    const bool skip = !P.mask[nl] || (ax == 0.f && ay == 0.f && az == 0.f) || (dot3(vx, vy, vz, ax, ay, az) <= P.search_cos);
+                    if (!skip) {
+                        const float* ov = P.ovec + nl * P.nvec * 3;
+                        c.cos = dot3(vx, vy, vz, ov[0], ov[1], ov[2]);
+                        c.val = fabsf(c.cos);
+                    }
+                }
+                if (cand_better(c, best)) best = c;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                Cand t{__shfl_xor_sync(0xffffffffu, best.val, o), __shfl_xor_sync(0xffffffffu, best.cos, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
+                if (cand_better(t, best)) best = t;
+            }
+            if (!isfinite(best.cos)) break;
+            const int kx = best.idx % w0 - d0, ky = (best.idx / w0) % w1 - d1, kz = best.idx / (w0 * w1) - d2;
+            const int bxv = ix + kx, byv = iy + ky, bzv = iz + kz;
+            const float* ov = P.ovec + ((int64_t)(bxv - 1) + (int64_t)P.nx * ((byv - 1) + (int64_t)P.ny * (bzv - 1))) * P.nvec * 3;
+            float nxv = ov[0], nyv = ov[1], nzv = ov[2];
+            if (!(best.cos > 0.f)) { nxv = -nxv; nyv = -nyv; nzv = -nzv; }
+            if (kWrite && lane == 0) {
+                float* o = out + 3 * (int64_t)(dir == 0 ? nf_known - 1 - nf : nf_known + nb);
+                o[0] = px; o[1] = py; o[2] = pz;
+            }
+            if (dir == 0) ++nf; else ++nb;
+            ++npts;
+            if (dot3(vx, vy, vz, nxv, nyv, nzv) < P.cos_thresh) break;
+            if (npts > P.len_max) break;
+            if (P.smooth != 0.f) {
+                const float om = 1.f - P.smooth;
+                const float tx = P.smooth * vx + om * nxv, ty = P.smooth * vy + om * nyv, tz = P.smooth * vz + om * nzv;
+                const float nrm = (float)sqrt(((double)(tx * tx) + (double)(ty * ty)) + (double)(tz * tz));
+                nxv = tx / nrm; nyv = ty / nrm; nzv = tz / nrm;
+            }
+            px = (float)bxv; py = (float)byv; pz = (float)bzv;             // the position of the chosen voxel (:603-605)
+            vx = nxv; vy = nyv; vz = nzv;
+        }
+    }
+    if (!kWrite && lane == 0) nfb[line] = make_int2(nf, nb);
+}
+
 __global__ void stream_len_kernel(const int2* __restrict__ nfb, int64_t n, int len_min, int64_t* __restrict__ len, int32_t* __restrict__ keep32, uint8_t* __restrict__ kept) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -157,7 +258,8 @@ using namespace fibers;
 extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
                                     const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
                                     const float* sublist /*host [nsub][3]*/, int nsub, int len_min, int len_max, float cosang_thresh,
-                                    float step_size, float smooth_coeff, void** result, int64_t* nstr, int64_t* npts_total) {
+                                    float step_size, float smooth_coeff, const int32_t* micro_search_dist, float micro_search_cosang,
+                                    void** result, int64_t* nstr, int64_t* npts_total) {
     if (!d_ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
     if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
     if (nx <= 0 || ny <= 0 || nz <= 0 || nsub <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions and the number of sub-voxel samples must be positive");
@@ -196,9 +298,15 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
     int2* nfb; int64_t *len, *off; int32_t *keep32, *sidx; uint8_t* kept;
     T_CUDA(D.alloc(&nfb, (size_t)nline)); T_CUDA(D.alloc(&len, (size_t)nline + 1)); T_CUDA(D.alloc(&off, (size_t)nline + 1));
     T_CUDA(D.alloc(&keep32, (size_t)nline + 1)); T_CUDA(D.alloc(&sidx, (size_t)nline + 1)); T_CUDA(D.alloc(&kept, (size_t)nline));
-    TrackParams P{ovec_arr, mask_arr, seeds, nseed, d_sub, nsub, nx, ny, nz, nvec, len_min, len_max, cosang_thresh, step_size, smooth_coeff};
-    const unsigned gl = (unsigned)((nline + 127) / 128);
-    stream_track_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
+    TrackParams P{ovec_arr, mask_arr, seeds, nseed, d_sub, nsub, nx, ny, nz, nvec, len_min, len_max, cosang_thresh, step_size, smooth_coeff, {0, 0, 0}, 0.f};
+    const bool micro = micro_search_dist != nullptr;
+    if (micro) {
+        for (int i = 0; i < 3; ++i) { if (micro_search_dist[i] < 0 || micro_search_dist[i] > 64) return fail(FIBERS_ERR_ARG, "micro_search_dist must be in 0..64"); P.sd[i] = micro_search_dist[i]; }
+        P.search_cos = micro_search_cosang;
+    }
+    const unsigned gl = (unsigned)(micro ? (nline * 32 + 127) / 128 : (nline + 127) / 128);          // micro: one warp per line
+    if (micro) stream_track_micro_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else stream_track_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
     stream_len_kernel<<<(unsigned)((nline + 255) / 256), 256>>>(nfb, nline, len_min, len, keep32, kept);
     count_launch(2);
     T_CUDA(cudaMemsetAsync(len + nline, 0, sizeof(int64_t))); T_CUDA(cudaMemsetAsync(keep32 + nline, 0, sizeof(int32_t)));
@@ -221,7 +329,8 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
         return fail(FIBERS_ERR_NOMEM, "stream: device allocation of the streamline buffers failed");
     }
     if (nkeep > 0) {
-        stream_track_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
+        if (micro) stream_track_micro_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
+        else stream_track_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
         count_launch(1);
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -232,7 +341,8 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
 
 extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
                              const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
-                             int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff, int device,
+                             int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff,
+                             const int32_t* micro_search_dist, float micro_search_cosang, int device,
                              void** result, int64_t* nstr, int64_t* npts_total) {
     if (!ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
     if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
@@ -257,7 +367,7 @@ extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny,
     if (mask) if (int rc = up(mask, (size_t)nvox, (const void**)&d_mask)) return rc;
     if (seed) if (int rc = up(seed, (size_t)nvox, (const void**)&d_seed)) return rc;
     return fibers_stream_device(d_ovec, nvec, nx, ny, nz, f ? d_f : nullptr, f_thresh, d_fa, fa_thresh, d_mask, d_seed, sublist, nsub,
-                                len_min, len_max, cosang_thresh, step_size, smooth_coeff, result, nstr, npts_total);
+                                len_min, len_max, cosang_thresh, step_size, smooth_coeff, micro_search_dist, micro_search_cosang, result, nstr, npts_total);
 }
 
 extern "C" int fibers_stream_fetch(void* result, int32_t* npts, float* xyz) {

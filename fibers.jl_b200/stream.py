@@ -1,9 +1,10 @@
 """Host-side mirror of the reference's `stream` (src/stream.jl:730-790): same keyword arguments, same defaults,
 same output order; one blocking call into libfibers_cuda.so (fibers_stream) plus the fetch of the result.
 
-Covers the regime with a deterministic answer -- orientation vectors, no local connection matrices, macroscopic
-voxels.  `lcms` (random sampling from the connection matrix, src/stream.jl:394-492) and the microscopy regime
-(voxel size <= 50 um, :524-617) are not on the GPU path and raise.  There is no CPU fallback.
+Covers what has a deterministic answer -- orientation vectors, no local connection matrices, in the macroscopic and in
+the microscopy regime (voxel size <= 50 um: regime-dependent defaults and the box search of stream_micro_new_point!,
+src/stream.jl:84-95, :547-617).  `lcms` (random sampling from the connection matrix, :394-492) and 2-D orientation
+ANGLES as input (:145-172) are not on the GPU path and raise.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -56,8 +57,8 @@ def draw_sublist(nsub: int, rng=None) -> np.ndarray:
     return g.uniform(-0.5 + e, 0.5 - e, size=(nsub, 3)).astype(np.float32)
 
 
-def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=3, len_min=3,
-           len_max=None, ang_thresh=45, step_size=0.5, smooth_coeff=0.2, search_dist=15, search_ang=10, lcms=None,
+def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=None, len_min=3,
+           len_max=None, ang_thresh=None, step_size=None, smooth_coeff=None, search_dist=15, search_ang=10, lcms=None,
            lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None) -> Tract:
     """stream(ovec; odf, f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size,
     smooth_coeff, search_dist, search_ang, lcms, lcm_thresh, verbose) -- reference: src/stream.jl:730.
@@ -69,8 +70,7 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     if lcms is not None:
         raise _lib.FibersCudaError(1, "stream: local connection matrices (lcms) are not on the GPU path")
     res = ovecs[0].header.get("volres") if isinstance(ovecs[0], MRI) else None
-    if res is not None and min(res) <= 0.05:
-        raise _lib.FibersCudaError(1, "stream: the microscopy regime (voxel size <= 50 um) is not on the GPU path")
+    domicro = res is not None and min(res) <= 0.05                   # microscopy regime (src/stream.jl:84)
     vols = []
     for o in ovecs:
         v = np.asfortranarray(_vol(o), dtype=np.float32)
@@ -95,16 +95,21 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
         if mask is not None and tuple(sv.shape) != tuple(_vol(mask).shape):
             raise ValueError(f"Dimension mismatch between seed mask {tuple(sv.shape)} and brain mask {tuple(_vol(mask).shape)}")
         sd = np.asfortranarray((sv.reshape((nx, ny, nz, -1), order="F")[..., 0] > 0).astype(np.uint8))
+    # defaults that depend on the regime (src/stream.jl:91-95)
     if nsub is None:
-        nsub = 3
+        nsub = 0 if domicro else 3
     if sublist is None:
         sublist = draw_sublist(int(nsub), rng)
     sub = np.ascontiguousarray(sublist, dtype=np.float32).reshape(-1, 3)
     if len_max is None:
         len_max = max(nx, ny, nz)                                   # maximum(ovec.volsize)
-    ang = 45 if ang_thresh is None else ang_thresh
-    step = 0.5 if step_size is None else step_size
-    smooth = 0.2 if smooth_coeff is None else smooth_coeff
+    ang = (20 if domicro else 45) if ang_thresh is None else ang_thresh
+    step = (1 if domicro else 0.5) if step_size is None else step_size
+    smooth = (0 if domicro else 0.2) if smooth_coeff is None else smooth_coeff
+    msd = None; mcos = 0.0
+    if domicro:
+        msd = (C.c_int32 * 3)(*([int(search_dist)] * 3))             # fill(Int(search_dist), 3) (:86)
+        mcos = float(np.float32(np.cos(np.deg2rad(np.float64(np.float32(search_ang))))))   # cosd(T(search_ang)) (:306)
     cos_thresh = np.float32(np.cos(np.deg2rad(np.float64(np.float32(ang)))))    # cosd(T(ang_thresh))
 
     L = _lib.lib(); _lib.require_device()
@@ -116,7 +121,7 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     t0 = time.perf_counter()
     _lib.check(L.fibers_stream(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
                                _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(cos_thresh),
-                               float(step), float(smooth), int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
+                               float(step), float(smooth), msd, mcos, int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
     t1 = time.perf_counter()
     try:
         npts = np.zeros(nstr.value, np.int32)

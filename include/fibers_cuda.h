@@ -181,7 +181,7 @@ int fibers_st_eigen_device(const float* d_sxx, const float* d_sxy, const float* 
 
 /* stream: src/stream.jl:730-790 (streamline tractography), the deterministic regime: orientation
  * VECTORS (ovec[i] = [nx,ny,nz,3] float32, i < nvec <= 8, e.g. the peak volumes of gqi_rec / dsi_rec or eigvec1 of dti_fit),
- * no local connection matrices, macroscopic voxels.  Replaces the StreamWork constructor's masking (:72-147), the
+ * no local connection matrices; macroscopic voxels and the microscopy regime.  Replaces the StreamWork constructor's masking (:72-147), the
  * `Threads.@threads` seed loop (:759-781) and stream_new_line / stream_new_point! / stream_pick_by_angle! (:621-690,
  * :497-541, :355-387).
  *   f        nvec volumes [nx,ny,nz] (vector amplitudes, e.g. qa1..3) or NULL; vectors with f < f_thresh are dropped (:136-138)
@@ -191,6 +191,9 @@ int fibers_st_eigen_device(const float* d_sxx, const float* d_sxy, const float* 
  *   sublist  [nsub][3] sub-voxel offsets.  The reference draws them from rand(Uniform(-.5+eps(), .5-eps()), 3) (:177-183, or a
  *            single zero offset when nsub == 0): the WRAPPER draws them (same call, Julia's RNG) and passes them in.
  *   cosang_thresh = cosd(T(ang_thresh)), step_size, smooth_coeff, len_min, len_max: the StreamWork fields of the same name.
+ *   micro_search_dist  NULL = macroscopic regime; [3] half widths of the search box = the microscopy regime (StreamWork sets it when
+ *            min(volres) <= 0.05: fill(search_dist, 3), 0 along the through-plane axis of 2-D data, :84-90, :153), in which the next
+ *            position is searched around the tentative step (stream_micro_new_point! :547-617); micro_search_cosang = cosd(T(search_ang)).
  * Output order = the reference's: seed voxels in column-major order, sub-voxel samples innermost, lines shorter than len_min
  * dropped; coordinates are the reference's 1-based voxel coordinates.  The number of points is not known beforehand, so the call
  * returns an opaque handle plus the counts; the caller allocates npts[nstr] (Int32) and xyz[3, npts_total] (Float32: the
@@ -198,12 +201,14 @@ int fibers_st_eigen_device(const float* d_sxx, const float* d_sxy, const float* 
  * The _device variant takes DEVICE volume pointers (peaks / qa planes a reconstruction left on the current device). */
 int fibers_stream(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
                   const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
-                  int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff, int device,
+                  int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff,
+                  const int32_t* micro_search_dist /*[3] or NULL*/, float micro_search_cosang, int device,
                   void** result, int64_t* nstr, int64_t* npts_total);
 int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
                          const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
                          const float* sublist, int nsub, int len_min, int len_max, float cosang_thresh,
-                         float step_size, float smooth_coeff, void** result, int64_t* nstr, int64_t* npts_total);
+                         float step_size, float smooth_coeff, const int32_t* micro_search_dist, float micro_search_cosang,
+                         void** result, int64_t* nstr, int64_t* npts_total);
 int fibers_stream_fetch(void* result, int32_t* npts, float* xyz);
 void fibers_stream_free(void* result);
 

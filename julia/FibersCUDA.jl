@@ -274,15 +274,17 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
                 seed::Union{MRI,Nothing}=nothing, nsub::Union{Integer,Nothing}=3, len_min::Integer=3,
                 len_max::Integer=(isa(ovec,MRI) ? maximum(ovec.volsize) : maximum(ovec[1].volsize)),
                 ang_thresh::Union{Real,Nothing}=45, step_size::Union{Real,Nothing}=.5,
-                smooth_coeff::Union{Real,Nothing}=.2, lcms::Union{MRI,Nothing}=nothing)
+                smooth_coeff::Union{Real,Nothing}=.2, search_dist::Integer=15, search_ang::Real=10,
+                lcms::Union{MRI,Nothing}=nothing)
   isnothing(lcms) || error("stream: local connection matrices are not on the GPU path")
   ovecs = isa(ovec, MRI) ? MRI[ovec] : ovec
   fs    = isa(f, MRI) ? MRI[f] : f
-  minimum(ovecs[1].volres) <= 0.05 && error("stream: the microscopy regime is not on the GPU path")
   all(o -> size(o.vol, 4) == 3, ovecs) || error("stream: orientation volumes must be [nx,ny,nz,3] vectors on the GPU path")
   nx, ny, nz = size(ovecs[1].vol)[1:3]
-  isnothing(nsub) && (nsub = 3); isnothing(ang_thresh) && (ang_thresh = 45)
-  isnothing(step_size) && (step_size = .5); isnothing(smooth_coeff) && (smooth_coeff = .2)
+  domicro = (minimum(ovecs[1].volres) <= 0.05)                    # src/stream.jl:84
+  micro_search_dist = domicro ? fill(Int32(search_dist), 3) : Int32[]
+  isnothing(nsub) && (nsub = domicro ? 0 : 3); isnothing(ang_thresh) && (ang_thresh = domicro ? 20 : 45)
+  isnothing(step_size) && (step_size = domicro ? 1 : .5); isnothing(smooth_coeff) && (smooth_coeff = domicro ? 0 : .2)
   if !isnothing(seed) && !isnothing(mask) && size(seed.vol) != size(mask.vol)
     error("Dimension mismatch between seed mask " * string(size(seed.vol)) * " and brain mask " * string(size(mask.vol)))
   end
@@ -297,11 +299,11 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
   GC.@preserve vols fvol begin
     check(ccall((:fibers_stream, libfibers), Cint,
                 (Ptr{Ptr{Float32}}, Cint, Cint, Cint, Cint, Ptr{Ptr{Float32}}, Cfloat, Ptr{Float32}, Cfloat, Ptr{UInt8}, Ptr{UInt8},
-                 Ptr{Float32}, Cint, Cint, Cint, Cfloat, Cfloat, Cfloat, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}),
+                 Ptr{Float32}, Cint, Cint, Cint, Cfloat, Cfloat, Cfloat, Ptr{Int32}, Cfloat, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}),
                 pointer.(vols), length(vols), nx, ny, nz, isnothing(fvol) ? C_NULL : pointer.(fvol), Float32(f_thresh),
                 isnothing(favol) ? C_NULL : favol, Float32(fa_thresh), isnothing(m) ? C_NULL : m, isnothing(sd) ? C_NULL : sd,
                 sub, size(sub, 2), len_min, len_max, cosd(Float32(ang_thresh)), Float32(step_size), Float32(smooth_coeff),
-                0, handle, nstr, ntot))
+                domicro ? micro_search_dist : C_NULL, domicro ? cosd(Float32(search_ang)) : 0f0, 0, handle, nstr, ntot))
   end
   npts = Vector{Int32}(undef, nstr[]); xyz = Matrix{Float32}(undef, 3, ntot[])
   try

@@ -3,12 +3,13 @@ tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this; the pro
 
 Follows /root/reference/src/stream.jl line by line for the regime the GPU path covers: orientation vectors
 given as 3-D vectors, no local connection matrices (`lcms === nothing`; that branch draws from
-`rand(Categorical(...))` and has no deterministic answer) and the macroscopic regime (voxel size > 50 um,
-`domicro == false`).
+`rand(Categorical(...))` and has no deterministic answer), in the macroscopic regime (voxel size > 50 um) and in the
+microscopy regime (`domicro`: the next POSITION is searched in a box around the tentative step).
 
     StreamWork (mask / vector masking)        src/stream.jl:72-140
     stream_pick_by_angle!                     src/stream.jl:355-387
     stream_new_point!                         src/stream.jl:497-541
+    stream_micro_new_point! (+ search area)   src/stream.jl:547-617, :266-300
     stream_new_line                           src/stream.jl:621-690
     stream (seed order, len_min filter)       src/stream.jl:730-790
 
@@ -102,7 +103,62 @@ def _new_point(st, mask, ovec, step):
     return _pick_by_angle(st, ix, iy, iz, ovec)
 
 
-def new_line(seed_vox, sub_vox, mask, ovec, len_max, cosang_thresh, step, smooth):
+def search_area(dist):
+    """Unit vectors from the centre of the (2 d1 + 1, 2 d2 + 1, 2 d3 + 1) search box to its voxels, zero outside the unit
+    ellipsoid -- src/stream.jl:268-292.  The centre itself is 0 / 0 = NaN (the reference keeps it: every comparison with
+    NaN is false, so the centre voxel always passes the cone test, :573-575)."""
+    d = [int(x) for x in dist]
+    A = np.zeros((2 * d[0] + 1, 2 * d[1] + 1, 2 * d[2] + 1, 3), dtype=F)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for iz in range(A.shape[2]):
+            for iy in range(A.shape[1]):
+                for ix in range(A.shape[0]):
+                    rx = F(F(ix - d[0]) / F(d[0] + F(0.5)))
+                    ry = F(F(iy - d[1]) / F(d[1] + F(0.5)))
+                    rz = F(F(iz - d[2]) / F(d[2] + F(0.5)))
+                    r = F(np.sqrt(F(F(F(rx * rx) + F(ry * ry)) + F(rz * rz))))
+                    if r < 1:
+                        A[ix, iy, iz] = [F(rx / r), F(ry / r), F(rz / r)]
+    return A
+
+
+def _micro_new_point(st, mask, ovec, step, dist, area, search_cosang):
+    """stream_micro_new_point!, src/stream.jl:547-617: tentative step, then the voxel of the search box (inside the mask and
+    inside the cone around the current direction) whose vector is most similar to the current one becomes the next POSITION."""
+    st.pos_next = (st.pos_now + (st.vec_now * step).astype(F)).astype(F)
+    ix, iy, iz = _rnd(st.pos_next[0]), _rnd(st.pos_next[1]), _rnd(st.pos_next[2])
+    nx, ny, nz = mask.shape
+    if not (1 <= ix <= nx and 1 <= iy <= ny and 1 <= iz <= nz):
+        return False
+    if not mask[ix - 1, iy - 1, iz - 1]:
+        return False
+    best = None                                          # (value, is_nan) of the first maximum in column-major order of the box
+    bcos = F(-np.inf); bpos = None
+    d = dist
+    for kz in range(-d[2], d[2] + 1):
+        for ky in range(-d[1], d[1] + 1):
+            for kx in range(-d[0], d[0] + 1):
+                x, y, z = ix + kx, iy + ky, iz + kz
+                val = F(-np.inf); cos = F(-np.inf)
+                if 1 <= x <= nx and 1 <= y <= ny and 1 <= z <= nz:
+                    v = area[kx + d[0], ky + d[1], kz + d[2]]
+                    skip = (not mask[x - 1, y - 1, z - 1]) or (v[0] == 0 and v[1] == 0 and v[2] == 0) or (_dot3(st.vec_now, v) <= search_cosang)
+                    if not skip:
+                        cos = _dot3(st.vec_now, ovec[:, 0, x - 1, y - 1, z - 1])
+                        val = F(abs(cos))
+                if best is None:
+                    best = val; bcos = cos; bpos = (x, y, z)
+                elif not np.isnan(best) and (np.isnan(val) or val > best):
+                    best = val; bcos = cos; bpos = (x, y, z)
+    if not np.isfinite(bcos):
+        return False
+    st.pos_next = np.array(bpos, dtype=F)
+    v = ovec[:, 0, bpos[0] - 1, bpos[1] - 1, bpos[2] - 1]
+    st.vec_next = v.copy() if bcos > 0 else (-v).astype(F)
+    return True
+
+
+def new_line(seed_vox, sub_vox, mask, ovec, len_max, cosang_thresh, step, smooth, micro=None):
     """src/stream.jl:621-690: returns the [3, npts] streamline of one (seed voxel, sub-voxel offset)."""
     step, smooth, cosang_thresh = F(step), F(smooth), F(cosang_thresh)
     st = _State()
@@ -114,7 +170,8 @@ def new_line(seed_vox, sub_vox, mask, ovec, len_max, cosang_thresh, step, smooth
         st.pos_now = (seed + np.asarray(sub_vox, dtype=F)).astype(F)
         st.vec_now = (ovec[:, st.ivec_next - 1, seed_vox[0] - 1, seed_vox[1] - 1, seed_vox[2] - 1] * F(fwd)).astype(F)
         while True:
-            if not _new_point(st, mask, ovec, step):
+            ok = _micro_new_point(st, mask, ovec, step, *micro) if micro is not None else _new_point(st, mask, ovec, step)
+            if not ok:
                 break
             (fwd_pts if fwd == 1 else bwd_pts).append(st.pos_now.copy())     # prepend! / append! (:660, :666)
             npts += 1
@@ -134,7 +191,7 @@ def new_line(seed_vox, sub_vox, mask, ovec, len_max, cosang_thresh, step, smooth
 
 
 def stream(ovecs, sublist, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, len_min=3, len_max=None,
-           cosang_thresh=None, step_size=0.5, smooth_coeff=0.2):
+           cosang_thresh=None, step_size=0.5, smooth_coeff=0.2, micro_search_dist=None, micro_search_cosang=None):
     """src/stream.jl:730-790.  Returns the list of [3, npts] streamlines in the reference's order (seed voxels in
     column-major order, sub-voxel samples innermost), lines shorter than len_min dropped."""
     m, arr = stream_work(ovecs, f, f_thresh, fa, fa_thresh, mask)
@@ -145,11 +202,15 @@ def stream(ovecs, sublist, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=N
         cosang_thresh = F(np.cos(np.deg2rad(45.0)))
     sm = m if seed is None else (np.asarray(seed).reshape(nx, ny, nz, -1)[..., 0] > 0)
     lin = np.flatnonzero(sm.reshape(-1, order="F"))           # findall: column-major order
+    micro = None
+    if micro_search_dist is not None:                        # microscopy regime (domicro, src/stream.jl:84-90, :266-300)
+        dist = [int(x) for x in micro_search_dist]
+        micro = (dist, search_area(dist), F(micro_search_cosang))
     out = []
     for l in lin:
         vox = [int(l % nx) + 1, int((l // nx) % ny) + 1, int(l // (nx * ny)) + 1]
         for sub in sublist:
-            s = new_line(vox, sub, m, arr, len_max, cosang_thresh, step_size, smooth_coeff)
+            s = new_line(vox, sub, m, arr, len_max, cosang_thresh, step_size, smooth_coeff, micro)
             if s.shape[1] >= len_min:
                 out.append(s)
     return out

@@ -150,8 +150,6 @@ def test_stream_rejects_what_is_not_on_the_gpu_path():
     with pytest.raises(Fb.FibersCudaError):
         Fb.stream(Fb.MRI(v), lcms=Fb.MRI(np.zeros((4, 4, 4, 10), F)))
     with pytest.raises(Fb.FibersCudaError):
-        Fb.stream(Fb.MRI(v, volres=(0.01, 0.01, 0.05)))
-    with pytest.raises(Fb.FibersCudaError):
         Fb.stream(Fb.MRI(np.zeros((4, 4, 4), F)))
 
 
@@ -173,7 +171,7 @@ def test_stream_device_resident_entry_point():
     PP = C.c_void_p * 2
     h = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
     Fb._lib.check(L.fibers_stream_device(PP(*[t.data_ptr() for t in d_v]), 2, *shape, PP(*[t.data_ptr() for t in d_f]), 0.1, None, 0.0, None, None,
-                                          Fb._lib.ptr(sub), 2, 3, max(shape), float(np.float32(np.cos(np.deg2rad(45.0)))), 0.5, 0.2,
+                                          Fb._lib.ptr(sub), 2, 3, max(shape), float(np.float32(np.cos(np.deg2rad(45.0)))), 0.5, 0.2, None, 0.0,
                                           C.byref(h), C.byref(nstr), C.byref(ntot)))
     try:
         npts = np.zeros(nstr.value, np.int32); xyz = np.zeros((3, ntot.value), np.float32, order="F")
@@ -182,3 +180,61 @@ def test_stream_device_resident_entry_point():
         L.fibers_stream_free(h)
     assert nstr.value == ref.n_count > 0 and np.array_equal(npts, ref.npts)
     assert np.array_equal(xyz, np.concatenate(ref.xyz, axis=1))
+
+
+def test_oracle_micro_regime_quirks():
+    """Search area (src/stream.jl:268-292): unit vectors inside the unit ellipsoid, zeros outside, NaN at the centre (0 / 0), which
+    the cone test cannot reject (:573-575).  Straight +x field, step 1, 5 x 5 x 1 box: the line hops to the voxel straight ahead."""
+    A = SO.search_area([2, 2, 0])
+    assert np.isnan(A[2, 2, 0]).all() and not A[0, 0, 0].any() and A[4, 2, 0, 0] == 1 and A[2, 0, 0, 1] == -1
+    np.testing.assert_allclose(A[3, 3, 0], [np.sqrt(0.5), np.sqrt(0.5), 0], rtol=1e-6)
+    v = straight_field((12, 6, 3))
+    m, arr = SO.stream_work([v])
+    micro = ([2, 2, 0], A, F(np.cos(np.deg2rad(10.0))))
+    s = SO.new_line([5, 3, 2], np.zeros(3, F), m, arr, len_max=100, cosang_thresh=F(np.cos(np.deg2rad(20.0))), step=1.0, smooth=0.0, micro=micro)
+    # every voxel of the box has |cos| = 1; the 10-degree cone around +x leaves the voxels straight ahead (dy = 0, dx > 0) and the
+    # centre, whose NaN vector cannot be rejected; the centre comes first in the box's column-major order, so it wins: the line
+    # advances exactly one voxel per step
+    assert np.all(s[1] == 3) and np.all(s[2] == 2)
+    fwd = s[0][: np.argmax(s[0] == 5.0) + 1][::-1]
+    np.testing.assert_array_equal(fwd, np.arange(5.0, 5.0 + len(fwd)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dist", [(3, 3, 0), (2, 2, 2)])
+def test_stream_gpu_micro_regime_bit_exact(dist):
+    """Microscopy regime (voxel size <= 50 um): regime defaults (nsub 0, 20 degrees, step 1, no smoothing) and the box search."""
+    import fibers_jl_b200 as Fb
+    shape = (22, 18, 6)
+    vols, _ = noisy_field(shape, 1, seed=12)
+    g = np.random.default_rng(2)
+    mask = np.asfortranarray((g.random(shape) < 0.92).astype(np.uint8))
+    # the Python mirror always fills the three half widths with search_dist (:86); call the C ABI through it with a cubic box, and
+    # the anisotropic box (through-plane 0, :153) through the oracle-equivalent keyword below
+    if dist[2] == dist[0]:
+        got = Fb.stream(Fb.MRI(vols[0], volres=(0.01, 0.01, 0.01)), mask=Fb.MRI(mask), search_dist=dist[0], search_ang=25)
+        ref = SO.stream(vols, [np.zeros(3, F)], mask=mask, step_size=1.0, smooth_coeff=0.0, cosang_thresh=F(np.cos(np.deg2rad(np.float64(F(20))))),
+                        micro_search_dist=dist, micro_search_cosang=F(np.cos(np.deg2rad(np.float64(F(25))))))
+    else:
+        import ctypes as C
+        L = Fb._lib.lib()
+        PP = C.c_void_p * 1
+        h = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
+        sub = np.zeros((1, 3), F)
+        Fb._lib.check(L.fibers_stream(PP(vols[0].ctypes.data), 1, *shape, None, 0.0, None, 0.0, Fb._lib.ptr(mask), None, Fb._lib.ptr(sub), 1, 3, max(shape),
+                                      float(F(np.cos(np.deg2rad(20.0)))), 1.0, 0.0, (C.c_int32 * 3)(*dist), float(F(np.cos(np.deg2rad(25.0)))), 0,
+                                      C.byref(h), C.byref(nstr), C.byref(ntot)))
+        try:
+            npts = np.zeros(nstr.value, np.int32); xyz = np.zeros((3, ntot.value), F, order="F")
+            Fb._lib.check(L.fibers_stream_fetch(h, Fb._lib.ptr(npts), Fb._lib.ptr(xyz)))
+        finally:
+            L.fibers_stream_free(h)
+        ends = np.cumsum(npts)
+        from fibers_jl_b200.stream import Tract
+        got = Tract([xyz[:, e - n:e] for e, n in zip(ends, npts)], npts)
+        ref = SO.stream(vols, [np.zeros(3, F)], mask=mask, step_size=1.0, smooth_coeff=0.0, cosang_thresh=F(np.cos(np.deg2rad(20.0))),
+                        micro_search_dist=dist, micro_search_cosang=F(np.cos(np.deg2rad(25.0))))
+    assert got.n_count == len(ref) and got.n_count > 100
+    nbad = sum(0 if np.array_equal(a, b) else 1 for a, b in zip(got.xyz, ref))
+    print(f"[parity] stream micro {dist}: {got.n_count} streamlines, {int(got.npts.sum())} points, mismatching lines {nbad}")
+    assert nbad == 0
