@@ -3,8 +3,9 @@ same output order; one blocking call into libfibers_cuda.so (fibers_stream) plus
 
 Covers what has a deterministic answer -- orientation vectors, no local connection matrices, in the macroscopic and in
 the microscopy regime (voxel size <= 50 um: regime-dependent defaults and the box search of stream_micro_new_point!,
-src/stream.jl:84-95, :547-617).  `lcms` (random sampling from the connection matrix, :394-492) and 2-D orientation
-ANGLES as input (:145-172) are not on the GPU path and raise.  There is no CPU fallback.
+src/stream.jl:84-95, :547-617); 2-D orientation ANGLES (:145-172) are turned into in-plane vectors here, as the
+StreamWork constructor does.  `lcms` (random sampling from the connection matrix, :394-492) is not on the GPU path and
+raises.  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -72,10 +73,30 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     res = ovecs[0].header.get("volres") if isinstance(ovecs[0], MRI) else None
     domicro = res is not None and min(res) <= 0.05                   # microscopy regime (src/stream.jl:84)
     vols = []
+    thrudim = None
     for o in ovecs:
         v = np.asfortranarray(_vol(o), dtype=np.float32)
+        if v.ndim == 3 or (v.ndim == 4 and v.shape[3] == 1):
+            # 2-D orientation ANGLES (src/stream.jl:145-172): in-plane unit vectors (cos, sin); the through-plane axis is the one
+            # with the largest voxel size.  Done here, like the StreamWork constructor does it; the library only sees vectors.
+            ang = v.reshape(v.shape[:3], order="F")
+            r3 = res if res is not None else (1.0, 1.0, 1.0)
+            thrudim = int(np.argmax(r3))
+            s1, s2 = [d for d in range(3) if d != thrudim]
+            vec = np.zeros(ang.shape + (3,), np.float32, order="F")
+            eps = np.finfo(np.float32).eps
+            if -np.pi / 2 - eps <= ang.min() and ang.max() <= np.pi / 2 + eps:          # radians
+                vec[..., s1] = np.cos(ang); vec[..., s2] = np.sin(ang)
+            elif -90 <= ang.min() and ang.max() <= 90:                                  # degrees
+                vec[..., s1] = np.cos(np.deg2rad(ang.astype(np.float64))).astype(np.float32)
+                vec[..., s2] = np.sin(np.deg2rad(ang.astype(np.float64))).astype(np.float32)
+            else:
+                raise ValueError("Input orientations should be 3D vectors or angles in [-90, 90]")
+            if mask is None:                                                            # mask = any(x -> x != 0, vol) (:107-112)
+                vec[ang == 0] = 0
+            v = vec
         if v.ndim != 4 or v.shape[3] != 3:
-            raise _lib.FibersCudaError(1, "stream: orientation volumes must be [nx,ny,nz,3] vectors on the GPU path")
+            raise _lib.FibersCudaError(1, "stream: orientation volumes must be [nx,ny,nz,3] vectors or [nx,ny,nz] angles")
         vols.append(v)
     nx, ny, nz = vols[0].shape[:3]
     if any(v.shape[:3] != (nx, ny, nz) for v in vols):
@@ -108,7 +129,10 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     smooth = (0 if domicro else 0.2) if smooth_coeff is None else smooth_coeff
     msd = None; mcos = 0.0
     if domicro:
-        msd = (C.c_int32 * 3)(*([int(search_dist)] * 3))             # fill(Int(search_dist), 3) (:86)
+        sd3 = [int(search_dist)] * 3                                 # fill(Int(search_dist), 3) (:86)
+        if thrudim is not None:
+            sd3[thrudim] = 0                                         # 2-D data: no search through the plane (:153)
+        msd = (C.c_int32 * 3)(*sd3)
         mcos = float(np.float32(np.cos(np.deg2rad(np.float64(np.float32(search_ang))))))   # cosd(T(search_ang)) (:306)
     cos_thresh = np.float32(np.cos(np.deg2rad(np.float64(np.float32(ang)))))    # cosd(T(ang_thresh))
 

@@ -279,10 +279,26 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
   isnothing(lcms) || error("stream: local connection matrices are not on the GPU path")
   ovecs = isa(ovec, MRI) ? MRI[ovec] : ovec
   fs    = isa(f, MRI) ? MRI[f] : f
-  all(o -> size(o.vol, 4) == 3, ovecs) || error("stream: orientation volumes must be [nx,ny,nz,3] vectors on the GPU path")
   nx, ny, nz = size(ovecs[1].vol)[1:3]
   domicro = (minimum(ovecs[1].volres) <= 0.05)                    # src/stream.jl:84
   micro_search_dist = domicro ? fill(Int32(search_dist), 3) : Int32[]
+  # 2-D orientation angles -> in-plane unit vectors, exactly as the StreamWork constructor does (src/stream.jl:145-172)
+  function as_vectors(o::MRI)
+    size(o.vol, 4) == 3 && return Array{Float32,4}(o.vol)
+    size(o.vol, 4) == 1 || error("Input orientations should be 3D vectors or angles ∊ [-90, 90]")
+    thrudim = argmax(o.volres); strdims = setdiff(1:3, thrudim)
+    domicro && (micro_search_dist[thrudim] = 0)
+    a = Float32.(o.vol[:,:,:,1]); v = zeros(Float32, nx, ny, nz, 3)
+    if -π/2-eps(Float32) <= minimum(a) && maximum(a) <= π/2+eps(Float32)
+      v[:,:,:,strdims[1]] .= cos.(a);  v[:,:,:,strdims[2]] .= sin.(a)
+    elseif -90 <= minimum(a) && maximum(a) <= 90
+      v[:,:,:,strdims[1]] .= cosd.(a); v[:,:,:,strdims[2]] .= sind.(a)
+    else
+      error("Input orientations should be 3D vectors or angles ∊ [-90, 90]")
+    end
+    isnothing(mask) && (v .*= (a .!= 0))                          # the mask would be any(x -> x != 0, vol) (:107-112)
+    return v
+  end
   isnothing(nsub) && (nsub = domicro ? 0 : 3); isnothing(ang_thresh) && (ang_thresh = domicro ? 20 : 45)
   isnothing(step_size) && (step_size = domicro ? 1 : .5); isnothing(smooth_coeff) && (smooth_coeff = domicro ? 0 : .2)
   if !isnothing(seed) && !isnothing(mask) && size(seed.vol) != size(mask.vol)
@@ -290,7 +306,7 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
   end
   sublist = nsub > 0 ? [Float32.(rand(Uniform(-.5+eps(), .5-eps()), 3)) for isub in 1:nsub] : [zeros(Float32, 3)]
   sub  = reduce(hcat, sublist)                                   # [3, nsub] column-major = [nsub][3] for the C side
-  vols = [Array{Float32,4}(o.vol) for o in ovecs]
+  vols = [as_vectors(o) for o in ovecs]
   fvol = isnothing(fs) ? nothing : [Array{Float32,3}(x.vol[:,:,:,1]) for x in fs]
   favol = isnothing(fa) ? nothing : Array{Float32,3}(fa.vol[:,:,:,1])
   m  = isnothing(mask) ? nothing : UInt8.(mask.vol[:,:,:,1] .> 0)

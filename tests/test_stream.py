@@ -149,8 +149,8 @@ def test_stream_rejects_what_is_not_on_the_gpu_path():
     v = straight_field((4, 4, 4))
     with pytest.raises(Fb.FibersCudaError):
         Fb.stream(Fb.MRI(v), lcms=Fb.MRI(np.zeros((4, 4, 4, 10), F)))
-    with pytest.raises(Fb.FibersCudaError):
-        Fb.stream(Fb.MRI(np.zeros((4, 4, 4), F)))
+    with pytest.raises(ValueError):
+        Fb.stream(Fb.MRI(np.full((4, 4, 4), 100.0, F)))            # neither vectors nor angles in [-90, 90]
 
 
 @pytest.mark.gpu
@@ -238,3 +238,20 @@ def test_stream_gpu_micro_regime_bit_exact(dist):
     nbad = sum(0 if np.array_equal(a, b) else 1 for a, b in zip(got.xyz, ref))
     print(f"[parity] stream micro {dist}: {got.n_count} streamlines, {int(got.npts.sum())} points, mismatching lines {nbad}")
     assert nbad == 0
+
+
+@pytest.mark.gpu
+def test_stream_gpu_angle_input_micro():
+    """2-D orientation angles (radians) in the microscopy regime: the wrapper builds in-plane vectors (src/stream.jl:145-172), the
+    search box is flat along the through-plane axis (:153); equals the oracle on those vectors."""
+    import fibers_jl_b200 as Fb
+    shape = (30, 24, 2)
+    g = np.random.default_rng(5)
+    xs, ys = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij")
+    ang = (0.9 * np.sin(xs / 7.0) * np.cos(ys / 5.0))[..., None] + 0.05 * g.standard_normal(shape)
+    ang = np.asfortranarray(np.clip(ang, -1.5, 1.5).astype(F))
+    got = Fb.stream(Fb.MRI(ang, volres=(0.01, 0.01, 0.05)), search_dist=3, search_ang=30)
+    vec = np.zeros(shape + (3,), F, order="F"); vec[..., 0] = np.cos(ang); vec[..., 1] = np.sin(ang); vec[ang == 0] = 0
+    ref = SO.stream([vec], [np.zeros(3, F)], step_size=1.0, smooth_coeff=0.0, cosang_thresh=F(np.cos(np.deg2rad(np.float64(F(20))))),
+                    micro_search_dist=(3, 3, 0), micro_search_cosang=F(np.cos(np.deg2rad(np.float64(F(30))))), len_max=30)
+    assert got.n_count == len(ref) > 100 and all(np.array_equal(a, b) for a, b in zip(got.xyz, ref))
