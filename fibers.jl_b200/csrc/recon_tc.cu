@@ -52,6 +52,9 @@ constexpr int W_MMA = 1, W_DWI = 2, W_CONV0 = 3, W_EPI0 = W_CONV0 + N_CONV;   //
 constexpr int TC_THREADS = (W_EPI0 + N_EPI) * 32;
 constexpr int N_CPART = N_EPI / 4;   // column parts in the TMEM drain
 constexpr int NSTAGE = 8;            // B ring, K16 sub-tiles (hi rows + lo rows): maximum depth; the launch picks what fits (p.nstage)
+constexpr int DBOXW_SPLIT = 132;     // TMA mode, rows not 16-byte aligned: voxels per box row (128 + the <= 3 voxels the map base was rounded down by)
+__host__ __device__ constexpr int dwi_box_bytes(int nmap) { return nmap > 1 ? ((16 / nmap * DBOXW_SPLIT * 4 + 127) / 128) * 128 : 16 * 128 * 4; }   // shared-memory slot of one box
+__host__ __device__ constexpr int dwi_stage_bytes(int nmap) { return (nmap > 1 ? nmap : 1) * dwi_box_bytes(nmap); }                                   // one ring stage: 16 volumes x 128 voxels
 constexpr int DSTAGE = 3;            // cp.async mode: raw DWI ring of the converters, K32 chunks of 128 voxels (16 KB each)
 constexpr int TSTAGE = 8;            // TMA mode: raw DWI ring, K16 boxes of 128 voxels (8 KB each), filled by the DWI producer warp: maximum depth (p.tstage)
 constexpr int OBOX_BYTES = 16 * 128 * 4;   // TMA mode: ODF staging box = 16 vertex rows x 128 voxels fp32, one TMA store each
@@ -93,11 +96,23 @@ struct TcParams {
     int plain;                   // 1: rows are stored only (DSI pdf rows): no peak search, no statistics
     int cvol; float dscale;      // DSI: every output row is divided by den = dscale * max(s[cvol], 0)  (cvol < 0: none)
     int dwi_vec;                 // DWI staging copies: 2 = 16 bytes (base 16-byte aligned, pitch % 4 == 0), 1 = 8 bytes, 0 = 4 bytes
+    int dshift[4];               // TMA mode, split maps: voxel coordinate of voxel 0 in DWI map r (its base is rounded down to 16 bytes)
     uint32_t conv_sleep, prod_sleep;   // back-off (ns) of the converters' a_empty wait and of the producers' ring waits
     int cand_cap;                // capacity of the candidate list (<= CAND_CAP; tests shrink it to force the fall-back)
     long long* trace;            // optional per-role clock trace of cluster 0 / CTA 0 (debug; FIBERS_TC_TRACE)
     uint32_t trace_skip;         // first traced tile iteration
 };
+
+// DWI slab maps of one launch.  TMA wants a 16-byte aligned base, row strides that are multiples of 16 bytes AND box
+// coordinates whose byte offset along the row is a multiple of 16 (measured on B200: an fp32 box at voxel coordinate
+// 4n + 1 or 4n + 2 raises cudaErrorIllegalInstruction, 4n + 4 is fine).  A slab whose frame pitch is the bare voxel
+// count (what a device-resident caller of the reference layout has: rows 8- or 4-byte aligned) is therefore described
+// by kTma = 2 or 4 maps: map r holds the volumes k = r (mod kTma), so its row stride kTma * pitch is a multiple of 16
+// bytes again; its base is the address of volume r rounded DOWN to 16 bytes, and its boxes are 132 voxels wide and
+// start at the tile's (aligned) voxel coordinate: the tile's 128 voxels sit TcParams::dshift[r] = 0..3 voxels into
+// each row of the box.  The boxes of the kTma maps land in one ring stage as [r][16 / kTma][132]; the converters read
+// the rows in volume order.
+struct DwiMaps { CUtensorMap m[4]; };
 
 // One launch of the kernel covers at most 384 matrix rows (TMEM columns 0..383; the A ring sits above).  GQI: a single pass (the ODF
 // rows).  DSI: the ODF rows, then the pdf rows in passes of <= 336 (plain mode).
@@ -300,10 +315,14 @@ __device__ __forceinline__ bool elect_one() {          // one lane of a converge
 // (tools/store_probe.cu: 172 KB of ODF per tile = 5.4 k cycles of that port); needs 16-byte aligned slab / output
 // rows.  !kTma: cp.async staging + direct stores (any alignment).
 // kTrace: per-role clock trace of cluster 0 (FIBERS_TC_TRACE); compiled out of the production instantiations.
-template <bool kTma, bool kTrace>
+template <int kTma, bool kTrace>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ NbrOffTable nbt,
-                const __grid_constant__ CUtensorMap tmapD, const __grid_constant__ CUtensorMap tmapO) {
+                const __grid_constant__ DwiMaps tmapD, const __grid_constant__ CUtensorMap tmapO) {
+    constexpr int NMAP = kTma ? kTma : 1;
+    constexpr int DROWS = 16 / NMAP;                                      // rows of one DWI box (NMAP boxes per ring stage)
+    constexpr int DBOXW = kTma > 1 ? DBOXW_SPLIT : VOX_CTA;               // voxels per box row
+    constexpr uint32_t DSLOT = dwi_box_bytes(NMAP), DSTG = dwi_stage_bytes(NMAP);
     const uint32_t* const c_nbr_off = nbt.off;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // the warp index is rebuilt from warp votes so that the compiler can prove it warp-uniform (uniform registers,
@@ -338,7 +357,7 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
     float* s_mean = s_min + 2 * N_CPART * VOX_CTA;                        // [2][128] mean ODF per voxel (from the extra matrix row)
     // raw DWI ring (128-byte aligned: TMA destination), then (TMA mode) the ODF staging boxes
     float* s_dwi = (float*)(((uintptr_t)(s_mean + 2 * VOX_CTA) + 127) & ~(uintptr_t)127);   // cp.async: [DSTAGE][32][128]; TMA: [TSTAGE][16][128]
-    uint8_t* s_obox = (uint8_t*)(s_dwi + (kTma ? p.tstage * 16 : DSTAGE * 32) * VOX_CTA);   // [N_CPART][obuf][16][128] fp32
+    uint8_t* s_obox = (uint8_t*)s_dwi + (kTma ? (size_t)p.tstage * DSTG : (size_t)DSTAGE * 32 * VOX_CTA * 4);   // [N_CPART][obuf][16][128] fp32
     uint4* s_nbr = (uint4*)(s_obox + (kTma ? (size_t)N_CPART * p.obuf * OBOX_BYTES : 0));  // [M] 8 x uint16 neighbour ids per vertex
     float* s_vert = (float*)(s_nbr + Mk);                                 // [M][3] first-half vertices (peak vectors); padded to 4 floats
     uint64_t* bars = (uint64_t*)(s_vert + ((3 * Mk + 3) & ~3));
@@ -481,12 +500,17 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
                     if (elect_one()) {
                         if (p.l2pf > 0 && ti_ + p.l2pf * ncluster < ntl) {     // the same box of a later tile of this cluster -> L2
                             const int t2 = ident ? ti_ + p.l2pf * ncluster : __ldg(p.tile_list + ti_ + p.l2pf * ncluster);
-                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                                         ::"l"(&tmapD), "r"(t2 * 256 + (int)rank * VOX_CTA), "r"(c * 16) : "memory");
+#pragma unroll
+                            for (int r = 0; r < kTma; ++r)
+                                asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                                             ::"l"(&tmapD.m[r]), "r"(t2 * 256 + (int)rank * VOX_CTA), "r"(c * DROWS) : "memory");
                         }
-                        mbar_expect_tx(&w_full[s], 16 * VOX_CTA * 4);
-                        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                     ::"r"(smem_u32(s_dwi + s * 16 * VOX_CTA)), "l"(&tmapD), "r"(vox0), "r"(c * 16), "r"(smem_u32(&w_full[s])) : "memory");
+                        mbar_expect_tx(&w_full[s], 16 * DBOXW * 4);
+#pragma unroll
+                        for (int r = 0; r < kTma; ++r)
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(smem_u32(s_dwi) + s * DSTG + r * DSLOT), "l"(&tmapD.m[r]), "r"(vox0), "r"(c * DROWS),
+                                           "r"(smem_u32(&w_full[s])) : "memory");
                     }
                     __syncwarp();
                     if (++s == p.tstage) { s = 0; ph ^= 1u; }
@@ -508,6 +532,9 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
         constexpr int PF = DSTAGE - 1;
         constexpr uint32_t STAGE_B = 32 * VOX_CTA * 4;
         const int vec = p.dwi_vec;
+        uint32_t vb[NMAP];                                              // TMA mode: this voxel's column in the box of map r
+#pragma unroll
+        for (int r = 0; r < NMAP; ++r) vb[r] = sd0 + r * DSLOT + (vl + (kTma > 1 ? p.dshift[r] : 0)) * 4;
         // prefetch cursor
         int p_ti = cluster_id, p_c = 0; uint32_t p_g = 0;
         int64_t p_vox0 = 0;
@@ -594,9 +621,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         mbar_wait<20>(&w_full[ws + h], wph);
-                        const uint32_t sbase = sd0 + (ws + h) * (16 * VOX_CTA * 4) + vl * 4;
+                        const uint32_t so = (ws + h) * DSTG;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[16 * h + j]) : "r"(sbase + j * (VOX_CTA * 4)));
+                        for (int j = 0; j < 16; ++j)                    // volume j of the stage: row j / kTma of the box of map j % kTma
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x[16 * h + j]) : "r"(vb[j % NMAP] + so + (j / NMAP) * (DBOXW * 4)));
                     }
                 } else {
                     asm volatile("cp.async.wait_group %0;" ::"n"(PF - 1) : "memory");   // this thread's copies of chunk g32 have landed
@@ -1079,10 +1107,10 @@ recon_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapB, con
 }
 
 // dynamic shared memory of one instantiation (carve-up of recon_tc_kernel; M = 0 for plain passes)
-size_t tc_smem_bytes(bool tma, int M, int Nh, int nstage, int tstage, int obuf) {
+size_t tc_smem_bytes(int tma, int M, int Nh, int nstage, int tstage, int obuf) {     // tma: 0 = cp.async staging, else the number of DWI maps
     size_t b = (size_t)nstage * 2 * Nh * 32 + (size_t)(M + 8) * KEY_ROW + 2 * (3 * VOX_CTA * 8 + (size_t)CAND_CAP * 4 + (N_CPART + 1) * VOX_CTA * 4);
     b = (b + 127) & ~(size_t)127;
-    b += tma ? (size_t)tstage * 16 * VOX_CTA * 4 + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
+    b += tma ? (size_t)tstage * dwi_stage_bytes(tma) + (size_t)N_CPART * obuf * OBOX_BYTES : (size_t)DSTAGE * 32 * VOX_CTA * 4;
     b += (size_t)M * 16 + (size_t)((3 * M + 3) & ~3) * 4 + (2 * NSTAGE + 2 * ASLOT + 2 + 2 * TSTAGE) * 8 + 16;
     return b + 1024 + 64;
 }
@@ -1148,7 +1176,7 @@ int tc_plan_init(Plan* p) {
         const int Nh = (ps.N1 + ps.N2) / 2, N1h = ps.N1 / 2, N2h = ps.N2 / 2;
         // smallest configuration of either instantiation must fit (the launch picks the ring depths)
         const int Mk = ps.plain ? 0 : ps.rows;
-        smem = std::max(smem, std::max(tc_smem_bytes(true, Mk, Nh, 2, 4, 0), tc_smem_bytes(false, Mk, Nh, 2, 0, 0)));
+        smem = std::max(smem, std::max(tc_smem_bytes(4, Mk, Nh, 2, 4, 0), tc_smem_bytes(0, Mk, Nh, 2, 0, 0)));
         // Split operand as a ready-made shared-memory image: [rank][K32 chunk][K16 sub-tile][hi | lo][row][16 halves],
         // rows in the order (blk1 rows 0..N1h, blk2 rows 0..N2h) of that rank, with the SWIZZLE_32B pattern the
         // tcgen05 descriptors expect already applied (16-byte chunk ^= bit 2 of the row).  A stage is then ONE
@@ -1209,11 +1237,15 @@ int raise_smem_limit(int device, bool tma, size_t smem) {
     std::lock_guard<std::mutex> lk(g_smem_mu);
     size_t& cur = g_smem_limit[tma ? 1 : 0][device & 63];
     if (smem <= cur) return 0;
-    cudaError_t e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(recon_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = tma ? cudaFuncSetAttribute(recon_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                : cudaFuncSetAttribute(recon_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int sm = (int)smem;
+    cudaError_t e = cudaSuccess;
+    auto raise = [&](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); };
+    if (tma) {
+        raise((const void*)recon_tc_kernel<1, false>); raise((const void*)recon_tc_kernel<1, true>);
+        raise((const void*)recon_tc_kernel<2, false>); raise((const void*)recon_tc_kernel<4, false>);
+    } else {
+        raise((const void*)recon_tc_kernel<0, false>); raise((const void*)recon_tc_kernel<0, true>);
+    }
     if (e != cudaSuccess) { set_error("tensor-core path: cannot raise the shared-memory limit"); cudaGetLastError(); return 1; }
     cur = smem;
     return 0;
@@ -1278,9 +1310,13 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.fix_cap = (int)(2 * ntile64);
         tp.ntiles = (int)((a.nvox + 255) / 256);
         tp.nbw = st->nbw;
-        // TMA instantiation when the slab rows and the output rows are 16-byte aligned (always true for the host entry points)
-        const bool tma = getenv("FIBERS_TC_NO_TMA") == nullptr && (uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0 &&
-                         (uintptr_t)out % 16 == 0 && a.out_pitch % 4 == 0 && a.nvox < (1ll << 31) - 512;
+        // TMA instantiation: the DWI slab through 1, 2 or 4 maps (16-, 8-, 4-byte aligned rows: DwiMaps); the output map (staged
+        // ODF stores, FIBERS_TC_OBUF) needs 16-byte aligned output rows, the default direct stores do not
+        int nmap = ((uintptr_t)a.dwi % 16 == 0 && a.dwi_pitch % 4 == 0) ? 1 : a.dwi_pitch % 2 == 0 ? 2 : 4;
+        if (const char* e = getenv("FIBERS_TC_DBG_NMAP")) nmap = std::max(nmap, atoi(e));      // (experiments: more maps than the pitch needs)
+        const bool out_al = (uintptr_t)out % 16 == 0 && a.out_pitch % 4 == 0;
+        const bool tma = getenv("FIBERS_TC_NO_TMA") == nullptr && (uintptr_t)a.dwi % 4 == 0 && p->nvol >= nmap && a.nvox < (1ll << 31) - 512 &&
+                         (nmap == 1 || getenv("FIBERS_TC_NO_SPLIT_TMA") == nullptr);
         // ring depths: the deepest B ring (L2 latency), a DWI ring that covers L2 latency (HBM latency is covered by the L2
         // prefetch one tile ahead) and one ODF staging box per epilogue warp, shrunk until the tile fits in shared memory
         const int Mk = ps.plain ? 0 : ps.rows, Nhh = (ps.N1 + ps.N2) / 2;
@@ -1291,11 +1327,12 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         tp.l2pf = std::max(0, envi("FIBERS_TC_L2PF", 0));
         tp.abl = envi("FIBERS_TC_ABLATE", 0);
         if (!tma) { tp.tstage = 0; tp.obuf = 0; tp.l2pf = 0; }
-        while (tc_smem_bytes(tma, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf) > (size_t)st->dev_smem) {
+        if (!out_al) tp.obuf = 0;
+        while (tc_smem_bytes(tma ? nmap : 0, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf) > (size_t)st->dev_smem) {
             if (tp.nstage > 4) --tp.nstage; else if (tp.obuf > 0) --tp.obuf; else if (tp.tstage > 4) tp.tstage -= 2; else if (tp.nstage > 2) --tp.nstage;
             else return fail(FIBERS_ERR_ARG, "tensor-core path: tile does not fit in shared memory");
         }
-        const size_t smem_launch = tc_smem_bytes(tma, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf);
+        const size_t smem_launch = tc_smem_bytes(tma ? nmap : 0, Mk, Nhh, tp.nstage, tp.tstage, tp.obuf);
         if (getenv("FIBERS_TC_VERBOSE")) {
             static std::atomic<int> once{0};
             if (once.fetch_add(1) < 4) fprintf(stderr, "[fibers tc] pass %zu: tma %d, B stages %d, DWI stages %d, ODF boxes %d, L2 prefetch %d, smem %zu\n",
@@ -1314,22 +1351,35 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         if (tma) {
             // per-launch tensor maps: the DWI slab [K][nvox] fp32 (row pitch dwi_pitch) in K16 x 128-voxel boxes, the output
             // rows [rows][nvox] fp32 (row pitch out_pitch) in 16 x 32 boxes; out-of-range voxels / rows are zero-filled / clipped
-            CUtensorMap mD, mO;
+            DwiMaps mD; CUtensorMap mO;
             cuuint32_t estr[2] = {1, 1};
-            cuuint64_t dD[2] = {(cuuint64_t)a.nvox, (cuuint64_t)p->nvol}, sD[1] = {(cuuint64_t)a.dwi_pitch * 4};
-            cuuint32_t bD[2] = {VOX_CTA, 16};
+            cuuint64_t sD[1] = {(cuuint64_t)a.dwi_pitch * 4 * nmap};
+            cuuint32_t bD[2] = {(cuuint32_t)(nmap > 1 ? DBOXW_SPLIT : VOX_CTA), (cuuint32_t)(16 / nmap)};
             cuuint64_t dO[2] = {(cuuint64_t)a.nvox, (cuuint64_t)ps.rows}, sO[1] = {(cuuint64_t)a.out_pitch * 4};
             cuuint32_t bO[2] = {32, 16};
-            if (((EncodeFn)st->encode)(&mD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.dwi, dD, sD, bD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
-                ((EncodeFn)st->encode)(&mO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)out, dO, sO, bO, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return fail(FIBERS_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed for the slab / output map");
-            if (tp.trace) recon_tc_kernel<true, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
-            else recon_tc_kernel<true, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            for (int r = 0; r < 4; ++r) {
+                const int rr = r < nmap ? r : 0;                            // (unused slots repeat map 0)
+                const uintptr_t row = (uintptr_t)(a.dwi + (int64_t)rr * a.dwi_pitch);
+                const int shift = (int)(row % 16) / 4;
+                tp.dshift[r] = shift;
+                cuuint64_t dD[2] = {(cuuint64_t)a.nvox + shift, (cuuint64_t)((p->nvol - rr + nmap - 1) / nmap)};
+                if (((EncodeFn)st->encode)(&mD.m[r], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)(row - shift * 4), dD, sD, bD, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return fail(FIBERS_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed for the slab map");
+            }
+            if (!out_al) mO = mD.m[0];                                      // never dereferenced: no staged stores
+            else if (((EncodeFn)st->encode)(&mO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)out, dO, sO, bO, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail(FIBERS_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed for the output map");
+            if (tp.trace && nmap == 1) recon_tc_kernel<1, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            else if (nmap == 1) recon_tc_kernel<1, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            else if (nmap == 2) recon_tc_kernel<2, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
+            else recon_tc_kernel<4, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, mO);
         } else {
-            if (tp.trace) recon_tc_kernel<false, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
-            else recon_tc_kernel<false, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, ps.tmap, ps.tmap);
+            DwiMaps mD;
+            for (int r = 0; r < 4; ++r) mD.m[r] = ps.tmap;                  // never dereferenced
+            if (tp.trace) recon_tc_kernel<0, true><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, ps.tmap);
+            else recon_tc_kernel<0, false><<<2 * nclusters, TC_THREADS, smem_launch, stream>>>(tp, ps.tmap, st->nbr_off, mD, ps.tmap);
         }
         count_launch(1);
         FB_CUDA(cudaGetLastError());

@@ -152,8 +152,11 @@ def test_full_volume_dti_invariants(env):
 
 
 def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
-    """The tensor-core kernel stages the DWI slab with 16-byte copies when the rows are 16-byte aligned and with
-    8- or 4-byte copies otherwise; all three must give the same bits.  Odd voxel count, partial last tile, ragged mask."""
+    """The tensor-core kernel takes the DWI slab through one TMA map when the rows are 16-byte aligned, through 2 or 4
+    maps with shifted bases when they are 8- or 4-byte aligned (pitch = bare voxel count, misaligned base pointer), and
+    through cp.async copies when told to (FIBERS_TC_NO_SPLIT_TMA); output rows need no alignment either.  All give the
+    same bits.  Odd voxel count, partial last tile, ragged mask."""
+    import os
     import torch
     import bench
     import fibers_jl_b200 as F
@@ -178,8 +181,18 @@ def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
     try:
         plan = D.Plan("gqi", 0, bval, bvec, F.sphere_642, 1.25)
         assert plan.kernel == "tc"
-        for dwi, dp in ((dwi_al, pitch_al), (dwi_un, pitch_un), (dwi_8, pitch_8)):
-            opitch = pitch_al
+        # (rows, pitch, output pitch, environment): base pointers 4 / 12 bytes past a 16-byte boundary, odd output pitch
+        dwi_o1 = torch.zeros(bval.shape[0] * pitch_al + 4, dtype=torch.float32, device=dev)
+        dwi_o1[1:1 + bval.shape[0] * pitch_al].view(bval.shape[0], pitch_al)[:, :nvox] = dwi_al[:, :nvox]
+        dwi_o3 = torch.zeros(bval.shape[0] * pitch_un + 4, dtype=torch.float32, device=dev)
+        dwi_o3[3:3 + bval.shape[0] * pitch_un].view(bval.shape[0], pitch_un)[:, :nvox] = dwi_al[:, :nvox]
+        cases = [(dwi_al, pitch_al, pitch_al, {}), (dwi_un, pitch_un, pitch_al, {}), (dwi_8, pitch_8, pitch_al, {}),
+                 (dwi_o1[1:], pitch_al, pitch_al, {}), (dwi_o3[3:], pitch_un, pitch_al, {}), (dwi_8, pitch_8, nvox + 2, {}),
+                 (dwi_un, pitch_un, pitch_al, {"FIBERS_TC_NO_SPLIT_TMA": "1"}), (dwi_8, pitch_8, pitch_al, {"FIBERS_TC_NO_SPLIT_TMA": "1"}),
+                 (dwi_al, pitch_al, nvox + 2, {"FIBERS_TC_NO_TMA": "1"})]
+        for dwi, dp, opitch, env in cases:
+            assert dwi.data_ptr() % 4 == 0
+            os.environ.update(env)
             odf = torch.full((321, opitch), 7.0, dtype=torch.float32, device=dev)
             peak = [torch.full((3, opitch), 7.0, dtype=torch.float32, device=dev) for _ in range(3)]
             qa = [torch.full((opitch,), 7.0, dtype=torch.float32, device=dev) for _ in range(3)]
@@ -188,9 +201,13 @@ def test_aligned_and_unaligned_dwi_pitch_agree_bit_for_bit():
             plan.recon(dwi.data_ptr(), dp, mask.data_ptr(), nvox, opitch, odf.data_ptr(), [p.data_ptr() for p in peak],
                        [q.data_ptr() for q in qa], stats.data_ptr(), d_peak_idx=idx.data_ptr(), finalize=True)
             torch.cuda.synchronize()
+            for k in env:
+                del os.environ[k]
             res.append((odf[:, :nvox].clone(), [p[:, :nvox].clone() for p in peak], [q[:nvox].clone() for q in qa],
                         idx[:, :nvox].clone(), int(stats[0].item())))
     finally:
+        for k in ("FIBERS_TC_NO_SPLIT_TMA", "FIBERS_TC_NO_TMA"):
+            os.environ.pop(k, None)
         D.set_kernel("auto")
     a = res[0]
     for b in res[1:]:

@@ -56,10 +56,11 @@ def run_dti(shape, bval, bvec, tag):
     report(f"adc_fit {tag}", nvox, ms, 4 * N + 9, 5 * N)
 
 
-def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642, aligned=True):
+def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642, aligned=True, dpitch=None, opitch=None, env=None):
     nvox = int(np.prod(shape)); N = bval.shape[0]; M = odf_dirs.nvert
-    pitch = (nvox + 63) // 64 * 64
-    dpitch = pitch if aligned else nvox                      # frame pitch of the DWI slab (16-byte aligned rows or not)
+    pitch = opitch or (nvox + 63) // 64 * 64
+    dpitch = dpitch or (pitch if aligned else nvox)          # frame pitch of the DWI slab (16-byte aligned rows or not)
+    os.environ.update(env or {})
     dwi = synth(nvox, bval, bvec, 5, dpitch)
     mask = torch.ones(nvox, dtype=torch.uint8, device=dev)
     odf = torch.empty((M, pitch), dtype=torch.float32, device=dev)
@@ -73,13 +74,25 @@ def run_recon(kind, shape, bval, bvec, kernel, tag, odf_dirs=F.sphere_642, align
     fn = lambda: plan.recon(dwi.data_ptr(), dpitch, mask.data_ptr(), nvox, pitch, odf.data_ptr(), [p.data_ptr() for p in peak],
                             [q.data_ptr() for q in qa], stats.data_ptr(), d_pdf=pdf.data_ptr() if pdf is not None else 0, finalize=True)
     ms = timeit(fn, steps=5 if kind == "dsi" else 10)
+    for k in (env or {}):
+        del os.environ[k]
     if kind == "gqi":
         report(f"gqi_rec {tag} [{plan.kernel}]", nvox, ms, 4 * N + 4 * M + 49, 2 * N * M)
     else:
         report(f"dsi_rec {tag} [{plan.kernel}]", nvox, ms, 8 * N + 4 * M + 49, 2 * N * (M + N), "tensor-bound in matrix form (3 kernel passes: odf rows, 2 x pdf rows)")
 
 
-ONLY = os.environ.get("BENCH_KERNELS_ONLY", "")          # "dti": the DTI / ADC rows only (A/B of kernel variants)
+ONLY = os.environ.get("BENCH_KERNELS_ONLY", "")          # "dti": the DTI / ADC rows only (A/B of kernel variants); "pitch": the frame-pitch rows
+if ONLY == "pitch":
+    b2, g2 = bench.make_tables()
+    nv = 145 * 174 * 145
+    for rep in range(2):
+        run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, rows 16-byte aligned (1 map)")
+        run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI pitch = nvox: rows 8-byte aligned (2 maps)", dpitch=nv)
+        run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI pitch = nvox + 1: rows 4-byte aligned (4 maps)", dpitch=nv + 1)
+        run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI and output pitch = nvox (the reference's own array layout)", dpitch=nv, opitch=nv)
+        run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI pitch = nvox, cp.async staging (FIBERS_TC_NO_SPLIT_TMA)", dpitch=nv, env={"FIBERS_TC_NO_SPLIT_TMA": "1"})
+    sys.exit(0)
 b1, g1 = phantom.shells_table(1, [(1000.0, 30)])
 run_dti((64, 64, 40), b1, g1, "cfg1 64x64x40x31")
 b2, g2 = bench.make_tables()
@@ -87,7 +100,8 @@ run_dti((145, 174, 145), b2, g2, "cfg4 145x174x145x288")
 if ONLY == "dti":
     sys.exit(0)
 run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288")
-run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288, DWI pitch = nvox (rows not 16-byte aligned)", aligned=False)
+run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288, DWI pitch = nvox (rows 8-byte aligned: 2 TMA maps)", aligned=False)
+run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2 145x174x145x288, DWI and output pitch = nvox (the reference's own array layout)", dpitch=145 * 174 * 145, opitch=145 * 174 * 145)
 run_recon("gqi", (145, 174, 145), b2, g2, "simt", "cfg2 145x174x145x288")
 b5, g5 = phantom.shells_table(8, [(4000.0, 120)])
 run_recon("gqi", (400, 400, 38), b5, g5, "tc", "cfg5 slab 400x400x38x128 (1/8 of 400x400x300)")
