@@ -66,6 +66,8 @@ SIGNATURES = {
     "fibers_mri_read_data": (_i, [C.c_char_p, _p, _p, _i64]),
     "fibers_mri_write": (_i, [C.c_char_p, _p, _i, _p, _p, _p, _f, _f, _f, _f, _f, _f, _i]),
     "fibers_trk_write": (_i, [C.c_char_p, _p, _p, _p, _i64, _p, _p]),
+    "fibers_trk_read_info": (_i, [C.c_char_p, _p]),
+    "fibers_trk_read_data": (_i, [C.c_char_p, _p, _p, _p, _p, _p]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),
     "fibers_cuda_host_unregister": (_i, [_p]),
     "fibers_dti_plan_create": (_i, [_p, _i, _i, _p, _p]),

@@ -453,3 +453,72 @@ extern "C" int fibers_trk_write(const char* path, const int32_t* volsize, const 
     if (!out.close()) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
     return 0;
 }
+
+// trk_read (src/trk.jl:358-425): header fields + streamlines; points come back as xyz ./ voxel_size .- .5 (0-based voxel
+// coordinates, Float32 arithmetic like the reference's broadcast over Vector{Float32}), scalars and properties as stored.
+namespace {
+bool trk_header(FILE* f, fibers_trk_info* info) {
+    uint8_t h[1000];
+    if (fread(h, 1, 1000, f) != 1000) return false;
+    memset(info, 0, sizeof(*info));
+    int16_t d[3]; memcpy(d, h + 6, 6);
+    for (int i = 0; i < 3; ++i) info->dim[i] = d[i];
+    memcpy(info->voxel_size, h + 12, 12); memcpy(info->origin, h + 24, 12);
+    int16_t ns, np; memcpy(&ns, h + 36, 2); memcpy(&np, h + 238, 2);
+    info->n_scalars = ns; info->n_properties = np;
+    memcpy(info->vox_to_ras, h + 440, 64);                        // row by row (the reference transposes what it reads, :385)
+    memcpy(info->voxel_order, h + 948, 4); memcpy(info->voxel_order_original, h + 952, 4);
+    memcpy(info->image_orientation_patient, h + 956, 24);
+    memcpy(&info->n_count, h + 988, 4); memcpy(&info->version, h + 992, 4); memcpy(&info->hdr_size, h + 996, 4);
+    return memcmp(h, "TRACK", 5) == 0 && info->n_scalars >= 0 && info->n_properties >= 0 && info->n_count >= 0;
+}
+}  // namespace
+
+extern "C" int fibers_trk_read_info(const char* path, fibers_trk_info* info) {
+    if (!path || !info) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(FIBERS_ERR_ARG, std::string("Could not open ") + path + " for reading");
+    bool ok = trk_header(f, info);
+    int64_t total = 0;
+    for (int32_t i = 0; ok && i < info->n_count; ++i) {          // one pass over the point counts
+        int32_t n;
+        ok = fread(&n, 4, 1, f) == 1 && n >= 0 &&
+             fseek(f, (long)(((int64_t)n * (3 + info->n_scalars) + info->n_properties) * 4), SEEK_CUR) == 0;
+        total += ok ? n : 0;
+    }
+    fclose(f);
+    if (!ok) return fail(FIBERS_ERR_ARG, std::string("Not a readable .trk file: ") + path);
+    info->total_points = total;
+    return 0;
+}
+
+extern "C" int fibers_trk_read_data(const char* path, const fibers_trk_info* info, int32_t* npts, float* xyz, float* scalars, float* properties) {
+    if (!path || !info || (info->n_count > 0 && (!npts || !xyz))) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    if ((info->n_scalars > 0 && !scalars) || (info->n_properties > 0 && !properties)) return fail(FIBERS_ERR_ARG, "NULL scalars / properties");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(FIBERS_ERR_ARG, std::string("Could not open ") + path + " for reading");
+    fibers_trk_info h2;
+    bool ok = trk_header(f, &h2) && h2.n_count == info->n_count && h2.n_scalars == info->n_scalars && h2.n_properties == info->n_properties;
+    const int ns = info->n_scalars, np = info->n_properties;
+    std::vector<float> buf;
+    int64_t p0 = 0;
+    for (int32_t i = 0; ok && i < info->n_count; ++i) {
+        int32_t n;
+        ok = fread(&n, 4, 1, f) == 1 && n >= 0 && p0 + n <= info->total_points;
+        if (!ok) break;
+        npts[i] = n;
+        buf.resize((size_t)n * (3 + ns) + np);
+        ok = buf.empty() || fread(buf.data(), 4, buf.size(), f) == buf.size();
+        if (!ok) break;
+        for (int32_t k = 0; k < n; ++k) {
+            const float* src = buf.data() + (size_t)k * (3 + ns);
+            for (int c = 0; c < 3; ++c) xyz[3 * (p0 + k) + c] = src[c] / info->voxel_size[c] - 0.5f;
+            for (int c = 0; c < ns; ++c) scalars[(size_t)ns * (p0 + k) + c] = src[3 + c];
+        }
+        for (int c = 0; c < np; ++c) properties[(size_t)np * i + c] = buf[(size_t)n * (3 + ns) + c];
+        p0 += n;
+    }
+    fclose(f);
+    if (!ok || p0 != info->total_points) return fail(FIBERS_ERR_ARG, std::string("Problem reading ") + path);
+    return 0;
+}

@@ -46,7 +46,7 @@ class Plan:
         self._h = h
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:       # (module globals are None during interpreter shutdown)
             _lib.lib().fibers_plan_destroy(self._h)
             self._h = None
 

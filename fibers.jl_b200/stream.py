@@ -25,6 +25,9 @@ class Tract:                       # the streamline fields of the reference's Tr
     sublist: np.ndarray = field(default=None, repr=False)   # the sub-voxel offsets that were used (the reference keeps them in StreamWork)
 
     ref: dict = field(default=None, repr=False)             # volsize / volres / vox2ras of the volume the header is built from (Tract{T}(ref::MRI))
+    scalars: list = field(default=None, repr=False)         # trk_read: [n_scalars, npts] float32 per streamline
+    properties: np.ndarray = field(default=None, repr=False)  # trk_read: [n_properties, nstr] float32
+    header: dict = field(default=None, repr=False)          # trk_read: the remaining header fields of the reference's Tract (src/trk.jl:11-35)
 
     @property
     def n_count(self):
@@ -42,6 +45,38 @@ def trk_write(tr: "Tract", outfile: str) -> bool:
     npts = np.ascontiguousarray(tr.npts, np.int32)
     _lib.check(_lib.lib().fibers_trk_write(outfile.encode(), _lib.ptr(vs), _lib.ptr(vr), _lib.ptr(M), int(len(npts)), _lib.ptr(npts), _lib.ptr(xyz)))
     return False
+
+
+class TrkInfo(C.Structure):            # fibers_trk_info (include/fibers_cuda.h)
+    _fields_ = [("dim", C.c_int32 * 3), ("voxel_size", C.c_float * 3), ("origin", C.c_float * 3), ("n_scalars", C.c_int32),
+                ("n_properties", C.c_int32), ("vox_to_ras", C.c_float * 16), ("voxel_order", C.c_char * 4),
+                ("voxel_order_original", C.c_char * 4), ("image_orientation_patient", C.c_float * 6), ("n_count", C.c_int32),
+                ("version", C.c_int32), ("hdr_size", C.c_int32), ("total_points", C.c_int64)]
+
+
+def trk_read(infile: str) -> "Tract":
+    """trk_read(infile) -- src/trk.jl:358-425: points come back as xyz ./ voxel_size .- .5 (0-based voxel coordinates);
+    scalars per point and properties per streamline as stored."""
+    L = _lib.lib()
+    info = TrkInfo()
+    _lib.check(L.fibers_trk_read_info(infile.encode(), C.byref(info)))
+    n, tot, ns, npr = info.n_count, info.total_points, info.n_scalars, info.n_properties
+    npts = np.zeros(n, np.int32)
+    xyz = np.zeros((3, tot), np.float32, order="F")
+    sc = np.zeros((ns, tot), np.float32, order="F")
+    pr = np.zeros((npr, n), np.float32, order="F")
+    _lib.check(L.fibers_trk_read_data(infile.encode(), C.byref(info), _lib.ptr(npts), _lib.ptr(xyz), _lib.ptr(sc) if ns else None,
+                                      _lib.ptr(pr) if npr else None))
+    cuts = np.cumsum(npts)[:-1]
+    vs = np.array(info.voxel_size[:], np.float32)
+    M = np.array(info.vox_to_ras[:], np.float32).reshape(4, 4)
+    hdr = {"dim": np.array(info.dim[:], np.int16), "voxel_size": vs, "origin": np.array(info.origin[:], np.float32), "n_scalars": ns,
+           "n_properties": npr, "vox_to_ras": M, "voxel_order": bytes(info.voxel_order), "voxel_order_original": bytes(info.voxel_order_original),
+           "image_orientation_patient": np.array(info.image_orientation_patient[:], np.float32), "n_count": n, "version": info.version,
+           "hdr_size": info.hdr_size}
+    return Tract(xyz=[np.asfortranarray(a) for a in np.split(xyz, cuts, axis=1)] if n else [], npts=npts,
+                 ref={"volsize": [int(d) for d in info.dim], "volres": vs, "vox2ras0": M},
+                 scalars=[np.asfortranarray(a) for a in np.split(sc, cuts, axis=1)] if n else [], properties=pr, header=hdr)
 
 
 def _vol(m):

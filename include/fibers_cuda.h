@@ -254,6 +254,23 @@ int fibers_mri_write(const char* path, const void* vol, int dtype, const int32_t
 int fibers_trk_write(const char* path, const int32_t* volsize /*[3]*/, const float* volres /*[3]*/, const float* vox2ras /*[16]*/,
                      int64_t nstr, const int32_t* npts, const float* xyz /*[3, sum(npts)]*/);
 
+/* trk_read (src/trk.jl:358-425): two calls, like the volume reader.  `info` = the header fields a caller of the reference's
+ * Tract reads back + the total number of points (so that the caller can allocate); `data` fills npts [n_count], xyz
+ * [3, total_points] as xyz ./ voxel_size .- .5 (0-based voxel coordinates, :412-413), scalars [n_scalars, total_points] and
+ * properties [n_properties, n_count] (NULL allowed when the counts are 0). */
+typedef struct {
+    int32_t dim[3];
+    float voxel_size[3], origin[3];
+    int32_t n_scalars, n_properties;
+    float vox_to_ras[16];        /* row-major */
+    char voxel_order[4], voxel_order_original[4];
+    float image_orientation_patient[6];
+    int32_t n_count, version, hdr_size;
+    int64_t total_points;
+} fibers_trk_info;
+int fibers_trk_read_info(const char* path, fibers_trk_info* info);
+int fibers_trk_read_data(const char* path, const fibers_trk_info* info, int32_t* npts, float* xyz, float* scalars, float* properties);
+
 /* Optional: page-lock a caller-owned host array (and release it) so that later calls take the direct DMA path.
  * Worth it for arrays that are used more than once (registration itself costs about as much as one copy). */
 int fibers_cuda_host_register(void* ptr, size_t bytes);

@@ -214,3 +214,57 @@ def test_trk_write_layout(tmp_path):
         assert n == ln.shape[1]
         pts = np.array(struct.unpack_from(f"<{3 * n}f", raw, off), np.float32).reshape(n, 3); off += 12 * n
         np.testing.assert_array_equal(pts, ((ln.T.astype(np.float64) + 0.5) * np.array([1.25, 2.0, 1.5])).astype(np.float32))
+
+
+def test_trk_read_layout_and_round_trip(tmp_path):
+    """fibers_trk_read_* against a file assembled byte by byte from the TrackVis v2 layout trk_read walks
+    (src/trk.jl:358-425): scalars per point, properties per streamline, points back as xyz ./ voxel_size .- .5;
+    then trk_write -> trk_read gives back the voxel coordinates stream() produced."""
+    from fibers_jl_b200.stream import Tract, trk_read, trk_write
+    vs = np.array([1.25, 2.0, 1.5], np.float32)
+    M = np.array([[-1.25, 0, 0, 90], [0, 0, 1.5, -126], [0, -2.0, 0, 72], [0, 0, 0, 1]], np.float32)
+    h = bytearray(1000)
+    h[0:6] = b"TRACK\0"
+    struct.pack_into("<3h", h, 6, 40, 50, 60)
+    struct.pack_into("<3f", h, 12, *vs)
+    struct.pack_into("<3f", h, 24, 1.0, 2.0, 3.0)
+    struct.pack_into("<h", h, 36, 2); h[38:41] = b"fa\0"; h[58:61] = b"md\0"
+    struct.pack_into("<h", h, 238, 1); h[240:244] = b"len\0"
+    struct.pack_into("<16f", h, 440, *M.reshape(-1))
+    h[948:952] = b"LIA\0"; h[952:956] = b"LAS\0"
+    struct.pack_into("<6f", h, 956, 1, 0, 0, 0, 0, -1)
+    struct.pack_into("<3i", h, 988, 3, 2, 1000)
+    rng = np.random.default_rng(5)
+    body = b""
+    lines = []
+    for n in (4, 0, 2):                                       # an empty streamline in the middle
+        pts = rng.uniform(0, 60, size=(n, 3)).astype(np.float32)
+        sc = rng.normal(size=(n, 2)).astype(np.float32)
+        prop = rng.normal(size=1).astype(np.float32)
+        lines.append((pts, sc, prop))
+        body += struct.pack("<i", n) + np.concatenate([pts, sc], axis=1).astype("<f4").tobytes() + prop.astype("<f4").tobytes()
+    (tmp_path / "b.trk").write_bytes(bytes(h) + body)
+    tr = trk_read(str(tmp_path / "b.trk"))
+    assert tr.n_count == 3 and tr.npts.tolist() == [4, 0, 2]
+    assert tr.header["n_scalars"] == 2 and tr.header["n_properties"] == 1 and tr.header["version"] == 2 and tr.header["hdr_size"] == 1000
+    assert tr.header["dim"].tolist() == [40, 50, 60] and tr.header["origin"].tolist() == [1.0, 2.0, 3.0]
+    assert tr.header["voxel_order"] == b"LIA" and tr.header["voxel_order_original"] == b"LAS"
+    np.testing.assert_array_equal(tr.header["vox_to_ras"], M)
+    np.testing.assert_array_equal(tr.header["image_orientation_patient"], np.array([1, 0, 0, 0, 0, -1], np.float32))
+    for i, (pts, sc, prop) in enumerate(lines):
+        want = ((pts / vs).astype(np.float32).astype(np.float64) - 0.5).astype(np.float32)     # Float32 ./ Float32 .- .5 (Float64 literal), stored as Float32
+        np.testing.assert_array_equal(tr.xyz[i], want.T)
+        np.testing.assert_array_equal(tr.scalars[i], sc.T)
+        np.testing.assert_array_equal(tr.properties[:, i], prop)
+    # truncated file -> error, like the reference's read! throwing EOFError
+    (tmp_path / "c.trk").write_bytes((bytes(h) + body)[:-6])
+    with pytest.raises(Exception):
+        trk_read(str(tmp_path / "c.trk"))
+    # round trip of a written tract
+    out = [np.asfortranarray(rng.uniform(0, 40, size=(3, n)).astype(np.float32)) for n in (5, 1, 7)]
+    t0 = Tract(out, np.array([5, 1, 7], np.int32), None, dict(volsize=[40, 50, 60], volres=vs, vox2ras0=M))
+    assert trk_write(t0, str(tmp_path / "d.trk")) is False
+    t1 = trk_read(str(tmp_path / "d.trk"))
+    assert t1.npts.tolist() == [5, 1, 7] and t1.header["n_scalars"] == 0 and t1.header["n_properties"] == 0
+    for a, b in zip(out, t1.xyz):
+        np.testing.assert_allclose(b, a, rtol=0, atol=2e-5)                # (x + .5) * vs / vs - .5: two roundings at |x| <= 60
