@@ -60,12 +60,15 @@ SIGNATURES = {
     "fibers_st_eigen_device": (_i, [_p] * 6 + [_i64, _p, _p, _p]),
     "fibers_stream": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _f, _i, _p, _p, _p]),
     "fibers_stream_device": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _f, _p, _p, _p]),
+    "fibers_stream_lcm": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _f, _p, _p, _p, _i, _i, _i, _f, _f, _p, C.c_double, _i, _i, C.c_uint64, _i, _p, _p, _p]),
+    "fibers_stream_fetch_scalars": (_i, [_p, _p]),
     "fibers_stream_fetch": (_i, [_p, _p, _p]),
     "fibers_stream_free": (None, [_p]),
     "fibers_mri_read_info": (_i, [C.c_char_p, _p]),
     "fibers_mri_read_data": (_i, [C.c_char_p, _p, _p, _i64]),
     "fibers_mri_write": (_i, [C.c_char_p, _p, _i, _p, _p, _p, _f, _f, _f, _f, _f, _f, _i]),
     "fibers_trk_write": (_i, [C.c_char_p, _p, _p, _p, _i64, _p, _p]),
+    "fibers_trk_write_ex": (_i, [C.c_char_p, _p, _p, _p, _i64, _p, _p, _i, _p, _i, _p]),
     "fibers_trk_read_info": (_i, [C.c_char_p, _p]),
     "fibers_trk_read_data": (_i, [C.c_char_p, _p, _p, _p, _p, _p]),
     "fibers_cuda_host_register": (_i, [_p, C.c_size_t]),

@@ -413,11 +413,19 @@ extern "C" int fibers_mri_write(const char* path, const void* vol, int dtype, co
 // ---- TrackVis .trk (version 2) writer: trk_write (src/trk.jl:433-495) with the header Tract{T}(ref::MRI) builds (:88-145) ----
 extern "C" int fibers_trk_write(const char* path, const int32_t* volsize, const float* volres, const float* vox2ras,
                                 int64_t nstr, const int32_t* npts, const float* xyz) {
+    return fibers_trk_write_ex(path, volsize, volres, vox2ras, nstr, npts, xyz, 0, nullptr, 0, nullptr);
+}
+
+extern "C" int fibers_trk_write_ex(const char* path, const int32_t* volsize, const float* volres, const float* vox2ras, int64_t nstr, const int32_t* npts,
+                                   const float* xyz, int ns, const float* scalars, int np, const float* properties) {
     if (!path || !volsize || !volres || !vox2ras || (nstr > 0 && (!npts || !xyz))) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    if (ns < 0 || ns > 10 || np < 0 || np > 10 || (ns > 0 && nstr > 0 && !scalars) || (np > 0 && nstr > 0 && !properties))
+        return fail(FIBERS_ERR_ARG, "between 0 and 10 scalars / properties, with their arrays");
     uint8_t h[1000]; memset(h, 0, sizeof(h));
     memcpy(h, "TRACK", 6);
     for (int i = 0; i < 3; ++i) { const int16_t d = (int16_t)volsize[i]; memcpy(h + 6 + 2 * i, &d, 2); }
-    memcpy(h + 12, volres, 12);                                   // voxel_size; origin (24..35) = 0; n_scalars (36) = 0; n_properties (238) = 0
+    memcpy(h + 12, volres, 12);                                   // voxel_size; origin (24..35) = 0; names stay empty
+    { const int16_t a = (int16_t)ns, b = (int16_t)np; memcpy(h + 36, &a, 2); memcpy(h + 238, &b, 2); }
     memcpy(h + 440, vox2ras, 64);                                 // vox_to_ras, row by row (permutedims before the write, :452)
     // voxel_order from vox2ras_to_orient (src/mri.jl:471-500): the dominant axis of every column and its sign
     for (int c = 0; c < 3; ++c) {
@@ -442,11 +450,14 @@ extern "C" int fibers_trk_write(const char* path, const int32_t* volsize, const 
     int64_t p0 = 0;
     for (int64_t i = 0; i < nstr; ++i) {
         const int32_t n = npts[i];
-        buf.resize((size_t)3 * n + 1);
+        buf.resize((size_t)(3 + ns) * n + 1 + np);
         memcpy(buf.data(), &n, 4);
-        for (int32_t k = 0; k < n; ++k)
+        for (int32_t k = 0; k < n; ++k) {
             for (int c = 0; c < 3; ++c)                            // T.((xyz .+ .5) .* voxel_size): Float64 arithmetic, rounded once (:477)
-                buf[1 + 3 * k + c] = (float)(((double)xyz[3 * (p0 + k) + c] + 0.5) * (double)volres[c]);
+                buf[1 + (size_t)(3 + ns) * k + c] = (float)(((double)xyz[3 * (p0 + k) + c] + 0.5) * (double)volres[c]);
+            for (int c = 0; c < ns; ++c) buf[1 + (size_t)(3 + ns) * k + 3 + c] = scalars[(size_t)ns * (p0 + k) + c];
+        }
+        for (int c = 0; c < np; ++c) buf[1 + (size_t)(3 + ns) * n + c] = properties[(size_t)np * i + c];
         if (!out.write(buf.data(), buf.size() * 4)) return fail(FIBERS_ERR_ARG, std::string("Problem saving ") + path);
         p0 += n;
     }

@@ -1,8 +1,10 @@
 // Deterministic streamline tractography on the GPU (`stream`, the downstream consumer of
 // the GQI / DSI / DTI peaks).  Replaces the `Threads.@threads` seed loop of the reference (src/stream.jl:730-790) and the
 // per-seed propagation it calls (stream_new_line :621-690, stream_new_point! :497-541, stream_pick_by_angle! :355-387)
-// for what has a deterministic answer: orientation VECTORS, no local connection matrices (that branch draws from
-// rand(Categorical(...))); macroscopic voxels and the microscopy regime (stream_micro_new_point! :547-617).
+// for orientation VECTORS: macroscopic voxels, the microscopy regime (stream_micro_new_point! :547-617) and -- macroscopic
+// only -- local connection matrices (stream_pick_by_lcm! :380-494).  That branch draws from rand(Categorical(...)) on Julia's
+// task-local generator (its answer depends on the thread schedule); here draw k of streamline `line` is a counter-based
+// uniform number (lcm_uniform), so the counting pass and the writing pass see the same draws and the oracle can follow.
 //
 //   stream_pack_kernel   the StreamWork constructor (:72-147): voxel mask (given, or "any vector component non-zero"),
 //                        intersected with fa >= fa_thresh; vectors zeroed outside the mask / where f[ivec] < f_thresh;
@@ -61,16 +63,38 @@ struct TrackParams {
     const float* ovec; const uint8_t* mask; const int32_t* seeds; int64_t nseed; const float* sub; int nsub;
     int nx, ny, nz, nvec, len_min, len_max; float cos_thresh, step, smooth;
     int sd[3]; float search_cos;       // microscopy regime: half widths of the search box, cosine of the search angle
+    const float* lcm; int s1, s2; unsigned long long lcm_seed;   // LCM branch: thresholded matrices [voxel][10], in-plane dimensions (0-based), generator seed
 };
+
+// draw k of streamline `line`: splitmix64 finaliser of seed + (line + 1) * golden + (k + 1) * 0xD1B54A32D192ED03, top 24 bits -> [0, 1)
+__device__ __forceinline__ float lcm_uniform(unsigned long long seed, long long line, int k) {
+    unsigned long long z = seed + (unsigned long long)(line + 1) * 0x9E3779B97F4A7C15ull + (unsigned long long)(k + 1) * 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(z >> 40) * 5.9604644775390625e-8f;
+}
+
+// lcm_out[v][j] = lcms[j][v] where it is >= lcm_thresh (compared in fp64 like Float32 .>= Float64), else 0  (:209, :220)
+__global__ void stream_pack_lcm_kernel(const float* __restrict__ lcms, double thresh, int64_t nvox, float* __restrict__ lcm_out) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvox) return;
+    for (int j = 0; j < 10; ++j) {
+        const float x = lcms[(int64_t)j * nvox + v];
+        lcm_out[v * 10 + j] = ((double)x >= thresh) ? x : 0.f;
+    }
+}
 
 __device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2) { return (a0 * b0 + a1 * b1) + a2 * b2; }
 
 // kWrite == false: counts -> nfb[line] = (points forward, points backward).
 // kWrite == true : points -> xyz + 3 * off[line] for the lines with kept[line] != 0 (nfb gives nf).
-template <bool kWrite>
+// kLcm: the LCM branch of stream_new_point! (:523-538): conventional pick first (for the method-difference flag), then the
+// pick by local connection matrix; every point also gets its flag (scal), and the angle threshold is not applied (:671-678).
+template <bool kWrite, bool kLcm>
 __global__ void __launch_bounds__(128) stream_track_kernel(TrackParams P, int2* __restrict__ nfb, const int64_t* __restrict__ off,
                                                             const int32_t* __restrict__ sidx, const uint8_t* __restrict__ kept,
-                                                            float* __restrict__ xyz, int32_t* __restrict__ npts_out) {
+                                                            float* __restrict__ xyz, int32_t* __restrict__ npts_out, float* __restrict__ scal) {
     const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= P.nseed * P.nsub) return;
     int nf_known = 0;
@@ -88,6 +112,7 @@ __global__ void __launch_bounds__(128) stream_track_kernel(TrackParams P, int2* 
     const float s0 = P.sub[isub * 3 + 0], s1 = P.sub[isub * 3 + 1], s2 = P.sub[isub * 3 + 2];
     int ivec = 0;                                          // W.ivec_next[tid] - 1 (:646): NOT reset between the directions
     int npts = 0, nf = 0, nb = 0;
+    int ndraw = 0;                                         // LCM branch: uniform numbers this line has consumed
     for (int dir = 0; dir < 2; ++dir) {
         const float fwd = dir == 0 ? 1.f : -1.f;
         float px = (float)(sx + 1) + s0, py = (float)(sy + 1) + s1, pz = (float)(sz + 1) + s2;     // 1-based coordinates (:652)
@@ -114,14 +139,72 @@ __global__ void __launch_bounds__(128) stream_track_kernel(TrackParams P, int2* 
             float nxv, nyv, nzv;
             if (bcos > 0.f) { nxv = bx; nyv = by; nzv = bz; } else { nxv = -bx; nyv = -by; nzv = -bz; }
             ivec = best;
+            bool isdiff = false;
+            if (kLcm) {
+                // ---- stream_pick_by_lcm! (:380-494).  In the voxel the line is already in, the vector chosen last is kept -- and
+                //      "last" is the conventional pick a few lines up (:399-411), so there is nothing to change. ----
+                const float pn[3] = {px, py, pz}, qn[3] = {qx, qy, qz};
+                int d[3] = {__float2int_rn(px) - ix, __float2int_rn(py) - iy, __float2int_rn(pz) - iz};
+                if (d[0] != 0 || d[1] != 0 || d[2] != 0) {
+                    const int s1 = P.s1, s2 = P.s2, st = 3 - s1 - s2;
+                    auto edge = [&]() {                       // dxyz columns (:229-231): 1 = (-1, 0), 2 = (0, -1), 3 = (1, 0), 4 = (0, 1) in (s1, s2)
+                        if (d[st] != 0) return 0;
+                        if (d[s2] == 0) return d[s1] == -1 ? 1 : d[s1] == 1 ? 3 : 0;
+                        if (d[s1] == 0) return d[s2] == -1 ? 2 : d[s2] == 1 ? 4 : 0;
+                        return 0;
+                    };
+                    int entry = edge();
+                    if (entry == 0) {                          // diagonal jump: keep the dimension that changes faster (:422-437)
+                        if (fabsf(pn[s1] - qn[s1]) < fabsf(pn[s2] - qn[s2])) d[s2] = 0; else d[s1] = 0;
+                        entry = edge();
+                    }
+                    // connections of the entry edge (:440-445): element j joins edges E1[j], E2[j]
+                    const int E1[10] = {1, 1, 1, 1, 2, 2, 2, 3, 3, 4}, E2[10] = {1, 2, 3, 4, 2, 3, 4, 3, 4, 4};
+                    float lcm[10];
+                    bool any = false;
+                    float tot = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        const float x = P.lcm[nl * 10 + j];
+                        lcm[j] = (E1[j] == entry || E2[j] == entry) ? x : 0.f;
+                        any = any || lcm[j] != 0.f;            // !iszero(lcm): NaN counts as non-zero
+                        tot += lcm[j];
+                    }
+                    if (!any) break;                           // (:447, :493)
+                    const float u = lcm_uniform(P.lcm_seed, line, ndraw++);
+                    float cp = lcm[0] / tot;                  // lcm ./= sum(lcm); rand(Categorical(lcm)): first i with cumulative p > u
+                    int il = 0;
+#pragma unroll
+                    for (int j = 1; j < 10; ++j)
+                        if (il == j - 1 && cp <= u) { il = j; cp += lcm[j] / tot; }
+                    const int ex = E1[il] == entry ? E2[il] : E1[il];                                // (:453-454)
+                    float dj[3] = {0.f, 0.f, 0.f};
+                    dj[ex == 1 || ex == 3 ? s1 : s2] = (ex == 1 || ex == 2) ? -1.f : 1.f;
+                    int kb = 0; float kcos = 0.f, kabs = 0.f;
+                    for (int i = 0; i < P.nvec; ++i) {                                                // (:460-471)
+                        const float wx = ov[3 * i], wy = ov[3 * i + 1], wz = ov[3 * i + 2];
+                        float c, a;
+                        if (wx == 0.f && wy == 0.f && wz == 0.f) c = a = -INFINITY;
+                        else { c = dot3(dj[0], dj[1], dj[2], wx, wy, wz); a = fabsf(c); }
+                        if (i == 0 || (!isnan(kabs) && (isnan(a) || a > kabs))) { kb = i; kcos = c; kabs = a; }
+                    }
+                    if (!isfinite(kcos)) break;                                                       // (:473)
+                    const float wx = ov[3 * kb], wy = ov[3 * kb + 1], wz = ov[3 * kb + 2];
+                    if (kcos > 0.f) { nxv = wx; nyv = wy; nzv = wz; } else { nxv = -wx; nyv = -wy; nzv = -wz; }
+                    ivec = kb;
+                    isdiff = kb != best;                                                              // (:537)
+                }
+            }
             // ---- stream_new_line: save the CURRENT position (:660 / :666) ----
             if (kWrite) {
-                float* o = out + 3 * (int64_t)(dir == 0 ? nf_known - 1 - nf : nf_known + nb);
+                const int64_t at = dir == 0 ? nf_known - 1 - nf : nf_known + nb;
+                float* o = out + 3 * at;
                 o[0] = px; o[1] = py; o[2] = pz;
+                if (kLcm) scal[off[line] + at] = isdiff ? 1.f : 0.f;                                  // (:671-674)
             }
             if (dir == 0) ++nf; else ++nb;
             ++npts;
-            if (dot3(vx, vy, vz, nxv, nyv, nzv) < P.cos_thresh) break;                              // (:677)
+            if (!kLcm && dot3(vx, vy, vz, nxv, nyv, nzv) < P.cos_thresh) break;                     // (:677; not used with LCMs, :676)
             if (npts > P.len_max) break;                                                            // (:681)
             if (P.smooth != 0.f) {                                                                  // (:684-688)
                 const float om = 1.f - P.smooth;
@@ -246,7 +329,8 @@ __global__ void stream_len_kernel(const int2* __restrict__ nfb, int64_t n, int l
 struct DevBuf { std::vector<void*> p; ~DevBuf() { for (void* q : p) cudaFree(q); }
                 template <class T> cudaError_t alloc(T** o, size_t n) { void* q = nullptr; cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) p.push_back(q); *o = (T*)q; return e; } };
 
-struct StreamResult { int device; int64_t nstr, npts; int32_t* d_npts; float* d_xyz; };
+struct StreamResult { int device; int64_t nstr, npts; int32_t* d_npts; float* d_xyz; float* d_scal; };   // d_scal: one flag per point (LCM branch) or NULL
+struct LcmArgs { const float* d_lcms; double thresh; int s1, s2; unsigned long long seed; };
 
 }  // namespace
 }  // namespace fibers
@@ -255,11 +339,11 @@ using namespace fibers;
 #define T_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? FIBERS_ERR_NOMEM : FIBERS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
 
 // Device-resident core: every volume pointer is a DEVICE pointer (e.g. the peak / qa planes a reconstruction just wrote).
-extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
-                                    const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
-                                    const float* sublist /*host [nsub][3]*/, int nsub, int len_min, int len_max, float cosang_thresh,
-                                    float step_size, float smooth_coeff, const int32_t* micro_search_dist, float micro_search_cosang,
-                                    void** result, int64_t* nstr, int64_t* npts_total) {
+static int stream_core(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
+                       const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
+                       const float* sublist /*host [nsub][3]*/, int nsub, int len_min, int len_max, float cosang_thresh,
+                       float step_size, float smooth_coeff, const int32_t* micro_search_dist, float micro_search_cosang,
+                       const LcmArgs* lcm, void** result, int64_t* nstr, int64_t* npts_total) {
     if (!d_ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
     if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
     if (nx <= 0 || ny <= 0 || nz <= 0 || nsub <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions and the number of sub-voxel samples must be positive");
@@ -298,15 +382,26 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
     int2* nfb; int64_t *len, *off; int32_t *keep32, *sidx; uint8_t* kept;
     T_CUDA(D.alloc(&nfb, (size_t)nline)); T_CUDA(D.alloc(&len, (size_t)nline + 1)); T_CUDA(D.alloc(&off, (size_t)nline + 1));
     T_CUDA(D.alloc(&keep32, (size_t)nline + 1)); T_CUDA(D.alloc(&sidx, (size_t)nline + 1)); T_CUDA(D.alloc(&kept, (size_t)nline));
-    TrackParams P{ovec_arr, mask_arr, seeds, nseed, d_sub, nsub, nx, ny, nz, nvec, len_min, len_max, cosang_thresh, step_size, smooth_coeff, {0, 0, 0}, 0.f};
+    TrackParams P{ovec_arr, mask_arr, seeds, nseed, d_sub, nsub, nx, ny, nz, nvec, len_min, len_max, cosang_thresh, step_size, smooth_coeff, {0, 0, 0}, 0.f,
+                  nullptr, 0, 1, 0ull};
     const bool micro = micro_search_dist != nullptr;
+    if (lcm) {
+        if (micro) return fail(FIBERS_ERR_ARG, "stream: local connection matrices are only defined for the macroscopic regime");
+        if (!lcm->d_lcms || lcm->s1 < 0 || lcm->s1 > 2 || lcm->s2 < 0 || lcm->s2 > 2 || lcm->s1 == lcm->s2) return fail(FIBERS_ERR_ARG, "stream: bad LCM arguments");
+        float* lcm_arr; T_CUDA(D.alloc(&lcm_arr, (size_t)nvox * 10));
+        stream_pack_lcm_kernel<<<gv, 256>>>(lcm->d_lcms, lcm->thresh, nvox, lcm_arr);
+        count_launch(1);
+        T_CUDA(cudaGetLastError());
+        P.lcm = lcm_arr; P.s1 = lcm->s1; P.s2 = lcm->s2; P.lcm_seed = lcm->seed;
+    }
     if (micro) {
         for (int i = 0; i < 3; ++i) { if (micro_search_dist[i] < 0 || micro_search_dist[i] > 64) return fail(FIBERS_ERR_ARG, "micro_search_dist must be in 0..64"); P.sd[i] = micro_search_dist[i]; }
         P.search_cos = micro_search_cosang;
     }
     const unsigned gl = (unsigned)(micro ? (nline * 32 + 127) / 128 : (nline + 127) / 128);          // micro: one warp per line
     if (micro) stream_track_micro_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
-    else stream_track_kernel<false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else if (lcm) stream_track_kernel<false, true><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else stream_track_kernel<false, false><<<gl, 128>>>(P, nfb, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     stream_len_kernel<<<(unsigned)((nline + 255) / 256), 256>>>(nfb, nline, len_min, len, keep32, kept);
     count_launch(2);
     T_CUDA(cudaMemsetAsync(len + nline, 0, sizeof(int64_t))); T_CUDA(cudaMemsetAsync(keep32 + nline, 0, sizeof(int32_t)));
@@ -322,28 +417,39 @@ extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx
     int64_t total = 0; int32_t nkeep = 0;
     T_CUDA(cudaMemcpy(&total, off + nline, sizeof(int64_t), cudaMemcpyDeviceToHost));
     T_CUDA(cudaMemcpy(&nkeep, sidx + nline, sizeof(int32_t), cudaMemcpyDeviceToHost));
-    StreamResult* R = new StreamResult{device, nkeep, total, nullptr, nullptr};
+    StreamResult* R = new StreamResult{device, nkeep, total, nullptr, nullptr, nullptr};
     if (cudaMalloc(&R->d_npts, sizeof(int32_t) * std::max<int64_t>(nkeep, 1)) != cudaSuccess ||
-        cudaMalloc(&R->d_xyz, sizeof(float) * 3 * std::max<int64_t>(total, 1)) != cudaSuccess) {
-        cudaFree(R->d_npts); cudaFree(R->d_xyz); delete R; cudaGetLastError();
+        cudaMalloc(&R->d_xyz, sizeof(float) * 3 * std::max<int64_t>(total, 1)) != cudaSuccess ||
+        (lcm && cudaMalloc(&R->d_scal, sizeof(float) * std::max<int64_t>(total, 1)) != cudaSuccess)) {
+        cudaFree(R->d_npts); cudaFree(R->d_xyz); cudaFree(R->d_scal); delete R; cudaGetLastError();
         return fail(FIBERS_ERR_NOMEM, "stream: device allocation of the streamline buffers failed");
     }
     if (nkeep > 0) {
         if (micro) stream_track_micro_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
-        else stream_track_kernel<true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts);
+        else if (lcm) stream_track_kernel<true, true><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts, R->d_scal);
+        else stream_track_kernel<true, false><<<gl, 128>>>(P, nfb, off, sidx, kept, R->d_xyz, R->d_npts, nullptr);
         count_launch(1);
     }
     cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { cudaFree(R->d_npts); cudaFree(R->d_xyz); delete R; return fail(FIBERS_ERR_CUDA, std::string("stream: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaFree(R->d_npts); cudaFree(R->d_xyz); cudaFree(R->d_scal); delete R; return fail(FIBERS_ERR_CUDA, std::string("stream: ") + cudaGetErrorString(e)); }
     *result = R; *nstr = nkeep; *npts_total = total;
     return 0;
 }
 
-extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
-                             const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
-                             int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff,
-                             const int32_t* micro_search_dist, float micro_search_cosang, int device,
-                             void** result, int64_t* nstr, int64_t* npts_total) {
+extern "C" int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, int nz, const float* const* d_f, float f_thresh,
+                                    const float* d_fa, float fa_thresh, const uint8_t* d_mask, const uint8_t* d_seed,
+                                    const float* sublist /*host [nsub][3]*/, int nsub, int len_min, int len_max, float cosang_thresh,
+                                    float step_size, float smooth_coeff, const int32_t* micro_search_dist, float micro_search_cosang,
+                                    void** result, int64_t* nstr, int64_t* npts_total) {
+    return stream_core(d_ovec, nvec, nx, ny, nz, d_f, f_thresh, d_fa, fa_thresh, d_mask, d_seed, sublist, nsub, len_min, len_max, cosang_thresh,
+                       step_size, smooth_coeff, micro_search_dist, micro_search_cosang, nullptr, result, nstr, npts_total);
+}
+
+static int stream_host(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
+                       const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
+                       int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff,
+                       const int32_t* micro_search_dist, float micro_search_cosang, const float* lcms, LcmArgs lcm, int device,
+                       void** result, int64_t* nstr, int64_t* npts_total) {
     if (!ovec || !sublist || !result || !nstr || !npts_total) return fail(FIBERS_ERR_ARG, "NULL pointer");
     if (nvec < 1 || nvec > MAX_NVEC) return fail(FIBERS_ERR_ARG, "between 1 and 8 orientation-vector volumes are supported");
     if (nx <= 0 || ny <= 0 || nz <= 0) return fail(FIBERS_ERR_ARG, "volume dimensions must be positive");
@@ -366,8 +472,31 @@ extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny,
     if (fa) if (int rc = up(fa, sizeof(float) * nvox, (const void**)&d_fa)) return rc;
     if (mask) if (int rc = up(mask, (size_t)nvox, (const void**)&d_mask)) return rc;
     if (seed) if (int rc = up(seed, (size_t)nvox, (const void**)&d_seed)) return rc;
-    return fibers_stream_device(d_ovec, nvec, nx, ny, nz, f ? d_f : nullptr, f_thresh, d_fa, fa_thresh, d_mask, d_seed, sublist, nsub,
-                                len_min, len_max, cosang_thresh, step_size, smooth_coeff, micro_search_dist, micro_search_cosang, result, nstr, npts_total);
+    if (lcms) if (int rc = up(lcms, sizeof(float) * 10 * nvox, (const void**)&lcm.d_lcms)) return rc;
+    return stream_core(d_ovec, nvec, nx, ny, nz, f ? d_f : nullptr, f_thresh, d_fa, fa_thresh, d_mask, d_seed, sublist, nsub,
+                       len_min, len_max, cosang_thresh, step_size, smooth_coeff, micro_search_dist, micro_search_cosang, lcms ? &lcm : nullptr,
+                       result, nstr, npts_total);
+}
+
+extern "C" int fibers_stream(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
+                             const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
+                             int len_min, int len_max, float cosang_thresh, float step_size, float smooth_coeff,
+                             const int32_t* micro_search_dist, float micro_search_cosang, int device,
+                             void** result, int64_t* nstr, int64_t* npts_total) {
+    return stream_host(ovec, nvec, nx, ny, nz, f, f_thresh, fa, fa_thresh, mask, seed, sublist, nsub, len_min, len_max, cosang_thresh, step_size,
+                       smooth_coeff, micro_search_dist, micro_search_cosang, nullptr, LcmArgs{}, device, result, nstr, npts_total);
+}
+
+// stream(...; lcms, lcm_thresh): the branch of stream_new_point! that follows local connection matrices (src/stream.jl:523-538, :380-494).
+// lcms: [nx, ny, nz, 10] like lcms.vol; strdim1 / strdim2: the in-plane dimensions (0-based; the reference derives them from the
+// all-zero component of the first orientation volume, :224-226); lcm_seed: seed of the counter-based uniform generator.
+extern "C" int fibers_stream_lcm(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
+                                 const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
+                                 int len_min, int len_max, float step_size, float smooth_coeff, const float* lcms, double lcm_thresh,
+                                 int strdim1, int strdim2, uint64_t lcm_seed, int device, void** result, int64_t* nstr, int64_t* npts_total) {
+    if (!lcms) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    return stream_host(ovec, nvec, nx, ny, nz, f, f_thresh, fa, fa_thresh, mask, seed, sublist, nsub, len_min, len_max, 0.f, step_size,
+                       smooth_coeff, nullptr, 0.f, lcms, LcmArgs{nullptr, lcm_thresh, strdim1, strdim2, (unsigned long long)lcm_seed}, device, result, nstr, npts_total);
 }
 
 extern "C" int fibers_stream_fetch(void* result, int32_t* npts, float* xyz) {
@@ -379,10 +508,21 @@ extern "C" int fibers_stream_fetch(void* result, int32_t* npts, float* xyz) {
     return 0;
 }
 
+// one value per point in the order of fibers_stream_fetch's xyz: 1 where the LCM pick differed from the conventional pick
+// (the scalars of the reference's Tract, src/stream.jl:783); an error for results of the other entry points
+extern "C" int fibers_stream_fetch_scalars(void* result, float* scalars) {
+    StreamResult* R = (StreamResult*)result;
+    if (!R || !scalars) return fail(FIBERS_ERR_ARG, "NULL pointer");
+    if (!R->d_scal) return fail(FIBERS_ERR_ARG, "this result carries no scalars (not an LCM run)");
+    T_CUDA(cudaSetDevice(R->device));
+    if (R->npts > 0) T_CUDA(cudaMemcpy(scalars, R->d_scal, sizeof(float) * R->npts, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 extern "C" void fibers_stream_free(void* result) {
     StreamResult* R = (StreamResult*)result;
     if (!R) return;
     cudaSetDevice(R->device);
-    cudaFree(R->d_npts); cudaFree(R->d_xyz);
+    cudaFree(R->d_npts); cudaFree(R->d_xyz); cudaFree(R->d_scal);
     delete R;
 }

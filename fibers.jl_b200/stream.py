@@ -43,7 +43,14 @@ def trk_write(tr: "Tract", outfile: str) -> bool:
     vr = np.ascontiguousarray(ref.get("volres", [1, 1, 1]), np.float32)
     M = np.ascontiguousarray(ref.get("vox2ras0", np.eye(4)), np.float32)
     npts = np.ascontiguousarray(tr.npts, np.int32)
-    _lib.check(_lib.lib().fibers_trk_write(outfile.encode(), _lib.ptr(vs), _lib.ptr(vr), _lib.ptr(M), int(len(npts)), _lib.ptr(npts), _lib.ptr(xyz)))
+    sc = pr = None
+    ns = npr = 0
+    if tr.scalars is not None and len(tr.scalars) and tr.scalars[0].shape[0] > 0:
+        sc = np.asfortranarray(np.concatenate(tr.scalars, axis=1), dtype=np.float32); ns = sc.shape[0]
+    if tr.properties is not None and np.size(tr.properties):
+        pr = np.asfortranarray(np.asarray(tr.properties, np.float32).reshape(-1, len(npts))); npr = pr.shape[0]
+    _lib.check(_lib.lib().fibers_trk_write_ex(outfile.encode(), _lib.ptr(vs), _lib.ptr(vr), _lib.ptr(M), int(len(npts)), _lib.ptr(npts), _lib.ptr(xyz),
+                                              ns, _lib.ptr(sc) if ns else None, npr, _lib.ptr(pr) if npr else None))
     return False
 
 
@@ -95,7 +102,7 @@ def draw_sublist(nsub: int, rng=None) -> np.ndarray:
 
 def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=None, len_min=3,
            len_max=None, ang_thresh=None, step_size=None, smooth_coeff=None, search_dist=15, search_ang=10, lcms=None,
-           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None) -> Tract:
+           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None, lcm_seed=0) -> Tract:
     """stream(ovec; odf, f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size,
     smooth_coeff, search_dist, search_ang, lcms, lcm_thresh, verbose) -- reference: src/stream.jl:730.
 
@@ -103,12 +110,11 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     ([nsub,3] float32; drawn like the reference draws them when omitted, with `rng` as the seed) and `device`."""
     ovecs = list(ovec) if isinstance(ovec, (list, tuple)) else [ovec]
     fs = None if f is None else (list(f) if isinstance(f, (list, tuple)) else [f])
-    if lcms is not None:
-        raise _lib.FibersCudaError(1, "stream: local connection matrices (lcms) are not on the GPU path")
     res = ovecs[0].header.get("volres") if isinstance(ovecs[0], MRI) else None
     domicro = res is not None and min(res) <= 0.05                   # microscopy regime (src/stream.jl:84)
     vols = []
     thrudim = None
+    ovec0_given = None
     for o in ovecs:
         v = np.asfortranarray(_vol(o), dtype=np.float32)
         if v.ndim == 3 or (v.ndim == 4 and v.shape[3] == 1):
@@ -132,6 +138,8 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
             v = vec
         if v.ndim != 4 or v.shape[3] != 3:
             raise _lib.FibersCudaError(1, "stream: orientation volumes must be [nx,ny,nz,3] vectors or [nx,ny,nz] angles")
+        if ovec0_given is None:
+            ovec0_given = v
         vols.append(v)
     nx, ny, nz = vols[0].shape[:3]
     if any(v.shape[:3] != (nx, ny, nz) for v in vols):
@@ -171,6 +179,17 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
         mcos = float(np.float32(np.cos(np.deg2rad(np.float64(np.float32(search_ang))))))   # cosd(T(search_ang)) (:306)
     cos_thresh = np.float32(np.cos(np.deg2rad(np.float64(np.float32(ang)))))    # cosd(T(ang_thresh))
 
+    if lcms is not None:
+        if domicro:
+            raise ValueError("stream: local connection matrices are only defined for the macroscopic regime")
+        lv = np.asfortranarray(_vol(lcms), dtype=np.float32)
+        if lv.shape != (nx, ny, nz, 10):
+            raise ValueError(f"stream: lcms must be [nx,ny,nz,10], got {lv.shape}")
+        # through-plane dimension = the component of the first orientation volume that is zero everywhere (:224-226)
+        thru = [d for d in range(3) if not np.any(ovec0_given[..., d])]
+        strdims = [d for d in range(3) if d not in thru]
+        if len(strdims) < 2:
+            raise IndexError("stream: the first orientation volume has fewer than two non-zero components (BoundsError in the reference, :230-231)")
     L = _lib.lib(); _lib.require_device()
     PP = C.c_void_p * nvec
     ov_ptrs = PP(*[v.ctypes.data for v in vols])
@@ -178,15 +197,27 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
     import time
     handle = C.c_void_p(); nstr = C.c_int64(); ntot = C.c_int64()
     t0 = time.perf_counter()
-    _lib.check(L.fibers_stream(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
-                               _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(cos_thresh),
-                               float(step), float(smooth), msd, mcos, int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
+    scal = None
+    if lcms is not None:
+        _lib.check(L.fibers_stream_lcm(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
+                                       _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(step), float(smooth),
+                                       _lib.ptr(lv), float(lcm_thresh), int(strdims[0]), int(strdims[1]), int(lcm_seed) & (2 ** 64 - 1),
+                                       int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
+    else:
+        _lib.check(L.fibers_stream(ov_ptrs, nvec, nx, ny, nz, f_ptrs, float(f_thresh), _lib.ptr(fav), float(fa_thresh), _lib.ptr(mk),
+                                   _lib.ptr(sd), _lib.ptr(sub), int(sub.shape[0]), int(len_min), int(len_max), float(cos_thresh),
+                                   float(step), float(smooth), msd, mcos, int(device), C.byref(handle), C.byref(nstr), C.byref(ntot)))
     t1 = time.perf_counter()
     try:
         npts = np.zeros(nstr.value, np.int32)
         xyz = np.zeros((3, ntot.value), np.float32, order="F")
         if handle.value:
             _lib.check(L.fibers_stream_fetch(handle, _lib.ptr(npts), _lib.ptr(xyz)))
+            if lcms is not None:
+                scal = np.zeros((1, ntot.value), np.float32, order="F")
+                _lib.check(L.fibers_stream_fetch_scalars(handle, _lib.ptr(scal)))
+        elif lcms is not None:
+            scal = np.zeros((1, 0), np.float32, order="F")
     finally:
         L.fibers_stream_free(handle)
     if timing is not None:                     # (bench aid) seconds in the tracking call and in the fetch of the points
@@ -199,4 +230,7 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
         M0 = np.asarray(href.header.get("vox2ras0", np.eye(4)), np.float32)
         ref = dict(volsize=[nx, ny, nz], vox2ras0=M0,
                    volres=href.header.get("volres", np.sqrt((M0[:3, :3].astype(np.float64) ** 2).sum(0)).tolist()))
-    return Tract(lines, npts, sub, ref)
+    tr = Tract(lines, npts, sub, ref)
+    if scal is not None:
+        tr.scalars = [scal[:, e - n:e] for e, n in zip(ends, npts)]
+    return tr

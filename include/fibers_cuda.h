@@ -181,7 +181,7 @@ int fibers_st_eigen_device(const float* d_sxx, const float* d_sxy, const float* 
 
 /* stream: src/stream.jl:730-790 (streamline tractography), the deterministic regime: orientation
  * VECTORS (ovec[i] = [nx,ny,nz,3] float32, i < nvec <= 8, e.g. the peak volumes of gqi_rec / dsi_rec or eigvec1 of dti_fit),
- * no local connection matrices; macroscopic voxels and the microscopy regime.  Replaces the StreamWork constructor's masking (:72-147), the
+ * no local connection matrices (those: fibers_stream_lcm below); macroscopic voxels and the microscopy regime.  Replaces the StreamWork constructor's masking (:72-147), the
  * `Threads.@threads` seed loop (:759-781) and stream_new_line / stream_new_point! / stream_pick_by_angle! (:621-690,
  * :497-541, :355-387).
  *   f        nvec volumes [nx,ny,nz] (vector amplitudes, e.g. qa1..3) or NULL; vectors with f < f_thresh are dropped (:136-138)
@@ -211,6 +211,25 @@ int fibers_stream_device(const float* const* d_ovec, int nvec, int nx, int ny, i
                          void** result, int64_t* nstr, int64_t* npts_total);
 int fibers_stream_fetch(void* result, int32_t* npts, float* xyz);
 void fibers_stream_free(void* result);
+
+/* stream(...; lcms, lcm_thresh): the branch that follows local connection matrices (src/stream.jl:208-236 set-up, :523-538
+ * stream_new_point!, :380-494 stream_pick_by_lcm!), macroscopic regime.  Every step first makes the conventional pick (for the
+ * method-difference flag), then, on entering a new voxel, zeroes the LCM elements that do not touch the entry edge, normalises
+ * them and draws one connection: rand(Categorical(lcm)) in the reference, on Julia's task-local generator (the answer depends on
+ * the thread schedule).  Here draw k of streamline l (reference order, before the len_min filter) is the counter-based uniform
+ * number  u = top 24 bits of splitmix64_finalise(lcm_seed + (l + 1) * 0x9E3779B97F4A7C15 + (k + 1) * 0xD1B54A32D192ED03) * 2^-24,
+ * and the connection is the first i with p[1] + ... + p[i] > u (Distributions' DiscreteNonParametric sampler).  No angle
+ * threshold is applied (:676).
+ *   lcms      [nx,ny,nz,10] float32 like lcms.vol; elements < lcm_thresh (compared in Float64, :220) count as 0
+ *   strdim1/2 the in-plane dimensions, 0-based: setdiff(1:3, thrudim) .- 1 with thrudim = the component of the FIRST orientation
+ *             volume that is zero everywhere (:224-226; the wrapper evaluates it, like cosd(ang_thresh) for the other branch)
+ * fibers_stream_fetch_scalars: one Float32 per point, in the order of fibers_stream_fetch's xyz: 1 where the LCM pick differed
+ * from the conventional one (the scalars str_add! receives, :783). */
+int fibers_stream_lcm(const float* const* ovec, int nvec, int nx, int ny, int nz, const float* const* f, float f_thresh,
+                      const float* fa, float fa_thresh, const uint8_t* mask, const uint8_t* seed, const float* sublist, int nsub,
+                      int len_min, int len_max, float step_size, float smooth_coeff, const float* lcms, double lcm_thresh,
+                      int strdim1, int strdim2, uint64_t lcm_seed, int device, void** result, int64_t* nstr, int64_t* npts_total);
+int fibers_stream_fetch_scalars(void* result, float* scalars);
 
 /* ---- volume I/O either side of the path: NIfTI-1 (.nii, .nii.gz) and MGH (.mgh, .mgz) ----------
  * fibers_mri_read_info   = load_nifti_hdr (src/mri.jl:1394-1551) / the header of load_mgh (:1217-1283) + what mri_read derives
@@ -253,6 +272,10 @@ int fibers_mri_write(const char* path, const void* vol, int dtype, const int32_t
  * src/mri.jl:471-500), no scalars / properties; points are stored as (xyz + .5) * voxel_size like the reference. */
 int fibers_trk_write(const char* path, const int32_t* volsize /*[3]*/, const float* volres /*[3]*/, const float* vox2ras /*[16]*/,
                      int64_t nstr, const int32_t* npts, const float* xyz /*[3, sum(npts)]*/);
+/* the same with n_scalars values per point (scalars [n_scalars, sum(npts)]) and n_properties per streamline (properties
+ * [n_properties, nstr]), unnamed like the Tract str_add! fills (src/trk.jl:166-260, write loop :470-490) */
+int fibers_trk_write_ex(const char* path, const int32_t* volsize, const float* volres, const float* vox2ras, int64_t nstr, const int32_t* npts,
+                        const float* xyz, int n_scalars, const float* scalars, int n_properties, const float* properties);
 
 /* trk_read (src/trk.jl:358-425): two calls, like the volume reader.  `info` = the header fields a caller of the reference's
  * Tract reads back + the total number of points (so that the caller can allocate); `data` fills npts [n_count], xyz

@@ -264,8 +264,9 @@ end
 """
     stream(ovec; f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size, smooth_coeff)
 
-GPU version of `Fibers.stream` (src/stream.jl:730-790) for orientation VECTORS without local connection matrices in
-the macroscopic regime.  The StreamWork constructor's masking, the seed loop and the propagation run in
+GPU version of `Fibers.stream` (src/stream.jl:730-790): macroscopic and microscopy regime, and (macroscopic) local
+connection matrices `lcms` (`fibers_stream_lcm`; the connection draws come from a counter-based generator seeded with
+`lcm_seed`, which this wrapper draws from Julia's RNG unless given).  The StreamWork constructor's masking, the seed loop and the propagation run in
 `fibers_stream`; this wrapper keeps the reference's defaults, draws the sub-voxel offsets exactly like StreamWork
 does (src/stream.jl:177-183) and assembles the `Tract`.
 """
@@ -275,8 +276,7 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
                 len_max::Integer=(isa(ovec,MRI) ? maximum(ovec.volsize) : maximum(ovec[1].volsize)),
                 ang_thresh::Union{Real,Nothing}=45, step_size::Union{Real,Nothing}=.5,
                 smooth_coeff::Union{Real,Nothing}=.2, search_dist::Integer=15, search_ang::Real=10,
-                lcms::Union{MRI,Nothing}=nothing)
-  isnothing(lcms) || error("stream: local connection matrices are not on the GPU path")
+                lcms::Union{MRI,Nothing}=nothing, lcm_thresh::Real=.099, lcm_seed::UInt64=rand(UInt64))
   ovecs = isa(ovec, MRI) ? MRI[ovec] : ovec
   fs    = isa(f, MRI) ? MRI[f] : f
   nx, ny, nz = size(ovecs[1].vol)[1:3]
@@ -312,6 +312,23 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
   m  = isnothing(mask) ? nothing : UInt8.(mask.vol[:,:,:,1] .> 0)
   sd = isnothing(seed) ? nothing : UInt8.(seed.vol[:,:,:,1] .> 0)
   handle = Ref{Ptr{Cvoid}}(C_NULL); nstr = Ref{Int64}(0); ntot = Ref{Int64}(0)
+  if !isnothing(lcms)
+    domicro && error("stream: local connection matrices are only defined for the macroscopic regime")
+    size(lcms.vol) == (nx, ny, nz, 10) || error("stream: lcms must be [nx ny nz 10]")
+    thrudim = findall(vec(all(x -> x==0, ovecs[1].vol, dims=(1,2,3))))   # src/stream.jl:224-226
+    strdims = setdiff(1:3, thrudim)
+    lv = Array{Float32,4}(lcms.vol)
+    GC.@preserve vols fvol begin
+      check(ccall((:fibers_stream_lcm, libfibers), Cint,
+                  (Ptr{Ptr{Float32}}, Cint, Cint, Cint, Cint, Ptr{Ptr{Float32}}, Cfloat, Ptr{Float32}, Cfloat, Ptr{UInt8}, Ptr{UInt8},
+                   Ptr{Float32}, Cint, Cint, Cint, Cfloat, Cfloat, Ptr{Float32}, Cdouble, Cint, Cint, UInt64, Cint,
+                   Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}),
+                  pointer.(vols), length(vols), nx, ny, nz, isnothing(fvol) ? C_NULL : pointer.(fvol), Float32(f_thresh),
+                  isnothing(favol) ? C_NULL : favol, Float32(fa_thresh), isnothing(m) ? C_NULL : m, isnothing(sd) ? C_NULL : sd,
+                  sub, size(sub, 2), len_min, len_max, Float32(step_size), Float32(smooth_coeff), lv, Float64(lcm_thresh),
+                  strdims[1]-1, strdims[2]-1, lcm_seed, 0, handle, nstr, ntot))
+    end
+  else
   GC.@preserve vols fvol begin
     check(ccall((:fibers_stream, libfibers), Cint,
                 (Ptr{Ptr{Float32}}, Cint, Cint, Cint, Cint, Ptr{Ptr{Float32}}, Cfloat, Ptr{Float32}, Cfloat, Ptr{UInt8}, Ptr{UInt8},
@@ -321,16 +338,22 @@ function stream(ovec::Union{MRI,Vector{MRI}}; f::Union{MRI,Vector{MRI},Nothing}=
                 sub, size(sub, 2), len_min, len_max, cosd(Float32(ang_thresh)), Float32(step_size), Float32(smooth_coeff),
                 domicro ? micro_search_dist : C_NULL, domicro ? cosd(Float32(search_ang)) : 0f0, 0, handle, nstr, ntot))
   end
-  npts = Vector{Int32}(undef, nstr[]); xyz = Matrix{Float32}(undef, 3, ntot[])
+  end
+  npts = Vector{Int32}(undef, nstr[]); xyz = Matrix{Float32}(undef, 3, ntot[]); flags = Vector{Float32}(undef, ntot[])
   try
     check(ccall((:fibers_stream_fetch, libfibers), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float32}), handle[], npts, xyz))
+    isnothing(lcms) || check(ccall((:fibers_stream_fetch_scalars, libfibers), Cint, (Ptr{Cvoid}, Ptr{Float32}), handle[], flags))
   finally
     ccall((:fibers_stream_free, libfibers), Cvoid, (Ptr{Cvoid},), handle[])
   end
   ends = cumsum(Int.(npts))
   str = [xyz[:, (ends[i]-npts[i]+1):ends[i]] for i in eachindex(npts)]
   tr = Tract{Float32}(isnothing(mask) ? ovecs[1] : mask)
-  str_add!(tr, str)                                               # src/stream.jl:785-787
+  if isnothing(lcms)
+    str_add!(tr, str)                                             # src/stream.jl:785-787
+  else
+    str_add!(tr, str, [flags[(ends[i]-npts[i]+1):ends[i]] for i in eachindex(npts)])   # the method-difference flags (:783)
+  end
   return tr
 end
 

@@ -268,3 +268,14 @@ def test_trk_read_layout_and_round_trip(tmp_path):
     assert t1.npts.tolist() == [5, 1, 7] and t1.header["n_scalars"] == 0 and t1.header["n_properties"] == 0
     for a, b in zip(out, t1.xyz):
         np.testing.assert_allclose(b, a, rtol=0, atol=2e-5)                # (x + .5) * vs / vs - .5: two roundings at |x| <= 60
+    # scalars per point (the method-difference flags of an LCM run) and a property per streamline survive the round trip
+    sc = [np.asfortranarray((rng.random((1, n)) < 0.5).astype(np.float32)) for n in (5, 1, 7)]
+    t2 = Tract(out, np.array([5, 1, 7], np.int32), None, dict(volsize=[40, 50, 60], volres=vs, vox2ras0=M), scalars=sc,
+               properties=np.array([[1.5, 2.5, 3.5]], np.float32))
+    assert trk_write(t2, str(tmp_path / "e.trk")) is False
+    raw = (tmp_path / "e.trk").read_bytes()
+    assert len(raw) == 1000 + 4 * (3 + 4 * 13 + 3) and struct.unpack_from("<h", raw, 36)[0] == 1 and struct.unpack_from("<h", raw, 238)[0] == 1
+    t3 = trk_read(str(tmp_path / "e.trk"))
+    for a, b in zip(sc, t3.scalars):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(t3.properties, np.array([[1.5, 2.5, 3.5]], np.float32))

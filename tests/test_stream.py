@@ -147,8 +147,10 @@ def test_stream_gpu_consumes_gqi_peaks():
 def test_stream_rejects_what_is_not_on_the_gpu_path():
     import fibers_jl_b200 as Fb
     v = straight_field((4, 4, 4))
-    with pytest.raises(Fb.FibersCudaError):
+    with pytest.raises(IndexError):                                 # one in-plane dimension only: BoundsError in the reference (:230-231)
         Fb.stream(Fb.MRI(v), lcms=Fb.MRI(np.zeros((4, 4, 4, 10), F)))
+    with pytest.raises(ValueError):                                 # LCMs are [nx,ny,nz,10]
+        Fb.stream(Fb.MRI(v), lcms=Fb.MRI(np.zeros((4, 4, 4, 9), F)))
     with pytest.raises(ValueError):
         Fb.stream(Fb.MRI(np.full((4, 4, 4), 100.0, F)))            # neither vectors nor angles in [-90, 90]
 
@@ -255,3 +257,107 @@ def test_stream_gpu_angle_input_micro():
     ref = SO.stream([vec], [np.zeros(3, F)], step_size=1.0, smooth_coeff=0.0, cosang_thresh=F(np.cos(np.deg2rad(np.float64(F(20))))),
                     micro_search_dist=(3, 3, 0), micro_search_cosang=F(np.cos(np.deg2rad(np.float64(F(30))))), len_max=30)
     assert got.n_count == len(ref) > 100 and all(np.array_equal(a, b) for a, b in zip(got.xyz, ref))
+
+
+def lcm_field(shape, nvec, seed):
+    """In-plane (x-y) orientation fields with holes + random local connection matrices with many sub-threshold elements."""
+    g = np.random.default_rng(seed)
+    nx, ny, nz = shape
+    xs, ys, zs = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    vols = []
+    for i in range(nvec):
+        ph = g.uniform(0, 2 * np.pi, 3)
+        th = 0.7 * np.sin(xs / 4.0 + ph[0]) + 0.6 * np.cos(ys / 3.0 + ph[1]) + 0.2 * np.sin(zs + ph[2]) + i * 1.3
+        v = np.stack([np.cos(th), np.sin(th), np.zeros_like(th)], axis=-1)
+        v[g.random(shape) < (0.04 + 0.08 * i)] = 0
+        vols.append(np.asfortranarray(v.astype(F)))
+    lcms = g.uniform(0, 1, shape + (10,)).astype(F)
+    lcms[g.random(shape + (10,)) < 0.3] = 0
+    lcms[g.random(shape) < 0.05] = 0                                  # voxels without any connection: the line ends there
+    return vols, np.asfortranarray(lcms)
+
+
+def test_oracle_lcm_known_answers():
+    """Hand-made cases of stream_pick_by_lcm! (src/stream.jl:380-494).  2-D field in the x-y plane, two vectors per voxel:
+    e1 = +x, e2 = +y.  A line running along +x enters every new voxel through its -x edge (entry edge type 3: dvox = now - next =
+    (-1, 0) is column 1 ... the reference names the edge by the jump that LEAVES through it, so dvox = (-1, 0) is type 1)."""
+    shape = (8, 8, 1)
+    a = np.zeros(shape + (3,), F); a[..., 0] = 1
+    a[7, 7, 0] = [0, 1, 0]                                            # (the reference finds the plane from the first volume: x and y must both occur)
+    b = np.zeros(shape + (3,), F); b[..., 1] = 1
+    m, arr = SO.stream_work([a, b])
+    # (i) only element (1, 3) is set: entry 1 -> exit 3 = jump (+1, 0): the line keeps to +x whatever is drawn; flags all False
+    l = np.zeros(shape + (10,), F); l[..., 2] = 1
+    L = SO.lcm_work(l, 0.099, a)
+    assert L[1] == [0, 1] and L[2][:, 0].tolist() == [-1, 0, 0] and L[2][:, 3].tolist() == [0, 1, 0]
+    s, fl = SO.new_line([2, 4, 1], np.zeros(3, F), m, arr, 100, F(0.7), 0.5, 0.0, None, (L, lambda: F(0.5)))
+    assert np.all(s[1] == 4) and s[0].max() == 8.0 and not fl.any()
+    # (ii) only element (1, 4) is set: entry 1 -> exit 4 = jump (0, +1): on entering the second voxel the line turns to +y
+    #      (the conventional pick would have kept +x: flag True at that point); the next voxel is entered through edge type 2
+    #      (dvox = (0, -1)), which element (1, 4) does not touch: the LCM is empty and the pass ends.  The backward pass starts
+    #      along the vector chosen LAST (+y, reversed), enters (2, 3) through edge 4, is sent to exit 1 (-x: flag True) and ends
+    #      at the next voxel (entry 3, no element).
+    l = np.zeros(shape + (10,), F); l[..., 3] = 1
+    L = SO.lcm_work(l, 0.099, a)
+    s, fl = SO.new_line([2, 4, 1], np.zeros(3, F), m, arr, 100, F(0.7), 0.5, 0.0, None, (L, lambda: F(0.5)))
+    np.testing.assert_array_equal(s, np.array([[3, 4, 1], [2.5, 4, 1], [2, 4, 1], [2, 4, 1], [2, 3.5, 1], [2, 3, 1]], F).T)
+    assert fl.tolist() == [False, True, False, False, True, False]
+    s_ii = s
+    # (iii) the draw decides between elements (1, 3) and (1, 4) with p = (.25, .75): u < .25 -> straight on, u >= .25 -> turn
+    l = np.zeros(shape + (10,), F); l[..., 2] = 1; l[..., 3] = 3
+    L = SO.lcm_work(l, 0.099, a)
+    s_lo, f_lo = SO.new_line([2, 4, 1], np.zeros(3, F), m, arr, 100, F(0.7), 0.5, 0.0, None, (L, lambda: F(0.2)))
+    s_hi, f_hi = SO.new_line([2, 4, 1], np.zeros(3, F), m, arr, 100, F(0.7), 0.5, 0.0, None, (L, lambda: F(0.25)))
+    assert np.all(s_lo[1] == 4) and s_lo[0].max() == 8.0 and s_lo[0].min() == 1.5 and not f_lo.any()
+    # (the turn of (ii); the backward pass gets one voxel further, because element (1, 3) serves entry 3 there)
+    assert np.array_equal(s_hi[:, :6], s_ii) and s_hi[:, 6].tolist() == [1.5, 3, 1] and f_hi.tolist() == [False, True, False, False, True, False, False]
+    # (iv) thresholding: an element below lcm_thresh is removed (compared in Float64: 0.099f0 < 0.099)
+    l = np.zeros(shape + (10,), F); l[..., 2] = F(0.099)
+    assert not SO.lcm_work(l, 0.099, a)[0].any()
+    assert SO.lcm_work(l, float(F(0.099)), a)[0].any()
+    # (v) the generator: reproducible, in [0, 1), different per line and per draw
+    u = [SO.lcm_uniform(3, ln, k) for ln in range(50) for k in range(20)]
+    assert min(u) >= 0 and max(u) < 1 and len(set(u)) > 990 and abs(float(np.mean(u)) - 0.5) < 0.05
+    assert SO.lcm_uniform(3, 7, 9) == SO.lcm_uniform(3, 7, 9)
+    assert SO.lcm_uniform(0, 0, 0) == F(_splitmix_top24(0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03) * 2.0 ** -24)
+
+
+def _splitmix_top24(z):
+    M = 2 ** 64 - 1
+    z &= M
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+    return (z ^ (z >> 31)) >> 40
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["xy_plane", "xz_plane_mask_seed"])
+def test_stream_gpu_lcm_bit_exact(case):
+    """fibers_stream_lcm against the oracle: same streamlines, same method-difference flags, same draws."""
+    import fibers_jl_b200 as Fb
+    shape = (24, 20, 3)
+    vols, lcms = lcm_field(shape, 2, seed=21)
+    kw, okw = {}, {}
+    if case == "xz_plane_mask_seed":                                  # through-plane = y: swap the axes of the volumes and of the vectors
+        vols = [np.asfortranarray(np.swapaxes(v, 1, 2)[..., [0, 2, 1]]) for v in vols]
+        lcms = np.asfortranarray(np.swapaxes(lcms, 1, 2))
+        shape = (24, 3, 20)
+        g = np.random.default_rng(4)
+        mask = np.asfortranarray((g.random(shape) < 0.92).astype(np.uint8))
+        seed = np.asfortranarray((g.random(shape) < 0.4).astype(np.uint8))
+        kw.update(mask=Fb.MRI(mask), seed=Fb.MRI(seed), smooth_coeff=0.0, lcm_thresh=0.3)
+        okw.update(mask=mask, seed=seed, smooth_coeff=0.0, lcm_thresh=0.3)
+    sub = Fb.draw_sublist(2, rng=9)
+    got = Fb.stream([Fb.MRI(v) for v in vols], lcms=Fb.MRI(lcms), lcm_seed=12345, sublist=sub, len_max=40, **kw)
+    ref, rfl = SO.stream(vols, list(sub), lcms=lcms, lcm_seed=12345, len_max=40, **okw)
+    assert got.n_count == len(ref) and got.n_count > 100
+    assert np.array_equal(got.npts, np.array([s.shape[1] for s in ref], np.int32))
+    nbad = sum(0 if np.array_equal(a, b) else 1 for a, b in zip(got.xyz, ref))
+    nflag = sum(0 if np.array_equal(a[0] != 0, b) else 1 for a, b in zip(got.scalars, rfl))
+    ndiff = int(sum(f.sum() for f in rfl))
+    print(f"[parity] stream lcm {case}: {got.n_count} streamlines, {int(got.npts.sum())} points, {ndiff} method-difference flags, "
+          f"mismatching lines {nbad}, mismatching flag rows {nflag}")
+    assert nbad == 0 and nflag == 0 and ndiff > 0
+    # another seed gives other lines (the draws matter)
+    other = Fb.stream([Fb.MRI(v) for v in vols], lcms=Fb.MRI(lcms), lcm_seed=999, sublist=sub, len_max=40, **kw)
+    assert other.n_count != got.n_count or any(not np.array_equal(a, b) for a, b in zip(other.xyz, got.xyz))
