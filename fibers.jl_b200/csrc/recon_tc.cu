@@ -1322,7 +1322,8 @@ int launch_recon_tc(Plan* p, const ReconArgs& a, cudaStream_t stream) {
         const int Mk = ps.plain ? 0 : ps.rows, Nhh = (ps.N1 + ps.N2) / 2;
         auto envi = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
         tp.nstage = std::max(2, std::min(NSTAGE, envi("FIBERS_TC_BSTAGES", 8)));
-        tp.tstage = std::max(2, std::min(TSTAGE, envi("FIBERS_TC_DSTAGES", 4))) & ~1;
+        // (plain passes -- DSI pdf rows -- keep no key tile in shared memory and are paced by the DWI feed: 8 stages there, - 4.4 % on cfg3)
+        tp.tstage = std::max(2, std::min(TSTAGE, envi("FIBERS_TC_DSTAGES", ps.plain ? 8 : 4))) & ~1;
         tp.obuf = std::max(0, std::min(2, envi("FIBERS_TC_OBUF", 0)));
         tp.l2pf = std::max(0, envi("FIBERS_TC_L2PF", 0));
         tp.abl = envi("FIBERS_TC_ABLATE", 0);

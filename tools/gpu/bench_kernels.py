@@ -93,6 +93,10 @@ if ONLY == "pitch":
         run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI and output pitch = nvox (the reference's own array layout)", dpitch=nv, opitch=nv)
         run_recon("gqi", (145, 174, 145), b2, g2, "tc", "cfg2, DWI pitch = nvox, cp.async staging (FIBERS_TC_NO_SPLIT_TMA)", dpitch=nv, env={"FIBERS_TC_NO_SPLIT_TMA": "1"})
     sys.exit(0)
+if ONLY == "dsi":
+    b3, g3 = phantom.dsi_grid_table()
+    run_recon("dsi", (96, 96, 60), b3, g3, "tc", "cfg3 96x96x60x515")
+    sys.exit(0)
 b1, g1 = phantom.shells_table(1, [(1000.0, 30)])
 run_dti((64, 64, 40), b1, g1, "cfg1 64x64x40x31")
 b2, g2 = bench.make_tables()
