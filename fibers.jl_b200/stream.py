@@ -102,12 +102,13 @@ def draw_sublist(nsub: int, rng=None) -> np.ndarray:
 
 def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mask=None, seed=None, nsub=None, len_min=3,
            len_max=None, ang_thresh=None, step_size=None, smooth_coeff=None, search_dist=15, search_ang=10, lcms=None,
-           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None, lcm_seed=0) -> Tract:
+           lcm_thresh=0.099, verbose=False, sublist=None, rng=None, device=0, timing=None, lcm_seed=None) -> Tract:
     """stream(ovec; odf, f, f_thresh, fa, fa_thresh, mask, seed, nsub, len_min, len_max, ang_thresh, step_size,
     smooth_coeff, search_dist, search_ang, lcms, lcm_thresh, verbose) -- reference: src/stream.jl:730.
 
     `ovec`: MRI or list of MRI, each [nx,ny,nz,3]; `f`: MRI or list of MRI [nx,ny,nz].  Extra keywords: `sublist`
-    ([nsub,3] float32; drawn like the reference draws them when omitted, with `rng` as the seed) and `device`."""
+    ([nsub,3] float32; drawn like the reference draws them when omitted, with `rng` as the seed), `lcm_seed` (seed of the
+    counter-based generator behind the LCM draws; drawn from `rng` when omitted) and `device`."""
     ovecs = list(ovec) if isinstance(ovec, (list, tuple)) else [ovec]
     fs = None if f is None else (list(f) if isinstance(f, (list, tuple)) else [f])
     res = ovecs[0].header.get("volres") if isinstance(ovecs[0], MRI) else None
@@ -190,6 +191,8 @@ def stream(ovec, *, odf=None, f=None, f_thresh=0.03, fa=None, fa_thresh=0.1, mas
         strdims = [d for d in range(3) if d not in thru]
         if len(strdims) < 2:
             raise IndexError("stream: the first orientation volume has fewer than two non-zero components (BoundsError in the reference, :230-231)")
+        if lcm_seed is None:                                         # the reference draws from Julia's RNG: a fresh seed per call unless one is given
+            lcm_seed = int(np.random.default_rng(rng).integers(0, 2 ** 63))
     L = _lib.lib(); _lib.require_device()
     PP = C.c_void_p * nvec
     ov_ptrs = PP(*[v.ctypes.data for v in vols])
