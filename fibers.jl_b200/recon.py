@@ -65,6 +65,42 @@ class RUMBASD:                 # reference: src/rusd.jl:11-20
     peak_idx: np.ndarray | None = None   # extra (test aid): 0-based vertex index or -1, [nx,ny,nz,5]
 
 
+def _write_fields(obj, basename: str, names) -> None:
+    """The loop shared by dti_write / gqi_write / dsi_write / rumba_write: MRI fields go to <basename>_<field>.nii.gz, vectors of
+    MRI to <basename>_<field><i>.nii.gz (i from 1), anything else (RUMBA-SD's SNR estimates) to <basename>_<field>.txt."""
+    from .io import mri_write
+    for name in names:
+        val = getattr(obj, name)
+        if isinstance(val, MRI):
+            mri_write(val, f"{basename}_{name}.nii.gz")
+        elif isinstance(val, (list, tuple)):
+            for i, m in enumerate(val):
+                mri_write(m, f"{basename}_{name}{i + 1}.nii.gz")
+        else:                                              # writedlm(fname, value, ' ')
+            with open(f"{basename}_{name}.txt", "w") as f:
+                f.write(" ".join(str(x) for x in np.atleast_1d(val).ravel()) + "\n")
+
+
+def dti_write(dti: "DTI", basename: str) -> None:
+    """dti_write(dti, basename) -- src/dti.jl:344-349: one NIfTI volume per field of the structure."""
+    _write_fields(dti, basename, ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "eigvec2", "eigvec3", "rd", "md", "fa"))
+
+
+def gqi_write(gqi: "GQI", basename: str) -> None:
+    """gqi_write(gqi, basename) -- src/gqi.jl:210-226."""
+    _write_fields(gqi, basename, ("odf", "peak", "qa"))
+
+
+def dsi_write(dsi: "DSI", basename: str) -> None:
+    """dsi_write(dsi, basename) -- src/dsi.jl:279-295."""
+    _write_fields(dsi, basename, ("pdf", "odf", "peak", "qa"))
+
+
+def rumba_write(rumba: "RUMBASD", basename: str) -> None:
+    """rumba_write(rumba, basename) -- src/rusd.jl:645-664 (the SNR estimates go to text files)."""
+    _write_fields(rumba, basename, ("fodf", "fgm", "fcsf", "peak", "gfa", "var", "snr_mean", "snr_std"))
+
+
 def _mask_u8(mask: MRI, shape):
     m = np.asarray(mask.vol)
     if m.ndim == 4 and m.shape[3] == 1:          # tutorial masks are [nx,ny,nz,1]

@@ -279,3 +279,30 @@ def test_trk_read_layout_and_round_trip(tmp_path):
     for a, b in zip(sc, t3.scalars):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(t3.properties, np.array([[1.5, 2.5, 3.5]], np.float32))
+
+
+def test_result_writers_file_names_and_content(tmp_path):
+    """dti_write / gqi_write / dsi_write / rumba_write (src/dti.jl:344, src/gqi.jl:210, src/dsi.jl:279, src/rusd.jl:645): one
+    <basename>_<field>[i].nii.gz per volume, RUMBA-SD's scalars as text; the volumes read back unchanged."""
+    rng = np.random.default_rng(2)
+    M = np.diag([2.0, 2.0, 2.0, 1.0]).astype(np.float32)
+
+    def vol(*shape):
+        return Fb.MRI(np.asfortranarray(rng.normal(size=shape).astype(np.float32)), header=dict(vox2ras0=M))
+    d = Fb.DTI(*(vol(3, 4, 2) for _ in range(4)), *(vol(3, 4, 2, 3) for _ in range(3)), *(vol(3, 4, 2) for _ in range(3)))
+    Fb.dti_write(d, str(tmp_path / "sub_dti"))
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted(f"sub_dti_{f}.nii.gz" for f in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "eigvec2", "eigvec3", "rd", "md", "fa"))
+    np.testing.assert_array_equal(fio.mri_read(str(tmp_path / "sub_dti_eigvec2.nii.gz")).vol, d.eigvec2.vol)
+    g = Fb.GQI(vol(3, 4, 2, 5), [vol(3, 4, 2, 3) for _ in range(3)], [vol(3, 4, 2) for _ in range(3)])
+    Fb.gqi_write(g, str(tmp_path / "g"))
+    assert sorted(p.name for p in tmp_path.glob("g_*")) == sorted(["g_odf.nii.gz"] + [f"g_{n}{i}.nii.gz" for n in ("peak", "qa") for i in (1, 2, 3)])
+    np.testing.assert_array_equal(fio.mri_read(str(tmp_path / "g_qa3.nii.gz")).vol.reshape(3, 4, 2), g.qa[2].vol)
+    s = Fb.DSI(vol(3, 4, 2, 7), vol(3, 4, 2, 5), [vol(3, 4, 2, 3) for _ in range(3)], [vol(3, 4, 2) for _ in range(3)])
+    Fb.dsi_write(s, str(tmp_path / "s"))
+    assert (tmp_path / "s_pdf.nii.gz").exists() and (tmp_path / "s_peak2.nii.gz").exists() and len(list(tmp_path.glob("s_*"))) == 8
+    r = Fb.RUMBASD(vol(3, 4, 2, 5), vol(3, 4, 2), vol(3, 4, 2), [vol(3, 4, 2, 3) for _ in range(5)], vol(3, 4, 2), vol(3, 4, 2),
+                   np.float32(21.5), np.float32(3.25))
+    Fb.rumba_write(r, str(tmp_path / "r"))
+    assert len(list(tmp_path.glob("r_peak*.nii.gz"))) == 5 and (tmp_path / "r_fodf.nii.gz").exists()
+    assert (tmp_path / "r_snr_mean.txt").read_text() == "21.5\n" and (tmp_path / "r_snr_std.txt").read_text() == "3.25\n"
