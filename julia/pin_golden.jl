@@ -1,0 +1,33 @@
+#=
+  pin_golden.jl -- pinning kit, step 2 of 3 (see tools/pin/export_inputs.py): runs the UNMODIFIED reference (Fibers.jl
+  dti_fit / adc_fit / gqi_rec / dsi_rec with their default arguments) on the inputs of this repository's golden
+  fixtures and writes its volumes with the reference's own *_write functions.  NOT RUN where this repository was built
+  (no Julia there): it exists so that anyone with Julia can pin the oracle against the real thing.
+
+      julia --project=<Fibers.jl checkout> julia/pin_golden.jl <inputs dir> <outputs dir>
+=#
+using Fibers, DelimitedFiles
+
+indir, outdir = ARGS[1], ARGS[2]
+mkpath(outdir)
+
+function load(name)
+  dwi  = mri_read(joinpath(indir, name * "_dwi.nii.gz"))
+  mask = mri_read(joinpath(indir, name * "_mask.nii.gz"))
+  dwi.bval = vec(readdlm(joinpath(indir, name * "_bval.txt"), Float32))     # assigned as they are: no re-normalisation
+  dwi.bvec = readdlm(joinpath(indir, name * "_bvec.txt"), Float32)
+  return dwi, mask
+end
+
+dwi, mask = load("dti_small")
+dti_write(dti_fit(dwi, mask), joinpath(outdir, "dti_small"))                # src/dti.jl:221, :344
+adc, s0 = adc_fit(dwi, mask)                                                # src/dti.jl:164
+mri_write(adc, joinpath(outdir, "dti_small_adc.nii.gz")); mri_write(s0, joinpath(outdir, "dti_small_adc_s0.nii.gz"))
+
+dwi, mask = load("gqi_small")
+gqi_write(gqi_rec(dwi, mask), joinpath(outdir, "gqi_small"))                # src/gqi.jl:109 (sphere_642, sigma = 1.25), :210
+
+dwi, mask = load("dsi_small")
+dsi_write(dsi_rec(dwi, mask), joinpath(outdir, "dsi_small"))                # src/dsi.jl:171 (sphere_642, hann_width = 32), :279
+
+println("reference outputs written to ", outdir)

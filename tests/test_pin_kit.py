@@ -1,0 +1,57 @@
+"""The pinning kit (tools/pin/*, julia/pin_golden.jl): anyone with Julia runs the real reference on the golden fixtures' inputs
+and compares its volumes with the oracle's.  Julia is not available here, so this test exercises the two Python ends: the exported
+inputs carry the fixtures bit for bit, and the checker accepts outputs equal to the oracle's and rejects perturbed ones."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import fibers_jl_b200 as Fb  # noqa: E402
+import fibers_oracle as O  # noqa: E402
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", "pin", name + ".py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_pin_kit_round_trip(tmp_path, capsys):
+    exp, chk = _load("export_inputs"), _load("check_outputs")
+    ind, outd = str(tmp_path / "in"), str(tmp_path / "out")
+    exp.main(ind)
+    os.makedirs(outd)
+    verts = np.asarray(O.load_sphere(642)[0][:321], np.float32)
+    for name in exp.FIXTURES:
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        # inputs: bit for bit, tables as float32 text that parses back exactly
+        assert np.array_equal(Fb.mri_read(os.path.join(ind, name + "_dwi.nii.gz")).vol, g["dwi"])
+        assert np.array_equal(np.loadtxt(os.path.join(ind, name + "_bval.txt"), dtype=np.float32), g["bval"])
+        assert np.array_equal(np.loadtxt(os.path.join(ind, name + "_bvec.txt"), dtype=np.float32).reshape(-1, 3), g["bvec"])
+        assert np.array_equal(Fb.mri_read(os.path.join(ind, name + "_mask.nii.gz")).vol.reshape(g["mask"].shape) > 0, g["mask"] > 0)
+
+        def put(field, arr):
+            Fb.mri_write(Fb.MRI(np.asfortranarray(np.asarray(arr, np.float32))), os.path.join(outd, f"{name}_{field}.nii.gz"))
+        if name == "dti_small":                              # what dti_write / mri_write of the reference would leave
+            for f in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "rd", "md", "fa", "adc", "adc_s0"):
+                put(f, g[f])
+        else:
+            put("odf", g["odf"])
+            if "pdf" in g.files:
+                put("pdf", g["pdf"])
+            for k in range(3):
+                idx = g["peak_idx"][..., k]
+                put(f"peak{k + 1}", np.where((idx >= 0)[..., None], verts[np.maximum(idx, 0)], 0))
+                put(f"qa{k + 1}", g["qa"][k])
+    assert chk.check(outd) == 0
+    assert "PINNED" in capsys.readouterr().out
+    # a reference that disagreed would be caught: 0.1 % on the GQI ODF, a swapped DSI peak
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gqi_small.npz"))
+    Fb.mri_write(Fb.MRI(np.asfortranarray((g["odf"] * 1.001).astype(np.float32))), os.path.join(outd, "gqi_small_odf.nii.gz"))
+    assert chk.check(outd) == 1
+    assert "NOT PINNED" in capsys.readouterr().out

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Pinning kit, step 3 of 3 (see export_inputs.py): compare the volumes the real reference wrote (julia/pin_golden.jl)
+with the float64 oracle's answers in tests/golden/*.npz, at the tolerances of the GPU parity tests (tests/parity.py):
+ODF / pdf within 1e-4 of the voxel's max, scalars within 1e-4 relative, principal eigenvector |dot| >= 0.9999 where the
+eigenvalues are separated, peak indices equal except where the float64 oracle itself cannot tell (margin <= 1e-5 of the
+voxel's max).  Exit code 0 = every check passed: the oracle is pinned on these fixtures."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import fibers_jl_b200 as Fb                    # noqa: E402
+import fibers_oracle as O                      # noqa: E402
+import parity as P                             # noqa: E402
+
+
+def vol(outdir, name):
+    return np.asarray(Fb.mri_read(os.path.join(outdir, name + ".nii.gz")).vol)
+
+
+def peak_indices(peaks, verts):
+    """[nx,ny,nz,3] vertex index of each written peak vector (-1 for the zero vector); the reference writes the vertex itself."""
+    nx, ny, nz = peaks[0].shape[:3]
+    idx = np.full((nx, ny, nz, 3), -1, np.int64)
+    for k, p in enumerate(peaks):
+        v = p.reshape(-1, 3, order="F").astype(np.float32)
+        nz_ = np.any(v != 0, axis=1)
+        d = ((v[nz_, None, :] - verts[None, :, :]) ** 2).sum(-1)
+        best = d.argmin(1)
+        assert np.all(d[np.arange(best.size), best] == 0), "a peak vector that is not a vertex of the sphere"
+        flat = np.full(v.shape[0], -1, np.int64); flat[nz_] = best
+        idx[..., k] = flat.reshape((nx, ny, nz), order="F")
+    return idx
+
+
+def check(outdir):
+    rows = []
+    ok_all = True
+
+    def row(name, value, limit, ok=None):
+        nonlocal ok_all
+        ok = (value <= limit) if ok is None else ok
+        ok_all &= bool(ok)
+        rows.append((name, value, limit, "ok" if ok else "FAIL"))
+    v642, f642 = O.load_sphere(642)
+    verts = np.asarray(v642[:321], np.float32)
+    nbr = O.neighbour_table(O.fold_faces(f642, 321), 321)
+    # ---- DTI / ADC ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dti_small.npz"))
+    valid = P.flat(g["valid"]); full = P.flat(g["kind"]) == 1; part = P.flat(g["kind"]) == 2
+    got = {n: vol(outdir, "dti_small_" + n) for n in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "rd", "md", "fa")}
+    row("dti: voxels the reference leaves at zero", float(np.count_nonzero(P.flat(got["s0"].reshape(g["s0"].shape))[~valid])), 0)
+    for n in ("s0", "eigval1", "md", "fa"):
+        row(f"dti {n} (full-sample voxels, relative)", P.rel_err(got[n].reshape(g[n].shape), g[n], full), P.SCALAR_TOL)
+    l1 = np.abs(P.flat(g["eigval1"]))[full]
+    for n in ("eigval2", "eigval3", "rd"):
+        d = np.abs(P.flat(got[n].reshape(g[n].shape))[full].astype(np.float64) - P.flat(g[n])[full]) / l1
+        row(f"dti {n} (relative to lambda1)", float(d.max()), P.SCALAR_TOL)
+    gap = (P.flat(g["eigval1"]) - P.flat(g["eigval2"]))[full] / l1
+    dots = np.abs((P.flat(got["eigvec1"], 3)[full].astype(np.float64) * P.flat(g["eigvec1"], 3)[full]).sum(1))
+    row("dti eigvec1: 1 - |dot| where lambda1 is separated", float(1 - dots[gap > 2e-2].min()), 1 - P.V1_DOT)
+    if part.any():
+        row("dti md / fa (partial-sample voxels, relative)", max(P.rel_err(got["md"].reshape(g["md"].shape), g["md"], part),
+                                                                  P.rel_err(got["fa"].reshape(g["fa"].shape), g["fa"], part)), 1e-3)
+    nzv = P.flat(g["adc"]) != 0
+    row("adc (relative)", P.rel_err(vol(outdir, "dti_small_adc").reshape(g["adc"].shape), g["adc"], nzv), P.SCALAR_TOL)
+    row("adc s0 (relative)", P.rel_err(vol(outdir, "dti_small_adc_s0").reshape(g["adc_s0"].shape), g["adc_s0"], nzv), P.SCALAR_TOL)
+    # ---- GQI / DSI ----
+    for name, has_pdf in (("gqi_small", False), ("dsi_small", True)):
+        g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        odf = vol(outdir, name + "_odf")
+        row(f"{name} odf (relative to the voxel's max)", P.odf_rel_err(odf, g["odf"].astype(np.float64)), P.ODF_TOL)
+        if has_pdf:
+            row(f"{name} pdf (relative to the voxel's max)", P.odf_rel_err(vol(outdir, name + "_pdf"), g["pdf"].astype(np.float64)), P.ODF_TOL)
+        idx = peak_indices([vol(outdir, f"{name}_peak{k}") for k in (1, 2, 3)], verts)
+        nmis, nun = P.peak_mismatch_report(idx, {"peak_idx": g["peak_idx"], "odf": g["odf"]}, nbr)
+        row(f"{name} peak indices: unexplained mismatches ({nmis} differ)", float(nun), 0)
+        qa = np.stack([vol(outdir, f"{name}_qa{k}").reshape(g["qa"].shape[1:]) for k in (1, 2, 3)])
+        same = P.flat(idx, 3) == P.flat(g["peak_idx"], 3)
+        d = np.abs(qa.astype(np.float64) - g["qa"]).reshape(3, -1, order="F").T[same]
+        row(f"{name} qa (absolute, where the peaks agree)", float(d.max()) if d.size else 0.0, 1e-4)
+    w = max(len(r[0]) for r in rows)
+    for n, v, lim, s in rows:
+        print(f"{n:{w}s}  {v:10.3e}  (limit {lim:.1e})  {s}")
+    print("PINNED: the reference's outputs agree with the oracle on the golden fixtures" if ok_all else "NOT PINNED: see the FAIL rows")
+    return 0 if ok_all else 1
+
+
+if __name__ == "__main__":
+    sys.exit(check(sys.argv[1] if len(sys.argv) > 1 else "pin_outputs"))
