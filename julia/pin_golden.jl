@@ -30,4 +30,10 @@ gqi_write(gqi_rec(dwi, mask), joinpath(outdir, "gqi_small"))                # sr
 dwi, mask = load("dsi_small")
 dsi_write(dsi_rec(dwi, mask), joinpath(outdir, "dsi_small"))                # src/dsi.jl:171 (sphere_642, hann_width = 32), :279
 
+# stream (src/stream.jl:730) without random sub-voxel offsets (nsub = 0): deterministic; the Tract goes out as .trk (src/trk.jl:433)
+ovec = [mri_read(joinpath(indir, "stream_small_ovec$i.nii.gz")) for i in 1:2]
+f    = [mri_read(joinpath(indir, "stream_small_f$i.nii.gz")) for i in 1:2]
+tr = stream(ovec; f=f, f_thresh=0.05, mask=mri_read(joinpath(indir, "stream_small_mask.nii.gz")), nsub=0)
+trk_write(tr, joinpath(outdir, "stream_small.trk"))
+
 println("reference outputs written to ", outdir)

@@ -48,6 +48,14 @@ def test_pin_kit_round_trip(tmp_path, capsys):
                 idx = g["peak_idx"][..., k]
                 put(f"peak{k + 1}", np.where((idx >= 0)[..., None], verts[np.maximum(idx, 0)], 0))
                 put(f"qa{k + 1}", g["qa"][k])
+    # the Tract of stream() as the reference's trk_write would leave it
+    from fibers_jl_b200.stream import Tract, trk_write
+    g = np.load(os.path.join(ROOT, "tests", "golden", "stream_small.npz"))
+    assert np.array_equal(Fb.mri_read(os.path.join(ind, "stream_small_ovec2.nii.gz")).vol, g["ovec"][1])
+    ends = np.cumsum(g["npts"])
+    lines = [np.asfortranarray(g["xyz"][:, e - n:e]) for e, n in zip(ends, g["npts"])]
+    M = np.diag([2.0, 2.0, 2.0, 1.0]).astype(np.float32)
+    trk_write(Tract(lines, g["npts"], None, dict(volsize=list(g["mask"].shape), volres=[2.0, 2.0, 2.0], vox2ras0=M)), os.path.join(outd, "stream_small.trk"))
     assert chk.check(outd) == 0
     assert "PINNED" in capsys.readouterr().out
     # a reference that disagreed would be caught: 0.1 % on the GQI ODF, a swapped DSI peak

@@ -361,3 +361,29 @@ def test_stream_gpu_lcm_bit_exact(case):
     # another seed gives other lines (the draws matter)
     other = Fb.stream([Fb.MRI(v) for v in vols], lcms=Fb.MRI(lcms), lcm_seed=999, sublist=sub, len_max=40, **kw)
     assert other.n_count != got.n_count or any(not np.array_equal(a, b) for a, b in zip(other.xyz, got.xyz))
+
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _golden_stream():
+    g = np.load(os.path.join(GOLD, "stream_small.npz"))
+    ends = np.cumsum(g["npts"])
+    return g, [g["xyz"][:, e - n:e] for e, n in zip(ends, g["npts"])]
+
+
+def test_oracle_reproduces_stream_fixture():
+    """tests/golden/stream_small.npz (tools/make_golden.py): the fixture the pinning kit hands to the real reference."""
+    g, want = _golden_stream()
+    got = SO.stream(list(g["ovec"]), [np.zeros(3, F)], f=list(g["f"]), f_thresh=float(g["f_thresh"]), mask=g["mask"])
+    assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+@pytest.mark.gpu
+def test_stream_gpu_matches_golden_fixture():
+    import fibers_jl_b200 as Fb
+    g, want = _golden_stream()
+    tr = Fb.stream([Fb.MRI(np.asfortranarray(v)) for v in g["ovec"]], f=[Fb.MRI(np.asfortranarray(x)) for x in g["f"]], f_thresh=float(g["f_thresh"]),
+                   mask=Fb.MRI(np.asfortranarray(g["mask"])), nsub=0)
+    assert tr.n_count == len(want) and np.array_equal(tr.npts, g["npts"])
+    assert all(np.array_equal(a, b) for a, b in zip(tr.xyz, want))

@@ -62,8 +62,33 @@ def main():
         isort, nvalid = O.find_peaks_literal(o, ff)
         exp.append([isort[k] if k < min(nvalid, 3) else -1 for k in range(3)] + [nvalid])
     np.savez_compressed(os.path.join(OUT, "peaks_kat.npz"), odf=cases, expected=np.asarray(exp, np.int32))
+    make_stream()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
+
+
+def make_stream():
+    """stream (src/stream.jl:730): two smooth orientation fields with holes, amplitudes, a mask; nsub = 0 (no random sub-voxel
+    offsets: the call is deterministic in the reference as well), otherwise the reference's defaults."""
+    import stream_oracle as SO
+    g = np.random.default_rng(104)
+    shape = (14, 12, 6)
+    xs, ys, zs = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    vols, fs = [], []
+    for i in range(2):
+        ph = g.uniform(0, 2 * np.pi, 6)
+        th = 0.6 * np.sin(xs / 5.0 + ph[0]) + 0.5 * np.cos(ys / 4.0 + ph[1]) + 0.3 * np.sin(zs / 3.0 + ph[2]) + i * 1.1
+        el = 0.5 * np.sin(xs / 6.0 + ph[3]) * np.cos(ys / 7.0 + ph[4]) + 0.2 * np.sin(zs / 2.5 + ph[5])
+        v = np.stack([np.cos(th) * np.cos(el), np.sin(th) * np.cos(el), np.sin(el)], axis=-1)
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        v[g.random(shape) < 0.05 + 0.1 * i] = 0
+        vols.append(v.astype(np.float32))
+        fs.append(g.uniform(0.0, 0.3, shape).astype(np.float32))
+    mask = (g.random(shape) < 0.9).astype(np.uint8)
+    lines = SO.stream(vols, [np.zeros(3, np.float32)], f=fs, f_thresh=0.05, mask=mask)
+    np.savez_compressed(os.path.join(OUT, "stream_small.npz"), ovec=np.stack(vols), f=np.stack(fs), mask=mask, f_thresh=np.float32(0.05),
+                        npts=np.array([s.shape[1] for s in lines], np.int32), xyz=np.concatenate(lines, axis=1).astype(np.float32))
+    print("stream_small:", len(lines), "streamlines,", sum(s.shape[1] for s in lines), "points")
 
 
 if __name__ == "__main__":

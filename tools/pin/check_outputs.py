@@ -81,6 +81,16 @@ def check(outdir):
         same = P.flat(idx, 3) == P.flat(g["peak_idx"], 3)
         d = np.abs(qa.astype(np.float64) - g["qa"]).reshape(3, -1, order="F").T[same]
         row(f"{name} qa (absolute, where the peaks agree)", float(d.max()) if d.size else 0.0, 1e-4)
+    # ---- stream: same lines in the same order; points up to the two roundings of the .trk round trip ((x + .5) * vs / vs - .5) ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "stream_small.npz"))
+    tr = Fb.trk_read(os.path.join(outdir, "stream_small.trk"))
+    same_counts = tr.n_count == g["npts"].shape[0] and np.array_equal(tr.npts, g["npts"])
+    row(f"stream_small: streamline and point counts ({tr.n_count} lines / {int(np.sum(tr.npts))} points against {g['npts'].shape[0]} / {int(g['npts'].sum())})",
+        0.0 if same_counts else 1.0, 0)
+    if same_counts:
+        # the reference keeps 1-based voxel coordinates in the Tract and writes (xyz + .5) * voxel_size: trk_read returns them as they were
+        got = np.concatenate(tr.xyz, axis=1) if tr.n_count else np.zeros((3, 0), np.float32)
+        row("stream_small: point coordinates (absolute, voxels)", float(np.abs(got.astype(np.float64) - g["xyz"]).max()) if got.size else 0.0, 2e-5)
     w = max(len(r[0]) for r in rows)
     for n, v, lim, s in rows:
         print(f"{n:{w}s}  {v:10.3e}  (limit {lim:.1e})  {s}")

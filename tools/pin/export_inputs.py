@@ -11,10 +11,11 @@ oracle restates the reference, and the golden fixtures are the oracle's own outp
 closes that gap with the three commands above: step 2 runs the unmodified reference on the fixtures' inputs, step 3
 compares its volumes with the oracle's (the same tolerances the GPU parity tests use).
 
-Per fixture: <name>_dwi.nii.gz (float32 [nx,ny,nz,nvol]), <name>_mask.nii.gz (float32 0 / 1), <name>_bval.txt (one value
+Per reconstruction fixture: <name>_dwi.nii.gz (float32 [nx,ny,nz,nvol]), <name>_mask.nii.gz (float32 0 / 1), <name>_bval.txt (one value
 per line), <name>_bvec.txt (three columns).  The tables are written with the shortest decimal that round-trips float32
 and under names `mri_read` does NOT pick up by itself (it would re-normalise the gradient vectors, src/mri.jl:705-712):
-the Julia script assigns them to `dwi.bval` / `dwi.bvec` as they are.
+the Julia script assigns them to `dwi.bval` / `dwi.bvec` as they are.  The tractography fixture is stream_small_ovec<i>.nii.gz,
+stream_small_f<i>.nii.gz and stream_small_mask.nii.gz.
 """
 import os
 import sys
@@ -41,6 +42,14 @@ def main(outdir):
         with open(os.path.join(outdir, name + "_bvec.txt"), "w") as f:
             f.write("".join(" ".join(str(np.float32(x)) for x in g) + "\n" for g in d["bvec"]))
         print(f"{name}: dwi {d['dwi'].shape}, {int(d['mask'].sum())} mask voxels, {d['bval'].shape[0]} volumes")
+    # stream (src/stream.jl:730): two orientation-vector volumes, their amplitudes, a mask; run with nsub = 0 (deterministic)
+    d = np.load(os.path.join(ROOT, "tests", "golden", "stream_small.npz"))
+    hdr = dict(vox2ras0=M, volres=[2.0, 2.0, 2.0])
+    for i in range(d["ovec"].shape[0]):
+        Fb.mri_write(Fb.MRI(np.asfortranarray(d["ovec"][i]), header=dict(hdr)), os.path.join(outdir, f"stream_small_ovec{i + 1}.nii.gz"))
+        Fb.mri_write(Fb.MRI(np.asfortranarray(d["f"][i]), header=dict(hdr)), os.path.join(outdir, f"stream_small_f{i + 1}.nii.gz"))
+    Fb.mri_write(Fb.MRI(np.asfortranarray(d["mask"].astype(np.float32)), header=dict(hdr)), os.path.join(outdir, "stream_small_mask.nii.gz"))
+    print(f"stream_small: {d['ovec'].shape[0]} orientation volumes {d['ovec'].shape[1:4]}, {int(d['mask'].sum())} mask voxels")
     print("inputs written to", outdir)
 
 
