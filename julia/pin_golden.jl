@@ -36,4 +36,10 @@ f    = [mri_read(joinpath(indir, "stream_small_f$i.nii.gz")) for i in 1:2]
 tr = stream(ovec; f=f, f_thresh=0.05, mask=mri_read(joinpath(indir, "stream_small_mask.nii.gz")), nsub=0)
 trk_write(tr, joinpath(outdir, "stream_small.trk"))
 
+# structure tensor (src/structens.jl:40-88), sigma = 1, rho = 2: eigenvalues as 3 frames, eigenvectors as 9 frames ([:, :, :, i, j] -> frame i + 3 (j - 1))
+v = mri_read(joinpath(indir, "structens_small_vol.nii.gz"))
+eigvec, eigval = st_recon(Float32.(v.vol[:, :, :, 1]), 1.0, 2.0)
+o = MRI(v, 3); o.vol = eigval;                                   mri_write(o, joinpath(outdir, "structens_small_eigval.nii.gz"))
+o = MRI(v, 9); o.vol = reshape(eigvec, size(eigvec)[1:3]..., 9); mri_write(o, joinpath(outdir, "structens_small_eigvec.nii.gz"))
+
 println("reference outputs written to ", outdir)

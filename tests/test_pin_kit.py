@@ -56,6 +56,11 @@ def test_pin_kit_round_trip(tmp_path, capsys):
     lines = [np.asfortranarray(g["xyz"][:, e - n:e]) for e, n in zip(ends, g["npts"])]
     M = np.diag([2.0, 2.0, 2.0, 1.0]).astype(np.float32)
     trk_write(Tract(lines, g["npts"], None, dict(volsize=list(g["mask"].shape), volres=[2.0, 2.0, 2.0], vox2ras0=M)), os.path.join(outd, "stream_small.trk"))
+    # st_recon: eigenvalues as 3 frames, eigenvectors as 9 frames
+    g = np.load(os.path.join(ROOT, "tests", "golden", "structens_small.npz"))
+    assert np.array_equal(Fb.mri_read(os.path.join(ind, "structens_small_vol.nii.gz")).vol.reshape(g["vol"].shape), g["vol"])
+    Fb.mri_write(Fb.MRI(np.asfortranarray(g["eigval"].astype(np.float32))), os.path.join(outd, "structens_small_eigval.nii.gz"))
+    Fb.mri_write(Fb.MRI(np.asfortranarray(g["eigvec"].reshape(g["vol"].shape + (9,), order="F"))), os.path.join(outd, "structens_small_eigvec.nii.gz"))
     assert chk.check(outd) == 0
     assert "PINNED" in capsys.readouterr().out
     # a reference that disagreed would be caught: 0.1 % on the GQI ODF, a swapped DSI peak

@@ -70,3 +70,31 @@ def test_st_eigen_and_recon_parity_on_the_gpu():
         assert strong.mean() > 0.3 and d[strong].min() > 0.9999, (sigma, rho, d[strong].min())
     with pytest.raises(TypeError):
         F.st_recon(vol.astype(np.float64), 1.0, 1.0)
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "structens_small.npz"))
+
+
+def test_oracle_reproduces_structens_fixture():
+    """tests/golden/structens_small.npz (tools/make_golden.py): the fixture the pinning kit hands to the real reference."""
+    g = _golden()
+    evec, evals = S.st_recon(g["vol"], float(g["sigma"]), float(g["rho"]))
+    assert np.array_equal(evals, g["eigval"]) and np.array_equal(evec.astype(np.float32), g["eigvec"])
+
+
+@pytest.mark.gpu
+def test_st_recon_gpu_matches_golden_fixture():
+    import fibers_jl_b200 as F
+    g = _golden()
+    evec, evals = F.st_recon(np.asfortranarray(g["vol"]), float(g["sigma"]), float(g["rho"]))
+    ww = g["eigval"]; wv = g["eigvec"].astype(np.float64)
+    sc = np.abs(ww).max()
+    loc = np.abs(ww).max(axis=-1, keepdims=True) + 1e-6 * sc
+    sep = (np.diff(ww, axis=-1).min(axis=-1, keepdims=True) / loc) > 1e-2
+    e = np.abs(evals - ww) / loc
+    assert e[np.broadcast_to(sep, e.shape)].max(initial=0) < 1e-4 and e.max() < 1e-3
+    strong = ((ww[..., 2] - ww[..., 1]) / (np.abs(ww[..., 2]) + 1e-30) > 0.2) & (ww[..., 2] > 1e-3 * sc)
+    d = np.abs(np.einsum("...i,...i->...", evec[..., :, 2].astype(np.float64), wv[..., :, 2]))
+    assert strong.mean() > 0.3 and d[strong].min() > 0.9999

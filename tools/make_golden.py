@@ -63,6 +63,7 @@ def main():
         exp.append([isort[k] if k < min(nvalid, 3) else -1 for k in range(3)] + [nvalid])
     np.savez_compressed(os.path.join(OUT, "peaks_kat.npz"), odf=cases, expected=np.asarray(exp, np.int32))
     make_stream()
+    make_structens()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
@@ -89,6 +90,23 @@ def make_stream():
     np.savez_compressed(os.path.join(OUT, "stream_small.npz"), ovec=np.stack(vols), f=np.stack(fs), mask=mask, f_thresh=np.float32(0.05),
                         npts=np.array([s.shape[1] for s in lines], np.int32), xyz=np.concatenate(lines, axis=1).astype(np.float32))
     print("stream_small:", len(lines), "streamlines,", sum(s.shape[1] for s in lines), "points")
+
+
+def make_structens():
+    """st_recon (src/structens.jl:40-88): two crossing families of planes + noise, sigma = 1, rho = 2."""
+    import structens_oracle as S
+    g = np.random.default_rng(105)
+    shape = (14, 12, 10)
+    x, y, z = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in shape], indexing="ij")
+
+    def planes(normal, period):
+        n = np.asarray(normal, np.float64); n /= np.linalg.norm(n)
+        return np.sin(2 * np.pi * (x * n[0] + y * n[1] + z * n[2]) / period)
+    vol = (planes((1.0, 0.3, 0.2), 6.0) + 0.5 * planes((-0.2, 1.0, 0.5), 9.0) + 0.05 * g.normal(size=shape)).astype(np.float32)
+    evec, evals = S.st_recon(vol, 1.0, 2.0)
+    np.savez_compressed(os.path.join(OUT, "structens_small.npz"), vol=vol, sigma=np.float64(1.0), rho=np.float64(2.0),
+                        eigvec=evec.astype(np.float32), eigval=evals.astype(np.float64))
+    print("structens_small:", vol.shape)
 
 
 if __name__ == "__main__":

@@ -91,6 +91,21 @@ def check(outdir):
         # the reference keeps 1-based voxel coordinates in the Tract and writes (xyz + .5) * voxel_size: trk_read returns them as they were
         got = np.concatenate(tr.xyz, axis=1) if tr.n_count else np.zeros((3, 0), np.float32)
         row("stream_small: point coordinates (absolute, voxels)", float(np.abs(got.astype(np.float64) - g["xyz"]).max()) if got.size else 0.0, 2e-5)
+    # ---- structure tensor: eigenvalues relative to the voxel's largest (1e-4 where the three are separated, 1e-3 anywhere:
+    #      the fp32 closed form is ill-conditioned for nearly equal pairs), principal vector up to sign where it is well defined ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "structens_small.npz"))
+    ww = g["eigval"]; wv = g["eigvec"].astype(np.float64)
+    ev = vol(outdir, "structens_small_eigval").astype(np.float64)
+    evec = vol(outdir, "structens_small_eigvec").reshape(ww.shape[:3] + (3, 3), order="F").astype(np.float64)
+    sc = np.abs(ww).max()
+    loc = np.abs(ww).max(axis=-1, keepdims=True) + 1e-6 * sc
+    sep = (np.diff(ww, axis=-1).min(axis=-1, keepdims=True) / loc) > 1e-2
+    err = np.abs(ev - ww) / loc
+    row("structens eigenvalues (separated voxels, relative to the largest)", float(err[np.broadcast_to(sep, err.shape)].max(initial=0)), 1e-4)
+    row("structens eigenvalues (all voxels)", float(err.max()), 1e-3)
+    strong = ((ww[..., 2] - ww[..., 1]) / (np.abs(ww[..., 2]) + 1e-30) > 0.2) & (ww[..., 2] > 1e-3 * sc)
+    dots = np.abs(np.einsum("...i,...i->...", evec[..., :, 2], wv[..., :, 2]))
+    row("structens principal eigenvector: 1 - |dot| where it is well defined", float(1 - dots[strong].min()), 1e-4)
     w = max(len(r[0]) for r in rows)
     for n, v, lim, s in rows:
         print(f"{n:{w}s}  {v:10.3e}  (limit {lim:.1e})  {s}")

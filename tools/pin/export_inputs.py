@@ -50,6 +50,10 @@ def main(outdir):
         Fb.mri_write(Fb.MRI(np.asfortranarray(d["f"][i]), header=dict(hdr)), os.path.join(outdir, f"stream_small_f{i + 1}.nii.gz"))
     Fb.mri_write(Fb.MRI(np.asfortranarray(d["mask"].astype(np.float32)), header=dict(hdr)), os.path.join(outdir, "stream_small_mask.nii.gz"))
     print(f"stream_small: {d['ovec'].shape[0]} orientation volumes {d['ovec'].shape[1:4]}, {int(d['mask'].sum())} mask voxels")
+    # structure tensor (src/structens.jl:40-88): one scalar volume; sigma = 1, rho = 2 in the Julia step
+    d = np.load(os.path.join(ROOT, "tests", "golden", "structens_small.npz"))
+    Fb.mri_write(Fb.MRI(np.asfortranarray(d["vol"]), header=dict(hdr)), os.path.join(outdir, "structens_small_vol.nii.gz"))
+    print(f"structens_small: volume {d['vol'].shape}")
     print("inputs written to", outdir)
 
 
