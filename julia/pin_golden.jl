@@ -1,6 +1,6 @@
 #=
   pin_golden.jl -- pinning kit, step 2 of 3 (see tools/pin/export_inputs.py): runs the UNMODIFIED reference (Fibers.jl
-  dti_fit / adc_fit / gqi_rec / dsi_rec with their default arguments) on the inputs of this repository's golden
+  dti_fit / adc_fit / gqi_rec / dsi_rec with their default arguments, rumba_rec, stream, st_recon) on the inputs of this repository's golden
   fixtures and writes its volumes with the reference's own *_write functions.  NOT RUN where this repository was built
   (no Julia there): it exists so that anyone with Julia can pin the oracle against the real thing.
 
@@ -29,6 +29,9 @@ gqi_write(gqi_rec(dwi, mask), joinpath(outdir, "gqi_small"))                # sr
 
 dwi, mask = load("dsi_small")
 dsi_write(dsi_rec(dwi, mask), joinpath(outdir, "dsi_small"))                # src/dsi.jl:171 (sphere_642, hann_width = 32), :279
+
+dwi, mask = load("rumba_small")
+rumba_write(rumba_rec(dwi, mask, sphere_362, 40), joinpath(outdir, "rumba_small"))   # src/rusd.jl:419 (40 iterations, other arguments default), :645
 
 # stream (src/stream.jl:730) without random sub-voxel offsets (nsub = 0): deterministic; the Tract goes out as .trk (src/trk.jl:433)
 ovec = [mri_read(joinpath(indir, "stream_small_ovec$i.nii.gz")) for i in 1:2]

@@ -37,7 +37,15 @@ def test_pin_kit_round_trip(tmp_path, capsys):
 
         def put(field, arr):
             Fb.mri_write(Fb.MRI(np.asfortranarray(np.asarray(arr, np.float32))), os.path.join(outd, f"{name}_{field}.nii.gz"))
-        if name == "dti_small":                              # what dti_write / mri_write of the reference would leave
+        if name == "rumba_small":                            # what rumba_write would leave (SNR estimates as text)
+            for f in ("fodf", "fgm", "fcsf", "gfa", "var"):
+                put(f, g[f])
+            for k in range(5):
+                put(f"peak{k + 1}", g["peak"][k])
+            for f in ("snr_mean", "snr_std"):
+                with open(os.path.join(outd, f"{name}_{f}.txt"), "w") as fh:
+                    fh.write(f"{np.float32(g[f])}\n")
+        elif name == "dti_small":                            # what dti_write / mri_write of the reference would leave
             for f in ("s0", "eigval1", "eigval2", "eigval3", "eigvec1", "rd", "md", "fa", "adc", "adc_s0"):
                 put(f, g[f])
         else:
@@ -68,3 +76,13 @@ def test_pin_kit_round_trip(tmp_path, capsys):
     Fb.mri_write(Fb.MRI(np.asfortranarray((g["odf"] * 1.001).astype(np.float32))), os.path.join(outd, "gqi_small_odf.nii.gz"))
     assert chk.check(outd) == 1
     assert "NOT PINNED" in capsys.readouterr().out
+
+
+def test_oracle_reproduces_rumba_fixture():
+    """tests/golden/rumba_small.npz (tools/make_golden.py): the fixture the pinning kit hands to the reference's rumba_rec."""
+    import rumba_oracle as R
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rumba_small.npz"))
+    v, _ = O.load_sphere(362)
+    r = R.rumba_rec(g["dwi"], g["mask"], g["bval"], g["bvec"], v, niter=int(g["niter"]), dtype=np.float64)
+    assert np.array_equal(r["fodf"].astype(np.float32), g["fodf"]) and np.array_equal(r["peak_idx"], g["peak_idx"])
+    assert r["snr_mean"] == float(g["snr_mean"]) and np.array_equal(r["gfa"], g["gfa"])

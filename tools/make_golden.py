@@ -64,6 +64,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "peaks_kat.npz"), odf=cases, expected=np.asarray(exp, np.int32))
     make_stream()
     make_structens()
+    make_rumba()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 
@@ -107,6 +108,19 @@ def make_structens():
     np.savez_compressed(os.path.join(OUT, "structens_small.npz"), vol=vol, sigma=np.float64(1.0), rho=np.float64(2.0),
                         eigvec=evec.astype(np.float32), eigval=evals.astype(np.float64))
     print("structens_small:", vol.shape)
+
+
+def make_rumba():
+    """rumba_rec (src/rusd.jl:419-636) on sphere_362 with 40 iterations (positional arguments 3 and 4), otherwise the defaults."""
+    import rumba_oracle as R
+    ph = phantom.gqi_phantom((6, 5, 4), nb0=3, shells=((2000.0, 45),), seed=106, mask_fill=0.8)
+    v, _ = O.load_sphere(362)
+    r = R.rumba_rec(ph["dwi"], ph["mask"], ph["bval"], ph["bvec"], v, niter=40, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "rumba_small.npz"), dwi=ph["dwi"], mask=ph["mask"], bval=ph["bval"], bvec=ph["bvec"],
+                        niter=np.int32(40), fodf=r["fodf"].astype(np.float32), fgm=r["fgm"], fcsf=r["fcsf"], gfa=r["gfa"], var=r["var"],
+                        snr_mean=np.float64(r["snr_mean"]), snr_std=np.float64(r["snr_std"]), peak_idx=r["peak_idx"],
+                        peak=np.stack(r["peak"]).astype(np.float32))
+    print("rumba_small:", ph["dwi"].shape, "snr", r["snr_mean"], r["snr_std"])
 
 
 if __name__ == "__main__":

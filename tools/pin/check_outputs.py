@@ -81,6 +81,35 @@ def check(outdir):
         same = P.flat(idx, 3) == P.flat(g["peak_idx"], 3)
         d = np.abs(qa.astype(np.float64) - g["qa"]).reshape(3, -1, order="F").T[same]
         row(f"{name} qa (absolute, where the peaks agree)", float(d.max()) if d.size else 0.0, 1e-4)
+    # ---- RUMBA-SD (tolerances of tests/test_gpu_rumba.py) ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rumba_small.npz"))
+    nvert = g["fodf"].shape[-1]
+    hv = np.asarray(O.load_sphere(362)[0][:nvert], np.float64)
+    row("rumba fodf (relative to the voxel's max)", P.odf_rel_err(vol(outdir, "rumba_small_fodf"), g["fodf"].astype(np.float64)), P.ODF_TOL)
+    for n in ("fgm", "fcsf", "gfa", "var"):
+        a = P.flat(vol(outdir, "rumba_small_" + n).reshape(g[n].shape)).astype(np.float64); r = P.flat(g[n]).astype(np.float64)
+        d = np.abs(a - r) / np.maximum(np.abs(r), 1e-3 if n in ("fgm", "fcsf") else 1e-30)
+        row(f"rumba {n} (relative)", float(max(d.max(), float(np.count_nonzero(a[r == 0])))), P.SCALAR_TOL)
+    for n, lim in (("snr_mean", 1e-4), ("snr_std", 1e-3)):
+        got = float(open(os.path.join(outdir, f"rumba_small_{n}.txt")).read().split()[0])
+        row(f"rumba {n} (relative)", abs(got - float(g[n])) / abs(float(g[n])), lim)
+    f64 = P.flat(g["fodf"], nvert).astype(np.float64)
+    ri = P.flat(g["peak_idx"], 5).astype(np.int64)
+    pk = [P.flat(vol(outdir, f"rumba_small_peak{k}"), 3).astype(np.float64) for k in range(1, 6)]
+    gi = np.full_like(ri, -1)
+    for k in range(5):                                   # a peak is amplitude x vertex: the vertex is the direction it points to
+        nzp = np.linalg.norm(pk[k], axis=1) > 0
+        gi[nzp, k] = np.argmax(pk[k][nzp] @ hv.T, axis=1)
+    unexplained = 0
+    for vx in np.nonzero((gi != ri).any(axis=1))[0]:
+        tol = 1e-5 * f64[vx].max()
+        a = [i for i in gi[vx] if i >= 0]; b = [i for i in ri[vx] if i >= 0]
+        va = np.sort(f64[vx][a])[::-1]; vb = np.sort(f64[vx][b])[::-1]
+        unexplained += not (len(a) == len(b) and np.all(np.abs(va - vb) <= tol))
+    row(f"rumba peak vertices: unexplained mismatches ({int((gi != ri).any(axis=1).sum())} differ)", float(unexplained), 0)
+    same = (gi == ri).all(axis=1)
+    perr = max(float(np.abs(pk[k] - P.flat(g["peak"][k], 3))[same].max(initial=0)) for k in range(5))
+    row("rumba peak vectors (absolute, where the vertices agree)", perr, 1e-4)
     # ---- stream: same lines in the same order; points up to the two roundings of the .trk round trip ((x + .5) * vs / vs - .5) ----
     g = np.load(os.path.join(ROOT, "tests", "golden", "stream_small.npz"))
     tr = Fb.trk_read(os.path.join(outdir, "stream_small.trk"))

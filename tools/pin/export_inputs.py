@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import fibers_jl_b200 as Fb                    # noqa: E402  (volume I/O is host code: no GPU needed)
 
-FIXTURES = ("dti_small", "gqi_small", "dsi_small")
+FIXTURES = ("dti_small", "gqi_small", "dsi_small", "rumba_small")
 
 
 def main(outdir):
